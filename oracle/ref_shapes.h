@@ -1,0 +1,395 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED. See ref_core.h.
+// Restates src/graphics/primitives/{triangle,plane,torus,aa_rect}.rs,
+// src/graphics/material.rs and the `roots` 0.0.4 quartic solver (Cargo.lock:81-84,
+// sources absent from the reference mount: restated from the crate's published
+// algorithm — discriminant test, depressed quartic, Ferrari resolvent cubic).
+#pragma once
+#include "ref_core.h"
+
+namespace ref {
+
+// ---------------------------------------------------------------- Material
+// material.rs:16-20 — only Diffuse and Emissive exist at this commit (finding F5)
+struct Material {
+  bool emissive;
+  Color3 color;      // Diffuse
+  Vec3 intensity;    // Emissive
+  static Material diffuse(Color3 c) { Material m; m.emissive = false; m.color = c; return m; }
+  static Material emit(Vec3 i) { Material m; m.emissive = true; m.intensity = i; return m; }
+};
+
+// ray.rs:46-63 — Hit::new normalises the normal (again)
+struct Hit {
+  float distance;
+  Vec3 normal;
+  Material mat;
+  bool is_entering;
+  Hit() {}
+  Hit(float d, Vec3 n, const Material& m, bool e) : distance(d), normal(normalize(n)), mat(m), is_entering(e) {}
+};
+
+// ---------------------------------------------------------------- roots 0.0.4 (restated)
+struct Roots {
+  int n = 0;
+  double v[4];
+  // roots: Roots::add_new_root keeps the set sorted ascending and drops exact duplicates
+  void add(double x) {
+    for (int i = 0; i < n; i++) if (v[i] == x) return;
+    if (n == 4) return;
+    int i = n;
+    while (i > 0 && v[i - 1] > x) { v[i] = v[i - 1]; i--; }
+    v[i] = x;
+    n++;
+  }
+};
+static inline Roots roots_quadratic_normalized(double a1, double a0) {
+  Roots r;
+  double disc = a1 * a1 - 4.0 * a0;
+  if (disc < 0.0) return r;
+  double a1_div_2 = a1 / 2.0;
+  if (disc == 0.0) { r.add(-a1_div_2); return r; }
+  double sq = std::sqrt(disc);
+  r.add(-a1_div_2 - sq / 2.0);
+  r.add(-a1_div_2 + sq / 2.0);
+  return r;
+}
+static inline Roots roots_quadratic(double a2, double a1, double a0) {
+  Roots r;
+  if (a2 == 0.0) { if (a1 != 0.0) r.add(-a0 / a1); return r; }
+  double disc = a1 * a1 - 4.0 * a2 * a0;
+  if (disc < 0.0) return r;
+  double a2x2 = 2.0 * a2;
+  if (disc == 0.0) { r.add(-a1 / a2x2); return r; }
+  double sq = std::sqrt(disc);
+  r.add((-a1 - sq) / a2x2);
+  r.add((-a1 + sq) / a2x2);
+  return r;
+}
+static inline Roots roots_cubic_normalized(double a2, double a1, double a0) {
+  Roots out;
+  double q = (3.0 * a1 - a2 * a2) / 9.0;
+  double r = (9.0 * a2 * a1 - 27.0 * a0 - 2.0 * a2 * a2 * a2) / 54.0;
+  double q3 = q * q * q;
+  double d = q3 + r * r;
+  double a2_div_3 = a2 / 3.0;
+  if (d < 0.0) {
+    double phi_3 = std::acos(r / std::sqrt(-q3)) / 3.0;
+    double sqrt_q_2 = 2.0 * std::sqrt(-q);
+    const double two_third_pi = 2.0943951023931954923;
+    out.add(sqrt_q_2 * std::cos(phi_3) - a2_div_3);
+    out.add(sqrt_q_2 * std::cos(phi_3 - two_third_pi) - a2_div_3);
+    out.add(sqrt_q_2 * std::cos(phi_3 + two_third_pi) - a2_div_3);
+  } else {
+    double sqrt_d = std::sqrt(d);
+    double s = std::cbrt(r + sqrt_d);
+    double t = std::cbrt(r - sqrt_d);
+    out.add(s + t - a2_div_3);
+    if (s == t && s + t != 0.0) out.add(-(s + t) / 2.0 - a2_div_3);
+  }
+  return out;
+}
+static inline Roots roots_cubic(double a3, double a2, double a1, double a0) {
+  if (a3 == 0.0) return roots_quadratic(a2, a1, a0);
+  if (a2 == 0.0 && a1 == 0.0 && a0 == 0.0) { Roots r; r.add(0.0); return r; }
+  return roots_cubic_normalized(a2 / a3, a1 / a3, a0 / a3);
+}
+static inline Roots roots_biquadratic(double a4, double a2, double a0) {
+  Roots out;
+  Roots q = roots_quadratic(a4, a2, a0);
+  for (int i = 0; i < q.n; i++) {
+    double x = q.v[i];
+    if (x > 0.0) { double s = std::sqrt(x); out.add(-s); out.add(s); }
+    else if (x == 0.0) out.add(0.0);
+  }
+  return out;
+}
+static inline Roots roots_quartic_depressed(double a2, double a1, double a0) {
+  if (a1 == 0.0) return roots_biquadratic(1.0, a2, a0);
+  if (a0 == 0.0) { Roots r = roots_cubic_normalized(0.0, a2, a1); r.add(0.0); return r; }
+  double a2_pow_2 = a2 * a2;
+  double a1_div_2 = a1 / 2.0;
+  double b2 = a2 * 5.0 / 2.0;
+  double b1 = 2.0 * a2_pow_2 - a0;
+  double b0 = (a2_pow_2 * a2 - a2 * a0 - a1_div_2 * a1_div_2) / 2.0;
+  Roots res = roots_cubic_normalized(b2, b1, b0);
+  double y = res.v[res.n - 1];          // the largest resolvent root
+  double a2_plus_2y = a2 + 2.0 * y;
+  Roots out;
+  if (a2_plus_2y > 0.0) {
+    double s = std::sqrt(a2_plus_2y);
+    double q0a = a2 + y - a1_div_2 / s;
+    double q0b = a2 + y + a1_div_2 / s;
+    Roots ra = roots_quadratic_normalized(s, q0a);
+    Roots rb = roots_quadratic_normalized(-s, q0b);
+    for (int i = 0; i < ra.n; i++) out.add(ra.v[i]);
+    for (int i = 0; i < rb.n; i++) out.add(rb.v[i]);
+  }
+  return out;
+}
+static inline Roots roots_quartic(double a4, double a3, double a2, double a1, double a0) {
+  if (a4 == 0.0) return roots_cubic(a3, a2, a1, a0);
+  if (a0 == 0.0) { Roots r = roots_cubic(a4, a3, a2, a1); r.add(0.0); return r; }
+  if (a1 == 0.0 && a3 == 0.0) return roots_biquadratic(a4, a2, a0);
+  double discriminant =
+      a4 * a0 * a4 * (256.0 * a4 * a0 * a0 + a1 * (144.0 * a2 * a1 - 192.0 * a3 * a0)) +
+      a4 * a0 * a2 * a2 * (16.0 * a2 * a2 - 80.0 * a3 * a1 - 128.0 * a4 * a0) +
+      (a3 * a3 * (a4 * a0 * (144.0 * a2 * a0 - 6.0 * a1 * a1) +
+                  (a0 * (18.0 * a3 * a2 * a1 - 27.0 * a3 * a3 * a0 - 4.0 * a2 * a2 * a2) +
+                   a1 * a1 * (a2 * a2 - 4.0 * a3 * a1)))) +
+      a4 * a1 * a1 * (18.0 * a3 * a2 * a1 - 27.0 * a4 * a1 * a1 - 4.0 * a2 * a2 * a2);
+  double pp = 8.0 * a4 * a2 - 3.0 * a3 * a3;
+  double rr = a3 * a3 * a3 + 8.0 * a4 * a4 * a1 - 4.0 * a4 * a3 * a2;
+  double delta0 = a2 * a2 - 3.0 * a3 * a1 + 12.0 * a4 * a0;
+  double dd = 64.0 * a4 * a4 * a4 * a0 - 16.0 * a4 * a4 * a2 * a2 + 16.0 * a4 * a3 * a3 * a2 -
+              16.0 * a4 * a4 * a3 * a1 - 3.0 * a3 * a3 * a3 * a3;
+  Roots out;
+  if (discriminant == 0.0) {
+    bool triple = delta0 == 0.0;
+    bool quadruple = triple && dd == 0.0;
+    bool no_roots = dd == 0.0 && pp > 0.0 && rr == 0.0;
+    if (quadruple) { out.add(-a3 / (4.0 * a4)); return out; }
+    if (triple) {
+      double x0 = (-72.0 * a4 * a4 * a0 + 10.0 * a4 * a2 * a2 - 3.0 * a3 * a3 * a2) /
+                  (9.0 * (8.0 * a4 * a4 * a1 - 4.0 * a4 * a3 * a2 + a3 * a3 * a3));
+      out.add(x0);
+      out.add(-(a3 / a4 + 3.0 * x0));
+      return out;
+    }
+    if (no_roots) return out;
+  } else {
+    if (discriminant > 0.0 && (pp > 0.0 || dd > 0.0)) return out;
+  }
+  double a4_pow_2 = a4 * a4, a4_pow_3 = a4_pow_2 * a4, a4_pow_4 = a4_pow_2 * a4_pow_2;
+  double p = pp / (8.0 * a4_pow_2);
+  double q = rr / (8.0 * a4_pow_3);
+  double r = (dd + 16.0 * a4_pow_2 * (12.0 * a0 * a4 - 3.0 * a1 * a3 + a2 * a2)) / (256.0 * a4_pow_4);
+  Roots dep = roots_quartic_depressed(p, q, r);
+  for (int i = 0; i < dep.n; i++) out.add(dep.v[i] - a3 / (4.0 * a4));
+  return out;
+}
+
+// ---------------------------------------------------------------- Shape
+// The reference uses Rc<dyn Tracable>; a tagged struct is the same thing flattened.
+enum ShapeType : int { SH_TRIANGLE = 0, SH_PLANE = 1, SH_TORUS = 2, SH_AARECT = 3 };
+
+struct Shape {
+  ShapeType type;
+  Material mat;
+  Vec3 v0, v1, v2;          // triangle
+  Vec3 location, normal;    // plane (location, normal) / torus (location)
+  float big_r, small_r;     // torus
+  float x_min, x_max, y_min, y_max, z_min, z_max;   // aa_rect (note: min/max interleaved, aa_rect.rs:8-16)
+  int source_index = -1;    // position in the scene's original shape list (debug / tests)
+
+  static Shape triangle(Vec3 a, Vec3 b, Vec3 c, Material m) {
+    Shape s{}; s.type = SH_TRIANGLE; s.v0 = a; s.v1 = b; s.v2 = c; s.mat = m; return s;
+  }
+  static Shape plane(Vec3 loc, Vec3 n, Material m) {
+    Shape s{}; s.type = SH_PLANE; s.location = loc; s.normal = n; s.mat = m; return s;
+  }
+  static Shape torus(Vec3 loc, float R, float r, Material m) {
+    Shape s{}; s.type = SH_TORUS; s.location = loc; s.big_r = R; s.small_r = r; s.mat = m; return s;
+  }
+  static Shape aarect(float x0, float x1, float y0, float y1, float z0, float z1, Material m) {
+    Shape s{}; s.type = SH_AARECT; s.x_min = x0; s.x_max = x1; s.y_min = y0; s.y_max = y1; s.z_min = z0; s.z_max = z1; s.mat = m; return s;
+  }
+
+  bool is_emissive() const { return mat.emissive; }
+
+  // Bounded::aabb — false for infinite shapes (plane.rs:33-36)
+  bool aabb(AABB* out) const {
+    switch (type) {
+      case SH_TRIANGLE: {   // triangle.rs:48-66
+        float xmn = fmin_(fmin_(v0.x, v1.x), v2.x), ymn = fmin_(fmin_(v0.y, v1.y), v2.y), zmn = fmin_(fmin_(v0.z, v1.z), v2.z);
+        float xmx = fmax_(fmax_(v0.x, v1.x), v2.x), ymx = fmax_(fmax_(v0.y, v1.y), v2.y), zmx = fmax_(fmax_(v0.z, v1.z), v2.z);
+        float pad = 0.1f * EPSILON;
+        *out = AABB(xmn - pad, ymn - pad, zmn - pad, xmx + pad, ymx + pad, zmx + pad);
+        return true;
+      }
+      case SH_TORUS: {      // torus.rs:33-52
+        float r = big_r + small_r;
+        *out = AABB(location.x - r, location.y - small_r, location.z - r, location.x + r, location.y + small_r, location.z + r);
+        return true;
+      }
+      case SH_AARECT:       // aa_rect.rs:57-67
+        *out = AABB(x_min, y_min, z_min, x_max, y_max, z_max);
+        return true;
+      default: return false;
+    }
+  }
+  // Bounded::location (ray.rs:77-83 default = AABB centre; torus.rs:28-30; aa_rect.rs:48-54)
+  bool centroid(Vec3* out) const {
+    switch (type) {
+      case SH_TRIANGLE: { AABB b; aabb(&b); *out = b.center(); return true; }
+      case SH_TORUS: *out = location; return true;
+      case SH_AARECT: *out = Vec3(0.5f * (x_min + x_max), 0.5f * (y_min + y_max), 0.5f * (z_min + z_max)); return true;
+      default: return false;
+    }
+  }
+
+  // triangle.rs:70-87 (Heron, evaluated on every call in the reference)
+  float surface_area() const {
+    if (type != SH_TRIANGLE) throw std::runtime_error("Not implemented");
+    float a = dis(v0, v1), b = dis(v1, v2), c = dis(v2, v0);
+    float s = (a + b + c) * 0.5f;
+    return std::sqrt(s * (s - a) * (s - b) * (s - c));
+  }
+  // triangle.rs:91-114 — returns (point, normal, intensity); quirk q2: random normal flip
+  void pick_random(Rng& rng, Vec3* p, Vec3* n_out, Vec3* intensity) const {
+    if (type != SH_TRIANGLE) throw std::runtime_error("Not implemented");
+    float r1 = rng.next();
+    float r2 = rng.next();
+    float r1_sqrt = std::sqrt(r1);
+    Vec3 p_hit = (1.0f - r1_sqrt) * v0 + (r1_sqrt * (1.0f - r2)) * v1 + (r2 * r1_sqrt) * v2;
+    Vec3 n = normalize(cross(v1 - v0, v2 - v0));
+    if (rng.next() > 0.5f) n = -n;
+    if (mat.emissive) { *p = p_hit; *n_out = n; *intensity = mat.intensity; }
+    else { *p = Vec3(); *n_out = Vec3(); *intensity = Vec3(); }
+  }
+
+  static bool is_approx_left_of(Vec3 a, Vec3 b, Vec3 n, Vec3 p) {   // triangle.rs:41-45
+    Vec3 edge = b - a;
+    Vec3 ap = p - a;
+    return dot(n, cross(edge, ap)) + 0.1f * EPSILON >= 0.0f;
+  }
+
+  // Tracable::trace_simple
+  bool trace_simple(const Ray& ray, float* t_out) const {
+    switch (type) {
+      case SH_TRIANGLE: {   // triangle.rs:159-191
+        Vec3 n = cross(v1 - v0, v2 - v0);
+        float n_dot_d = dot(n, ray.dir);
+        if (n_dot_d == 0.0f) return false;
+        float orig_dis = dot(n, v0);
+        float t = (orig_dis - dot(n, ray.origin)) / n_dot_d;
+        if (t <= 0.0f) return false;
+        n = normalize(n);
+        Vec3 p = ray.at(t);
+        if (is_approx_left_of(v0, v1, n, p) && is_approx_left_of(v1, v2, n, p) && is_approx_left_of(v2, v0, n, p)) { *t_out = t; return true; }
+        return false;
+      }
+      case SH_PLANE: {      // plane.rs:80-99
+        float n_dot_dir = dot(normal, ray.dir);
+        if (n_dot_dir == 0.0f) return false;
+        float o_distance = dot(normal, location);
+        float t = (o_distance - dot(normal, ray.origin)) / n_dot_dir;
+        if (t <= 0.0f) return false;
+        *t_out = t;
+        return true;
+      }
+      case SH_AARECT: {     // aa_rect.rs:142-174 (own 1/dir, strict tmin >= tmax, strict > 0)
+        float invdx = 1.0f / ray.dir.x, invdy = 1.0f / ray.dir.y, invdz = 1.0f / ray.dir.z;
+        float tx1 = (x_min - ray.origin.x) * invdx, tx2 = (x_max - ray.origin.x) * invdx;
+        float ty1 = (y_min - ray.origin.y) * invdy, ty2 = (y_max - ray.origin.y) * invdy;
+        float tz1 = (z_min - ray.origin.z) * invdz, tz2 = (z_max - ray.origin.z) * invdz;
+        float tmin = fmax_(fmax_(fmin_(tx1, tx2), fmin_(ty1, ty2)), fmin_(tz1, tz2));
+        float tmax = fmin_(fmin_(fmax_(tx1, tx2), fmax_(ty1, ty2)), fmax_(tz1, tz2));
+        if (tmin >= tmax) return false;
+        if (tmin > 0.0f) { *t_out = tmin; return true; }
+        if (tmax > 0.0f) { *t_out = tmax; return true; }
+        return false;
+      }
+      case SH_TORUS: {      // ray.rs:110-116 default: trace().distance
+        Hit h;
+        if (!trace(ray, &h)) return false;
+        *t_out = h.distance;
+        return true;
+      }
+    }
+    return false;
+  }
+
+  // Tracable::trace
+  bool trace(const Ray& ray, Hit* out) const {
+    switch (type) {
+      case SH_TRIANGLE: {   // triangle.rs:116-157
+        Vec3 n = cross(v1 - v0, v2 - v0);
+        float n_dot_d = dot(n, ray.dir);
+        if (n_dot_d == 0.0f) return false;
+        float orig_dis = dot(n, v0);
+        float t = (orig_dis - dot(n, ray.origin)) / n_dot_d;
+        if (t <= 0.0f) return false;
+        n = normalize(n);
+        Vec3 p = ray.at(t);
+        if (is_approx_left_of(v0, v1, n, p) && is_approx_left_of(v1, v2, n, p) && is_approx_left_of(v2, v0, n, p)) {
+          if (n_dot_d > 0.0f) *out = Hit(t, -n, mat, false);
+          else *out = Hit(t, n, mat, true);
+          return true;
+        }
+        return false;
+      }
+      case SH_PLANE: {      // plane.rs:45-77
+        Vec3 nrm = normal;
+        float n_dot_dir = dot(nrm, ray.dir);
+        if (n_dot_dir == 0.0f) return false;
+        float o_distance = dot(nrm, location);
+        float t = (o_distance - dot(nrm, ray.origin)) / n_dot_dir;
+        if (t <= 0.0f) return false;
+        if (n_dot_dir > 0.0f) nrm = -nrm;
+        *out = Hit(t, nrm, mat, true);
+        return true;
+      }
+      case SH_AARECT: {     // aa_rect.rs:71-139 — face normal by float equality
+        float invdx = 1.0f / ray.dir.x, invdy = 1.0f / ray.dir.y, invdz = 1.0f / ray.dir.z;
+        float tx1 = (x_min - ray.origin.x) * invdx, tx2 = (x_max - ray.origin.x) * invdx;
+        float ty1 = (y_min - ray.origin.y) * invdy, ty2 = (y_max - ray.origin.y) * invdy;
+        float tz1 = (z_min - ray.origin.z) * invdz, tz2 = (z_max - ray.origin.z) * invdz;
+        float tmin = fmax_(fmax_(fmin_(tx1, tx2), fmin_(ty1, ty2)), fmin_(tz1, tz2));
+        float tmax = fmin_(fmin_(fmax_(tx1, tx2), fmax_(ty1, ty2)), fmax_(tz1, tz2));
+        if (tmin >= tmax) return false;
+        if (tmin > 0.0f) {
+          Vec3 nn;
+          if (tmin == tx1) nn = Vec3(-1, 0, 0);
+          else if (tmin == tx2) nn = Vec3(1, 0, 0);
+          else if (tmin == ty1) nn = Vec3(0, -1, 0);
+          else if (tmin == ty2) nn = Vec3(0, 1, 0);
+          else if (tmin == tz1) nn = Vec3(0, 0, -1);
+          else nn = Vec3(0, 0, 1);
+          *out = Hit(tmin, nn, mat, true);
+          return true;
+        }
+        if (tmax > 0.0f) {
+          Vec3 nn;
+          if (tmax == tx1) nn = Vec3(1, 0, 0);
+          else if (tmax == tx2) nn = Vec3(-1, 0, 0);
+          else if (tmax == ty1) nn = Vec3(0, 1, 0);
+          else if (tmax == ty2) nn = Vec3(0, -1, 0);
+          else if (tmax == tz1) nn = Vec3(0, 0, 1);
+          else nn = Vec3(0, 0, -1);
+          *out = Hit(tmax, nn, mat, false);
+          return true;
+        }
+        return false;
+      }
+      case SH_TORUS: {      // torus.rs:61-126 — f64 quartic
+        double a = (double)big_r, b = (double)small_r;
+        Vec3 d = ray.origin - location;
+        Vec3 e = ray.dir;
+        double dx = d.x, dy = d.y, dz = d.z, ex = e.x, ey = e.y, ez = e.z;
+        double g = 4.0 * a * a * (ex * ex + ez * ez);
+        double h = 8.0 * a * a * (dx * ex + dz * ez);
+        double i = 4.0 * a * a * (dx * dx + dz * dz);
+        double j = ex * ex + ey * ey + ez * ez;
+        double k = 2.0 * (dx * ex + dy * ey + dz * ez);
+        double l = dx * dx + dy * dy + dz * dz + a * a - b * b;
+        Roots rs = roots_quartic(j * j, 2.0 * j * k, 2.0 * j * l + k * k - g, 2.0 * k * l - h, l * l - i);
+        double pos[4]; int np = 0;
+        for (int q = 0; q < rs.n; q++) if (rs.v[q] >= 0.0001) pos[np++] = rs.v[q];   // torus.rs:130-139
+        if (np == 0) return false;
+        double closest = pos[0];
+        for (int q = 1; q < np; q++) closest = std::fmin(closest, pos[q]);
+        double px = (double)d.x + (double)e.x * closest;
+        double py = (double)d.y + (double)e.y * closest;
+        double pz = (double)d.z + (double)e.z * closest;
+        double alpha = 1.0 - a / std::sqrt(px * px + pz * pz);
+        Vec3 n = unit((float)(alpha * px), (float)py, (float)(alpha * pz));
+        if (np % 2 == 1) *out = Hit((float)closest, -n, mat, false);
+        else *out = Hit((float)closest, n, mat, true);
+        return true;
+      }
+    }
+    return false;
+  }
+};
+
+}  // namespace ref

@@ -1,0 +1,29 @@
+"""In-tree build of libwpt.so with nvcc for sm_100a (no JIT cache: the .so travels with the tree)."""
+import os
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB = os.path.join(PKG_DIR, "libwpt.so")
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h", "Makefile"))]
+    deps.append(os.path.join(PKG_DIR, "..", "include", "wpt.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    """Compile every CUDA/C++ source of the package into wasm_pathtracer_b200/libwpt.so."""
+    if force or _stale():
+        cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout)
+        if r.returncode != 0:
+            raise RuntimeError("building libwpt.so failed")
+    return LIB

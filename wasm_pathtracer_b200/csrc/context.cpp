@@ -1,0 +1,227 @@
+// Session logic behind the C ABI: scene (re)build + upload, render targets, the wavefront
+// driver loop. No CPU rendering path exists here: without a CUDA device every entry point
+// fails.
+#include "context.h"
+#include <cstring>
+#include <cmath>
+
+namespace wpt {
+
+void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw CudaError(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+}
+
+Context::Context(int dev, uint32_t w, uint32_t h, uint32_t sid, const float cam5[5]) {
+  if (dev == -2) {   // host-only: scenes, BVHs and OBJ parsing can be inspected without a GPU
+    has_device = false; device = -2;
+    W = w; H = h;
+    std::memcpy(cam, cam5, sizeof cam);
+    wpt_default_config(&cfg);
+    select_scene(sid);
+    return;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) throw CudaError("no CUDA device available (libwpt has no CPU fallback)");
+  if (dev < 0) WPT_CUDA(cudaGetDevice(&dev));
+  device = dev;
+  WPT_CUDA(cudaSetDevice(device));
+  WPT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  W = w; H = h;
+  std::memcpy(cam, cam5, sizeof cam);
+  wpt_default_config(&cfg);
+  WPT_CUDA(cudaMallocHost((void**)&h_ring, 64 * sizeof(uint32_t)));
+  WPT_CUDA(cudaMallocHost((void**)&h_counters, 8 * sizeof(unsigned long long)));
+  w_shadow_n.alloc(2); w_ring.alloc(64); w_counters.alloc(8);
+  WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 8 * sizeof(unsigned long long), stream));
+  alloc_targets();
+  select_scene(sid);
+}
+
+Context::~Context() {
+  if (!has_device) return;
+  cudaSetDevice(device);
+  if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+  if (h_rgba) cudaFreeHost(h_rgba);
+  if (h_sampling) cudaFreeHost(h_sampling);
+  if (h_ring) cudaFreeHost(h_ring);
+  if (h_counters) cudaFreeHost(h_counters);
+}
+
+void Context::alloc_targets() {
+  if (!has_device) return;
+  size_t n = (size_t)W * H;
+  d_accum.release(); d_rgba.release(); d_sampling.release();
+  d_accum.alloc(n); d_rgba.alloc(n * 4); d_sampling.alloc(n * 4);
+  if (h_rgba) cudaFreeHost(h_rgba);
+  if (h_sampling) cudaFreeHost(h_sampling);
+  h_rgba = h_sampling = nullptr;
+  WPT_CUDA(cudaMallocHost((void**)&h_rgba, n * 4 + 4));
+  WPT_CUDA(cudaMallocHost((void**)&h_sampling, n * 4 + 4));
+  slots = 0; slot_region[2] = 0;
+  clear_targets();
+}
+
+void Context::clear_targets() {   // RenderTarget::clear / new, render_target.rs:31-53
+  if (!has_device) return;
+  size_t n = (size_t)W * H;
+  WPT_CUDA(cudaMemsetAsync(d_accum.p, 0, n * sizeof(float4), stream));
+  for (size_t i = 0; i < n; i++) { h_sampling[i * 4] = h_sampling[i * 4 + 1] = h_sampling[i * 4 + 2] = 0; h_sampling[i * 4 + 3] = 255; }
+  WPT_CUDA(cudaMemcpyAsync(d_sampling.p, h_sampling, n * 4, cudaMemcpyHostToDevice, stream));
+  rgba_stale = true;
+}
+
+void Context::reset() {   // wasm_interface.rs:137-148
+  if (!has_device) return;
+  clear_targets();
+  WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 8 * sizeof(unsigned long long), stream));
+  iterations = launches = 0;
+  photons_shot_total = photons_stored_total = 0;
+}
+
+void Context::select_scene(uint32_t id) {
+  std::vector<HostShape> shapes; std::vector<HostMaterial> mats;
+  if (id == WPT_SCENE_MUSEUM) scene_museum(shapes, mats);
+  else if (id == WPT_SCENE_BUNNY) {
+    auto it = mesh_tris.find(1);   // MESH_BUNNY_HIGH, scenes.rs:12
+    scene_bunny(it == mesh_tris.end() ? nullptr : &it->second, shapes, mats);
+  } else throw std::runtime_error("Invalid scene");
+  HostScene ns;
+  build_scene(ns, std::move(shapes), std::move(mats), cfg.bvh_kind);
+  if (ns.depth2 + 2 > 64 || ns.depth4 * 3 + 4 > 64) throw std::runtime_error("BVH too deep for the device traversal stack");
+  scene = std::move(ns);
+  scene_id = id;
+  upload_scene();
+  photons_ready = false; photon_shots = photon_count = 0;
+}
+
+void Context::upload_scene() {
+  if (!has_device) return;
+  std::vector<DNode2> n2; std::vector<DNode4> n4; std::vector<DShape> shp; std::vector<DMaterial> mats; std::vector<DLight> lights;
+  flatten_scene(scene, n2, n4, shp, mats, lights);
+  WPT_CUDA(cudaStreamSynchronize(stream));   // nothing may still read the old buffers
+  d_nodes2.upload(n2, stream); d_nodes4.upload(n4, stream); d_shapes.upload(shp, stream); d_mats.upload(mats, stream); d_lights.upload(lights, stream);
+  WPT_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
+}
+
+RenderParams Context::params(uint32_t render_type) const {
+  RenderParams rp{};
+  rp.scene.nodes2 = d_nodes2.p; rp.scene.nodes4 = d_nodes4.p; rp.scene.shapes = d_shapes.p; rp.scene.mats = d_mats.p; rp.scene.lights = d_lights.p;
+  rp.scene.num_inf = scene.num_inf; rp.scene.num_shapes = (uint32_t)scene.shapes.size(); rp.scene.num_lights = (uint32_t)scene.lights.size();
+  rp.scene.bvh_kind = scene.bvh_kind;
+  rp.scene.bg_r = scene.bg[0]; rp.scene.bg_g = scene.bg[1]; rp.scene.bg_b = scene.bg[2];
+  rp.cam.ox = cam[0]; rp.cam.oy = cam[1]; rp.cam.oz = cam[2];
+  // sin/cos of the camera angles are evaluated once on the host (vec3.rs:103-104,116-117)
+  rp.cam.cx = std::cos(cam[3]); rp.cam.sx = std::sin(cam[3]); rp.cam.cy = std::cos(cam[4]); rp.cam.sy = std::sin(cam[4]);
+  float fw = (float)W, fh = (float)H;
+  rp.cam.w_inv = 1.0f / fw; rp.cam.h_inv = 1.0f / fh; rp.cam.ar = fw / fh;   // tracer.rs:168-172
+  rp.photons.child_base = p_child_base.p; rp.photons.cum = p_cum.p;
+  rp.photons.num_lights = (uint32_t)scene.lights.size(); rp.photons.num_nodes = (uint32_t)p_child_base.n;
+  rp.W = W; rp.H = H;
+  rp.render_type = render_type; rp.light_debug = cfg.light_debug; rp.base_seed = cfg.base_seed;
+  return rp;
+}
+
+void Context::region(uint32_t* rx, uint32_t* ry, uint32_t* rw, uint32_t* rh) const {
+  *rx = cfg.region_x; *ry = cfg.region_y;
+  *rw = cfg.region_w ? cfg.region_w : W;
+  *rh = cfg.region_h ? cfg.region_h : H;
+  if (*rx + *rw > W || *ry + *rh > H) throw std::runtime_error("region outside the viewport");
+}
+
+// One slot per pixel of this session's rows of the region: rows ry + rank, ry + rank + world, ...
+void Context::ensure_slots(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh) {
+  require_device();
+  uint32_t world = cfg.world ? cfg.world : 1, rank = cfg.rank;
+  uint32_t key[6] = {rx, ry, rw, rh, rank, world};
+  if (slots && !std::memcmp(key, slot_region, sizeof key)) return;
+  uint32_t rows = rh > rank ? (rh - rank + world - 1) / world : 0;
+  uint32_t n = rows * rw;
+  s_ray_o.alloc(n); s_ray_d.alloc(n); s_col.alloc(n); s_sh_o.alloc(n); s_sh_d.alloc(n); s_sh_c.alloc(n); s_tail.alloc(n);
+  s_misc.alloc(n); s_hit.alloc(n); s_pixel.alloc(n); s_spp.alloc(n);
+  w_shadow_q0.alloc(n); w_shadow_q1.alloc(n);
+  launch_fill_pixels(s_pixel.p, W, rx, ry, rw, rh, rank, world, stream);
+  slots = n;
+  std::memcpy(slot_region, key, sizeof key);
+}
+
+PathState Context::path_state() {
+  PathState st{};
+  st.ray_o = s_ray_o.p; st.ray_d = s_ray_d.p; st.col = s_col.p; st.misc = s_misc.p; st.hit = s_hit.p;
+  st.sh_o = s_sh_o.p; st.sh_d = s_sh_d.p; st.sh_c = s_sh_c.p; st.tail = s_tail.p; st.pixel = s_pixel.p; st.n = slots;
+  return st;
+}
+WaveBuffers Context::wave_buffers() {
+  WaveBuffers wb{};
+  wb.shadow_q[0] = w_shadow_q0.p; wb.shadow_q[1] = w_shadow_q1.p; wb.shadow_n = w_shadow_n.p; wb.active_ring = w_ring.p;
+  wb.counters = w_counters.p; wb.accum = d_accum.p;
+  return wb;
+}
+
+// The wavefront loop: shade(0) generates the first camera rays, then trace / shade alternate
+// until no slot is live. The live count is read back every `poll` iterations.
+void Context::run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp) {
+  require_device();
+  if (!slots) return;
+  if (render_type == WPT_PNEE && !photons_ready) throw std::runtime_error("photon tree not built");
+  RenderParams rp = params(render_type);
+  PathState st = path_state();
+  WaveBuffers wb = wave_buffers();
+  launch_setup_slots(st, d_spp_per_slot, uniform_spp, d_accum.p, stream);
+  WPT_CUDA(cudaMemsetAsync(w_shadow_n.p, 0, 2 * sizeof(uint32_t), stream));
+  WPT_CUDA(cudaMemsetAsync(w_ring.p, 0, 64 * sizeof(uint32_t), stream));
+  launches += 1;
+  const int grid = device_sm_count() * 8;
+  const uint32_t poll = 8;
+  uint32_t iter = 0;
+  launch_shade(rp, st, wb, iter, grid, stream);
+  launches += 1;
+  for (;;) {
+    for (uint32_t k = 0; k < poll; k++) {
+      iter++;
+      launch_trace(rp, st, wb, iter, grid, stream);
+      launch_shade(rp, st, wb, iter, grid, stream);
+      launches += 2;
+    }
+    WPT_CUDA(cudaMemcpyAsync(h_ring, w_ring.p, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+    if (h_ring[iter & 63u] == 0) break;
+  }
+  iterations += iter;
+  rgba_stale = true;
+}
+
+void Context::render_exact(uint32_t spp) {
+  require_device();
+  uint32_t rx, ry, rw, rh;
+  region(&rx, &ry, &rw, &rh);
+  ensure_slots(rx, ry, rw, rh);
+  run_wavefront(cfg.render_type, nullptr, spp);
+}
+
+const uint8_t* Context::results(uint32_t show_sampling) {   // wasm_interface.rs:120-134
+  require_device();
+  size_t n = (size_t)W * H;
+  if (show_sampling == 1) {
+    WPT_CUDA(cudaMemcpyAsync(h_sampling, d_sampling.p, n * 4, cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+    return h_sampling;
+  }
+  if (rgba_stale) {
+    launch_resolve_rgba(d_accum.p, d_rgba.p, (uint32_t)n, stream);
+    WPT_CUDA(cudaMemcpyAsync(h_rgba, d_rgba.p, n * 4, cudaMemcpyDeviceToHost, stream));
+    rgba_stale = false;
+  }
+  WPT_CUDA(cudaStreamSynchronize(stream));
+  return h_rgba;
+}
+
+void Context::stats(uint64_t out[8]) {
+  require_device();
+  WPT_CUDA(cudaMemcpyAsync(h_counters, w_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaStreamSynchronize(stream));
+  out[0] = h_counters[0]; out[1] = h_counters[2]; out[2] = h_counters[1];
+  out[3] = photons_shot_total; out[4] = photons_stored_total; out[5] = iterations; out[6] = launches; out[7] = 0;
+}
+
+}  // namespace wpt

@@ -1,0 +1,119 @@
+// Session object behind the C ABI (include/wpt.h). One context = one GPU = one host thread
+// at a time (the reference is single-threaded per instance, wasm_interface.rs:59-62).
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/wpt.h"
+#include "host_scene.h"
+#include "kernels.h"
+
+namespace wpt {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+void cuda_check(cudaError_t e, const char* what);
+#define WPT_CUDA(x) ::wpt::cuda_check((x), #x)
+
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    release();
+    if (count) WPT_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    n = count;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void upload(const std::vector<T>& v, cudaStream_t s) {
+    alloc(v.size());
+    if (!v.empty()) WPT_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct HalfSettings { uint32_t type; uint32_t adaptive; };
+
+struct Context {
+  int device = 0;
+  bool has_device = true;                  // false: host-only session (scene / BVH inspection)
+  void require_device() const { if (!has_device) throw CudaError("no CUDA device in a host-only session (libwpt has no CPU fallback)"); }
+  cudaStream_t stream = nullptr;
+  uint32_t W = 0, H = 0, scene_id = 0;
+  float cam[5] = {0, 0, 0, 0, 0};
+  wpt_config cfg;
+  HalfSettings left{WPT_NORMAL_NEE, 0}, right{WPT_PNEE, 1};   // wasm_interface.rs:90-97
+  uint32_t light_debug = 0;
+
+  // meshes / textures (wasm_interface.rs:38-41)
+  std::map<uint32_t, std::vector<float>> mesh_preload;
+  std::map<uint32_t, std::vector<HostShape>> mesh_tris;
+  std::map<uint32_t, std::vector<uint8_t>> textures;
+
+  HostScene scene;
+  DevBuf<DNode2> d_nodes2;
+  DevBuf<DNode4> d_nodes4;
+  DevBuf<DShape> d_shapes;
+  DevBuf<DMaterial> d_mats;
+  DevBuf<DLight> d_lights;
+
+  // render targets (render_target.rs): accumulators + RGBA8 + sampling-debug RGBA8
+  DevBuf<float4> d_accum;
+  DevBuf<uint8_t> d_rgba, d_sampling;
+  uint8_t* h_rgba = nullptr;       // pinned, W*H*4
+  uint8_t* h_sampling = nullptr;   // pinned, W*H*4
+  bool rgba_stale = true;
+
+  // wavefront state
+  DevBuf<float4> s_ray_o, s_ray_d, s_col, s_sh_o, s_sh_d, s_sh_c, s_tail;
+  DevBuf<uint4> s_misc;
+  DevBuf<float2> s_hit;
+  DevBuf<uint32_t> s_pixel, s_spp;
+  DevBuf<uint32_t> w_shadow_q0, w_shadow_q1, w_shadow_n, w_ring;
+  DevBuf<unsigned long long> w_counters;
+  uint32_t* h_ring = nullptr;                 // pinned [64]
+  unsigned long long* h_counters = nullptr;   // pinned [8]
+  uint32_t slots = 0;                         // slots of the current partition
+  uint32_t slot_region[6] = {0, 0, 0, 0, 0, 0};   // region + rank/world the pixel map was built for
+
+  // photons
+  DevBuf<uint32_t> p_child_base;
+  DevBuf<float> p_cum;
+  bool photons_ready = false;
+  uint64_t photon_shots = 0, photon_count = 0;
+  std::vector<uint32_t> ph_light; std::vector<float> ph_loc, ph_w;     // host copies (read-backs)
+  std::vector<uint32_t> pt_meta; std::vector<float> pt_cum, pt_bins;   // flattened tree (read-backs)
+
+  // counters since the last reset
+  uint64_t iterations = 0, launches = 0, photons_shot_total = 0, photons_stored_total = 0;
+
+  Context(int device, uint32_t w, uint32_t h, uint32_t scene_id, const float cam5[5]);
+  ~Context();
+
+  void select_scene(uint32_t id);          // wasm_interface.rs:389-398 + upload
+  void upload_scene();
+  void alloc_targets();
+  void clear_targets();
+  void reset();
+  void ensure_slots(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh);
+  RenderParams params(uint32_t render_type) const;
+  PathState path_state();
+  WaveBuffers wave_buffers();
+  void region(uint32_t* rx, uint32_t* ry, uint32_t* rw, uint32_t* rh) const;
+
+  // drivers
+  void run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp);
+  void render_exact(uint32_t spp);
+  uint64_t render_adaptive(uint64_t budget);
+  void build_photons();
+  void compute(uint64_t num_samples);      // wasm_interface.rs:374-384
+  void photon_sample_batch(const float* pts3, const uint32_t* seeds, uint64_t n, uint32_t* light, float* pdf);
+  void error_map(float* mse, float stats3[3]);
+  void round_spp(uint32_t* spp);
+  const uint8_t* results(uint32_t show_sampling);
+  void stats(uint64_t out[8]);
+};
+
+}  // namespace wpt

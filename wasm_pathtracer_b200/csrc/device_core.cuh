@@ -1,0 +1,522 @@
+// Device-side geometry, RNG and traversal. Compiled with -fmad=false and without
+// -use_fast_math: every f32 expression is written in the reference's evaluation order so
+// that results are bit-identical to Rust's (no FMA contraction, IEEE div/sqrt).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "wpt_types.h"
+
+namespace wpt {
+
+#define WPT_DEV __device__ __forceinline__
+#define WPT_STACK 64          // (node, entry distance) entries; host checks BVH depth against it
+#define WPT_INF CUDART_INF_F
+
+// ------------------------------------------------------------------ vectors (math/vec3.rs)
+struct F3 { float x, y, z; };
+WPT_DEV F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+WPT_DEV F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+WPT_DEV F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+WPT_DEV F3 operator-(F3 a) { return f3(-a.x, -a.y, -a.z); }
+WPT_DEV F3 operator*(F3 a, F3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+WPT_DEV F3 operator*(F3 a, float m) { return f3(m * a.x, m * a.y, m * a.z); }   // vec3.rs:151-165
+WPT_DEV F3 operator*(float m, F3 a) { return f3(m * a.x, m * a.y, m * a.z); }
+WPT_DEV F3 operator/(F3 a, float d) { return f3(a.x / d, a.y / d, a.z / d); }
+WPT_DEV float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+WPT_DEV F3 cross(F3 a, F3 t) { return f3(a.y * t.z - a.z * t.y, a.z * t.x - a.x * t.z, a.x * t.y - a.y * t.x); }
+WPT_DEV float len(F3 a) { return sqrtf(dot(a, a)); }
+WPT_DEV F3 normalize(F3 a) { return a * (1.0f / len(a)); }   // vec3.rs:27-29
+WPT_DEV F3 orthogonal(F3 s) {                                 // vec3.rs:37-54
+  if (fabsf(s.z) > 0.1f) return normalize(f3(1.0f, 1.0f, -(s.x * 1.0f + s.y * 1.0f) / s.z));
+  if (fabsf(s.x) > 0.1f) return normalize(f3(-(s.y * 1.0f + s.z * 1.0f) / s.x, 1.0f, 1.0f));
+  return normalize(f3(1.0f, -(s.x * 1.0f + s.z * 1.0f) / s.y, 1.0f));
+}
+WPT_DEV F3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
+
+struct Ray { F3 o, d, inv; };
+WPT_DEV Ray make_ray(F3 o, F3 d) { Ray r; r.o = o; r.d = d; r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); return r; }   // ray.rs:31-33
+
+// ------------------------------------------------------------------ RNG (rng.rs) + stream contract
+struct Rng {
+  uint32_t s;
+  WPT_DEV uint32_t u32() { uint32_t x = s; x ^= x << 13; x ^= x >> 17; x ^= x << 5; s = x; return x; }
+  WPT_DEV float f32() { return (float)u32() * (1.0f / 4294967296.0f); }   // rng.rs:19-21
+  WPT_DEV uint32_t range(uint32_t lo, uint32_t hi) {                       // rng.rs:25-38
+    if (hi == lo + 1) return 0;
+    float f = f32();
+    if (f == 1.0f) return hi - 1;
+    return (uint32_t)floorf(f * (float)(hi - lo)) + lo;
+  }
+};
+WPT_DEV uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+WPT_DEV uint32_t stream_seed(uint32_t index, uint32_t sample, uint32_t stream, uint32_t base) {
+  uint32_t s = mix32(index + mix32(sample + mix32(stream ^ base)));
+  return s == 0 ? 0xBABABEBEu : s;
+}
+// cos/sin of a in [0, 2*pi] from f32 + - * only (DESIGN.md "shared trig")
+WPT_DEV void shared_sincos(float a, float* s_out, float* c_out) {
+  int k = (int)(a * 0.63661977f + 0.5f);
+  float fk = (float)k;
+  float r = (a - fk * 1.5707963f) - fk * (-4.371139e-8f);
+  float r2 = r * r;
+  float s = r + r * r2 * (-1.6666654611e-1f + r2 * (8.3321608736e-3f + r2 * (-1.9515295891e-4f)));
+  float c = (1.0f - 0.5f * r2) + r2 * r2 * (4.166664568298827e-2f + r2 * (-1.388731625493765e-3f + r2 * 2.443315711809948e-5f));
+  switch (k & 3) {
+    case 0: *s_out = s;  *c_out = c;  break;
+    case 1: *s_out = c;  *c_out = -s; break;
+    case 2: *s_out = -s; *c_out = -c; break;
+    default: *s_out = -c; *c_out = s; break;
+  }
+}
+
+// ------------------------------------------------------------------ boxes (aabb.rs)
+// AABB::hit, aabb.rs:132-164. Box = (a.x,a.y,a.z)-(a.w,b.x,b.y).
+WPT_DEV bool box_hit(float x0, float y0, float z0, float x1, float y1, float z1, const Ray& r, float* t) {
+  float tx1 = (x0 - r.o.x) * r.inv.x, tx2 = (x1 - r.o.x) * r.inv.x;
+  float ty1 = (y0 - r.o.y) * r.inv.y, ty2 = (y1 - r.o.y) * r.inv.y;
+  float tz1 = (z0 - r.o.z) * r.inv.z, tz2 = (z1 - r.o.z) * r.inv.z;
+  float tmin = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fminf(tz1, tz2));
+  float tmax = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+  if (tmin > tmax) return false;
+  if (tmin >= 0.0f) { *t = tmin; return true; }
+  if (tmax >= 0.0f) { *t = 0.0f; return true; }
+  return false;
+}
+// one lane of AABBx4::hit, aabb.rs:252-288: -inf for a miss
+WPT_DEV float box_hit_x4(float x0, float y0, float z0, float x1, float y1, float z1, const Ray& r) {
+  float tx1 = (x0 - r.o.x) * r.inv.x, tx2 = (x1 - r.o.x) * r.inv.x;
+  float ty1 = (y0 - r.o.y) * r.inv.y, ty2 = (y1 - r.o.y) * r.inv.y;
+  float tz1 = (z0 - r.o.z) * r.inv.z, tz2 = (z1 - r.o.z) * r.inv.z;
+  float tmin = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fminf(tz1, tz2));
+  float tmax = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+  if (tmin > tmax || tmax < 0.0f) return -WPT_INF;
+  if (tmin >= 0.0f) return tmin;
+  return 0.0f;
+}
+
+// ------------------------------------------------------------------ roots 0.0.4 quartic (f64)
+struct Roots4 {
+  int n; double v[4];
+  WPT_DEV void add(double x) {
+    for (int i = 0; i < n; i++) if (v[i] == x) return;
+    if (n == 4) return;
+    int i = n;
+    while (i > 0 && v[i - 1] > x) { v[i] = v[i - 1]; i--; }
+    v[i] = x; n++;
+  }
+};
+__device__ __noinline__ void d_quadratic_normalized(double a1, double a0, Roots4& r) {
+  double disc = a1 * a1 - 4.0 * a0;
+  if (disc < 0.0) return;
+  double h = a1 / 2.0;
+  if (disc == 0.0) { r.add(-h); return; }
+  double sq = sqrt(disc);
+  r.add(-h - sq / 2.0);
+  r.add(-h + sq / 2.0);
+}
+__device__ __noinline__ void d_quadratic(double a2, double a1, double a0, Roots4& r) {
+  if (a2 == 0.0) { if (a1 != 0.0) r.add(-a0 / a1); return; }
+  double disc = a1 * a1 - 4.0 * a2 * a0;
+  if (disc < 0.0) return;
+  double a2x2 = 2.0 * a2;
+  if (disc == 0.0) { r.add(-a1 / a2x2); return; }
+  double sq = sqrt(disc);
+  r.add((-a1 - sq) / a2x2);
+  r.add((-a1 + sq) / a2x2);
+}
+__device__ __noinline__ void d_cubic_normalized(double a2, double a1, double a0, Roots4& out) {
+  double q = (3.0 * a1 - a2 * a2) / 9.0;
+  double r = (9.0 * a2 * a1 - 27.0 * a0 - 2.0 * a2 * a2 * a2) / 54.0;
+  double q3 = q * q * q;
+  double d = q3 + r * r;
+  double a2_div_3 = a2 / 3.0;
+  if (d < 0.0) {
+    double phi_3 = acos(r / sqrt(-q3)) / 3.0;
+    double sqrt_q_2 = 2.0 * sqrt(-q);
+    const double two_third_pi = 2.0943951023931954923;
+    out.add(sqrt_q_2 * cos(phi_3) - a2_div_3);
+    out.add(sqrt_q_2 * cos(phi_3 - two_third_pi) - a2_div_3);
+    out.add(sqrt_q_2 * cos(phi_3 + two_third_pi) - a2_div_3);
+  } else {
+    double sqrt_d = sqrt(d);
+    double s = cbrt(r + sqrt_d);
+    double t = cbrt(r - sqrt_d);
+    out.add(s + t - a2_div_3);
+    if (s == t && s + t != 0.0) out.add(-(s + t) / 2.0 - a2_div_3);
+  }
+}
+__device__ __noinline__ void d_cubic(double a3, double a2, double a1, double a0, Roots4& r) {
+  if (a3 == 0.0) { d_quadratic(a2, a1, a0, r); return; }
+  if (a2 == 0.0 && a1 == 0.0 && a0 == 0.0) { r.add(0.0); return; }
+  d_cubic_normalized(a2 / a3, a1 / a3, a0 / a3, r);
+}
+__device__ __noinline__ void d_biquadratic(double a4, double a2, double a0, Roots4& out) {
+  Roots4 q; q.n = 0;
+  d_quadratic(a4, a2, a0, q);
+  for (int i = 0; i < q.n; i++) {
+    double x = q.v[i];
+    if (x > 0.0) { double s = sqrt(x); out.add(-s); out.add(s); }
+    else if (x == 0.0) out.add(0.0);
+  }
+}
+__device__ __noinline__ void d_quartic_depressed(double a2, double a1, double a0, Roots4& out) {
+  if (a1 == 0.0) { d_biquadratic(1.0, a2, a0, out); return; }
+  if (a0 == 0.0) { d_cubic_normalized(0.0, a2, a1, out); out.add(0.0); return; }
+  double a2_pow_2 = a2 * a2;
+  double a1_div_2 = a1 / 2.0;
+  double b2 = a2 * 5.0 / 2.0;
+  double b1 = 2.0 * a2_pow_2 - a0;
+  double b0 = (a2_pow_2 * a2 - a2 * a0 - a1_div_2 * a1_div_2) / 2.0;
+  Roots4 res; res.n = 0;
+  d_cubic_normalized(b2, b1, b0, res);
+  double y = res.v[res.n - 1];
+  double a2_plus_2y = a2 + 2.0 * y;
+  if (a2_plus_2y > 0.0) {
+    double s = sqrt(a2_plus_2y);
+    double q0a = a2 + y - a1_div_2 / s;
+    double q0b = a2 + y + a1_div_2 / s;
+    Roots4 ra; ra.n = 0; Roots4 rb; rb.n = 0;
+    d_quadratic_normalized(s, q0a, ra);
+    d_quadratic_normalized(-s, q0b, rb);
+    for (int i = 0; i < ra.n; i++) out.add(ra.v[i]);
+    for (int i = 0; i < rb.n; i++) out.add(rb.v[i]);
+  }
+}
+__device__ __noinline__ void d_quartic(double a4, double a3, double a2, double a1, double a0, Roots4& out) {
+  out.n = 0;
+  if (a4 == 0.0) { d_cubic(a3, a2, a1, a0, out); return; }
+  if (a0 == 0.0) { d_cubic(a4, a3, a2, a1, out); out.add(0.0); return; }
+  if (a1 == 0.0 && a3 == 0.0) { d_biquadratic(a4, a2, a0, out); return; }
+  double discriminant =
+      a4 * a0 * a4 * (256.0 * a4 * a0 * a0 + a1 * (144.0 * a2 * a1 - 192.0 * a3 * a0)) +
+      a4 * a0 * a2 * a2 * (16.0 * a2 * a2 - 80.0 * a3 * a1 - 128.0 * a4 * a0) +
+      (a3 * a3 * (a4 * a0 * (144.0 * a2 * a0 - 6.0 * a1 * a1) +
+                  (a0 * (18.0 * a3 * a2 * a1 - 27.0 * a3 * a3 * a0 - 4.0 * a2 * a2 * a2) +
+                   a1 * a1 * (a2 * a2 - 4.0 * a3 * a1)))) +
+      a4 * a1 * a1 * (18.0 * a3 * a2 * a1 - 27.0 * a4 * a1 * a1 - 4.0 * a2 * a2 * a2);
+  double pp = 8.0 * a4 * a2 - 3.0 * a3 * a3;
+  double rr = a3 * a3 * a3 + 8.0 * a4 * a4 * a1 - 4.0 * a4 * a3 * a2;
+  double delta0 = a2 * a2 - 3.0 * a3 * a1 + 12.0 * a4 * a0;
+  double dd = 64.0 * a4 * a4 * a4 * a0 - 16.0 * a4 * a4 * a2 * a2 + 16.0 * a4 * a3 * a3 * a2 -
+              16.0 * a4 * a4 * a3 * a1 - 3.0 * a3 * a3 * a3 * a3;
+  if (discriminant == 0.0) {
+    bool triple = delta0 == 0.0;
+    bool quadruple = triple && dd == 0.0;
+    bool no_roots = dd == 0.0 && pp > 0.0 && rr == 0.0;
+    if (quadruple) { out.add(-a3 / (4.0 * a4)); return; }
+    if (triple) {
+      double x0 = (-72.0 * a4 * a4 * a0 + 10.0 * a4 * a2 * a2 - 3.0 * a3 * a3 * a2) /
+                  (9.0 * (8.0 * a4 * a4 * a1 - 4.0 * a4 * a3 * a2 + a3 * a3 * a3));
+      out.add(x0);
+      out.add(-(a3 / a4 + 3.0 * x0));
+      return;
+    }
+    if (no_roots) return;
+  } else if (discriminant > 0.0 && (pp > 0.0 || dd > 0.0)) return;
+  double a4_pow_2 = a4 * a4, a4_pow_3 = a4_pow_2 * a4, a4_pow_4 = a4_pow_2 * a4_pow_2;
+  double p = pp / (8.0 * a4_pow_2);
+  double q = rr / (8.0 * a4_pow_3);
+  double r = (dd + 16.0 * a4_pow_2 * (12.0 * a0 * a4 - 3.0 * a1 * a3 + a2 * a2)) / (256.0 * a4_pow_4);
+  Roots4 dep; dep.n = 0;
+  d_quartic_depressed(p, q, r, dep);
+  for (int i = 0; i < dep.n; i++) out.add(dep.v[i] - a3 / (4.0 * a4));
+}
+
+// ------------------------------------------------------------------ primitives
+// Torus::trace, torus.rs:61-126. Returns hit distance (f32) and outward-or-flipped normal.
+__device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray& ray, float* t_out, F3* n_out) {
+  double a = (double)q1.x, b = (double)q1.y;
+  F3 d = ray.o - xyz(q0);
+  F3 e = ray.d;
+  double dx = d.x, dy = d.y, dz = d.z, ex = e.x, ey = e.y, ez = e.z;
+  double g = 4.0 * a * a * (ex * ex + ez * ez);
+  double h = 8.0 * a * a * (dx * ex + dz * ez);
+  double i = 4.0 * a * a * (dx * dx + dz * dz);
+  double j = ex * ex + ey * ey + ez * ez;
+  double k = 2.0 * (dx * ex + dy * ey + dz * ez);
+  double l = dx * dx + dy * dy + dz * dz + a * a - b * b;
+  Roots4 rs;
+  d_quartic(j * j, 2.0 * j * k, 2.0 * j * l + k * k - g, 2.0 * k * l - h, l * l - i, rs);
+  int np = 0; double closest = 0.0;
+  for (int q = 0; q < rs.n; q++)
+    if (rs.v[q] >= 0.0001) { closest = np == 0 ? rs.v[q] : fmin(closest, rs.v[q]); np++; }   // torus.rs:130-139,107-110
+  if (np == 0) return false;
+  *t_out = (float)closest;
+  if (n_out) {
+    double px = (double)d.x + (double)e.x * closest;
+    double py = (double)d.y + (double)e.y * closest;
+    double pz = (double)d.z + (double)e.z * closest;
+    double alpha = 1.0 - a / sqrt(px * px + pz * pz);
+    F3 n = normalize(f3((float)(alpha * px), (float)py, (float)(alpha * pz)));
+    *n_out = (np % 2 == 1) ? -n : n;   // odd number of positive roots: inside (torus.rs:120-124)
+  }
+  return true;
+}
+
+// Tracable::trace_simple for shape record `s`. `limit`/`strict` implement the acceptance test
+// of trace_shapes_md (scene.rs:450-472): the first candidate needs t <= max_dis, later ones
+// 0 < t < best. Rejecting on t before the edge tests does not change any result.
+WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float limit, bool strict, float* t_out) {
+  const float4* p = reinterpret_cast<const float4*>(shapes + idx);
+  float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+  uint32_t type = __float_as_uint(q0.w) & 0xFFu;
+  if (type == SH_TRIANGLE) {   // triangle.rs:159-191
+    float4 q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    F3 v0 = xyz(q0), v1 = xyz(q1), v2 = xyz(q2);
+    F3 n = f3(q1.w, q2.w, q3.x);
+    float n_dot_d = dot(n, ray.d);
+    if (n_dot_d == 0.0f) return false;
+    float orig_dis = dot(n, v0);
+    float t = (orig_dis - dot(n, ray.o)) / n_dot_d;
+    if (t <= 0.0f) return false;
+    if (strict ? !(t < limit) : !(t <= limit)) return false;
+    F3 nn = f3(q3.y, q3.z, q3.w);
+    F3 pt = ray.o + t * ray.d;
+    const float slack = 0.1f * WPT_EPSILON;   // triangle.rs:41-45
+    if (!(dot(nn, cross(v1 - v0, pt - v0)) + slack >= 0.0f)) return false;
+    if (!(dot(nn, cross(v2 - v1, pt - v1)) + slack >= 0.0f)) return false;
+    if (!(dot(nn, cross(v0 - v2, pt - v2)) + slack >= 0.0f)) return false;
+    *t_out = t;
+    return true;
+  }
+  float t;
+  if (type == SH_PLANE) {      // plane.rs:80-99
+    F3 nr = xyz(q1);
+    float n_dot_dir = dot(nr, ray.d);
+    if (n_dot_dir == 0.0f) return false;
+    t = (q1.w - dot(nr, ray.o)) / n_dot_dir;
+    if (t <= 0.0f) return false;
+  } else if (type == SH_AARECT) {   // aa_rect.rs:142-174 (own 1/dir: the same value as ray.inv)
+    float tx1 = (q0.x - ray.o.x) * ray.inv.x, tx2 = (q1.x - ray.o.x) * ray.inv.x;
+    float ty1 = (q0.y - ray.o.y) * ray.inv.y, ty2 = (q1.y - ray.o.y) * ray.inv.y;
+    float tz1 = (q0.z - ray.o.z) * ray.inv.z, tz2 = (q1.z - ray.o.z) * ray.inv.z;
+    float tmin = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fminf(tz1, tz2));
+    float tmax = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+    if (tmin >= tmax) return false;
+    if (tmin > 0.0f) t = tmin;
+    else if (tmax > 0.0f) t = tmax;
+    else return false;
+  } else {                     // torus: ray.rs:110-116 default = trace().distance
+    if (!torus_trace(q0, q1, ray, &t, nullptr)) return false;
+  }
+  if (strict ? !(0.0f < t && t < limit) : !(t <= limit)) return false;
+  *t_out = t;
+  return true;
+}
+
+// Tracable::trace for the winning shape (scene.rs:140): distance, Hit::new-normalised normal,
+// material index. Returns false if the full intersection reports no hit.
+WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float* t_out, F3* n_out, uint32_t* mat_out) {
+  const float4* p = reinterpret_cast<const float4*>(shapes + idx);
+  float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+  uint32_t meta = __float_as_uint(q0.w);
+  uint32_t type = meta & 0xFFu;
+  *mat_out = meta >> 8;
+  F3 n; float t;
+  if (type == SH_TRIANGLE) {   // triangle.rs:116-157
+    float4 q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    F3 v0 = xyz(q0), v1 = xyz(q1), v2 = xyz(q2);
+    F3 nu = f3(q1.w, q2.w, q3.x);
+    float n_dot_d = dot(nu, ray.d);
+    if (n_dot_d == 0.0f) return false;
+    t = (dot(nu, v0) - dot(nu, ray.o)) / n_dot_d;
+    if (t <= 0.0f) return false;
+    F3 nn = f3(q3.y, q3.z, q3.w);
+    F3 pt = ray.o + t * ray.d;
+    const float slack = 0.1f * WPT_EPSILON;
+    if (!(dot(nn, cross(v1 - v0, pt - v0)) + slack >= 0.0f)) return false;
+    if (!(dot(nn, cross(v2 - v1, pt - v1)) + slack >= 0.0f)) return false;
+    if (!(dot(nn, cross(v0 - v2, pt - v2)) + slack >= 0.0f)) return false;
+    n = (n_dot_d > 0.0f) ? -nn : nn;
+  } else if (type == SH_PLANE) {   // plane.rs:45-77
+    F3 nr = xyz(q1);
+    float n_dot_dir = dot(nr, ray.d);
+    if (n_dot_dir == 0.0f) return false;
+    t = (q1.w - dot(nr, ray.o)) / n_dot_dir;
+    if (t <= 0.0f) return false;
+    n = (n_dot_dir > 0.0f) ? -nr : nr;
+  } else if (type == SH_AARECT) {  // aa_rect.rs:71-139
+    float tx1 = (q0.x - ray.o.x) * ray.inv.x, tx2 = (q1.x - ray.o.x) * ray.inv.x;
+    float ty1 = (q0.y - ray.o.y) * ray.inv.y, ty2 = (q1.y - ray.o.y) * ray.inv.y;
+    float tz1 = (q0.z - ray.o.z) * ray.inv.z, tz2 = (q1.z - ray.o.z) * ray.inv.z;
+    float tmin = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fminf(tz1, tz2));
+    float tmax = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+    if (tmin >= tmax) return false;
+    if (tmin > 0.0f) {
+      t = tmin;
+      if (tmin == tx1) n = f3(-1, 0, 0); else if (tmin == tx2) n = f3(1, 0, 0);
+      else if (tmin == ty1) n = f3(0, -1, 0); else if (tmin == ty2) n = f3(0, 1, 0);
+      else if (tmin == tz1) n = f3(0, 0, -1); else n = f3(0, 0, 1);
+    } else if (tmax > 0.0f) {
+      t = tmax;
+      if (tmax == tx1) n = f3(1, 0, 0); else if (tmax == tx2) n = f3(-1, 0, 0);
+      else if (tmax == ty1) n = f3(0, 1, 0); else if (tmax == ty2) n = f3(0, -1, 0);
+      else if (tmax == tz1) n = f3(0, 0, 1); else n = f3(0, 0, -1);
+    } else return false;
+  } else {
+    if (!torus_trace(q0, q1, ray, &t, &n)) return false;
+  }
+  *t_out = t;
+  *n_out = normalize(n);   // Hit::new, ray.rs:59-62
+  return true;
+}
+
+// ------------------------------------------------------------------ Scene::trace_g (scene.rs:162-184)
+struct GHit { float t; int id; uint32_t visits; };
+
+// trace_shapes_md over a leaf (scene.rs:450-472); updates (best_t, best_id) if the leaf
+// reports a hit — a later leaf wins exact ties because the test is t <= max_dis.
+WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const Ray& ray, float& bound, int& best_id) {
+  bool have = false; float bt = 0.0f; uint32_t bi = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    float t;
+    if (shape_trace_simple(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) { have = true; bt = t; bi = first + i; }
+  }
+  if (have) { bound = bt; best_id = (int)bi; }
+}
+
+// traverse_bvh_guarded + traverse_bvh (scene.rs:191-288), iterative with an explicit stack of
+// (node, entry distance): a popped node is skipped iff the current bound is < its entry
+// distance — exactly the `lshape_dis < right_dis` early-outs of the recursion.
+WPT_DEV void traverse_bvh2(const DScene& sc, const Ray& ray, float& bound, int& best_id, uint32_t& visits, uint32_t* stack_n, float* stack_d) {
+  const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
+  float4 ra = __ldg(nodes), rb = __ldg(nodes + 1);
+  visits += 1;   // the root guard (scene.rs:207,210)
+  float h;
+  if (!(box_hit(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, ray, &h) && h < bound)) return;
+  int sp = 0;
+  uint32_t lf = __float_as_uint(rb.z), cnt = __float_as_uint(rb.w);
+  for (;;) {
+    visits += 1;
+    if (cnt != 0) {
+      leaf_scan(sc, sc.num_inf + lf, cnt, ray, bound, best_id);
+    } else {
+      const float4* c = nodes + (size_t)lf * 2;
+      float4 la = __ldg(c), lb = __ldg(c + 1), qa = __ldg(c + 2), qb = __ldg(c + 3);
+      float dl, dr;
+      bool hl = box_hit(la.x, la.y, la.z, la.w, lb.x, lb.y, ray, &dl) && dl < bound;
+      if (!hl) {
+        // left misses: traverse_bvh_guarded(right) — counts the guard (scene.rs:283-286)
+        visits += 1;
+        bool hr = box_hit(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < bound;
+        if (hr) { lf = __float_as_uint(qb.z); cnt = __float_as_uint(qb.w); continue; }
+      } else {
+        bool hr = box_hit(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < bound;
+        if (!hr) { lf = __float_as_uint(lb.z); cnt = __float_as_uint(lb.w); continue; }
+        if (dl < dr) {   // left first; tie -> right first (scene.rs:244,261)
+          stack_n[sp] = lf + 1; stack_d[sp] = dr; sp++;
+          lf = __float_as_uint(lb.z); cnt = __float_as_uint(lb.w);
+        } else {
+          stack_n[sp] = lf; stack_d[sp] = dl; sp++;
+          lf = __float_as_uint(qb.z); cnt = __float_as_uint(qb.w);
+        }
+        continue;
+      }
+    }
+    // pop
+    bool found = false;
+    while (sp > 0) {
+      sp--;
+      if (bound < stack_d[sp]) continue;   // near hit closer than the far box: skip it
+      float4 nb = __ldg(nodes + (size_t)stack_n[sp] * 2 + 1);
+      lf = __float_as_uint(nb.z); cnt = __float_as_uint(nb.w);
+      found = true;
+      break;
+    }
+    if (!found) return;
+  }
+}
+
+// scene.rs:346-388 — the exact compare-and-swap network (not stable for n == 4)
+WPT_DEV void sort_small(int* id, float* d, uint32_t n) {
+#define WPT_SWAP(i, j) { int ti = id[i]; id[i] = id[j]; id[j] = ti; float td = d[i]; d[i] = d[j]; d[j] = td; }
+  if (n == 2) {
+    if (d[1] < d[0]) WPT_SWAP(0, 1)
+  } else if (n == 3) {
+    if (d[1] < d[0]) WPT_SWAP(0, 1)
+    if (d[2] < d[1]) WPT_SWAP(1, 2)
+    if (d[1] < d[0]) WPT_SWAP(0, 1)
+  } else if (n == 4) {
+    if (d[1] < d[0]) WPT_SWAP(0, 1)
+    if (d[3] < d[2]) WPT_SWAP(2, 3)
+    if (d[0] < d[2]) {
+      if (d[2] < d[1]) {
+        WPT_SWAP(1, 2)
+        if (d[3] < d[2]) WPT_SWAP(2, 3)
+      }
+    } else {
+      WPT_SWAP(0, 2)
+      WPT_SWAP(1, 2)
+      if (d[3] < d[1]) { WPT_SWAP(1, 3) WPT_SWAP(2, 3) }
+      else if (d[3] < d[2]) WPT_SWAP(2, 3)
+    }
+  }
+#undef WPT_SWAP
+}
+
+// traverse_bvh4 (scene.rs:292-342), iterative: children are pushed in reverse sorted order; a
+// popped child is dropped iff its box distance is > the current bound, which is what the
+// recursion's early `return` does for it and all later (farther) siblings.
+WPT_DEV void traverse_bvh4(const DScene& sc, const Ray& ray, float& bound, int& best_id, uint32_t& visits, uint32_t* stack_n, float* stack_d) {
+  int sp = 0;
+  int node = 0;
+  for (;;) {
+    visits += 1;
+    if (node < 0) {
+      uint32_t code = (uint32_t)node;
+      leaf_scan(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, bound, best_id);
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + node);
+      float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
+      int4 ch = __ldg(reinterpret_cast<const int4*>(p + 6));
+      uint32_t nc = __ldg(reinterpret_cast<const uint32_t*>(p + 7));
+      int id[4] = {0, 0, 0, 0}; float d[4] = {WPT_INF, WPT_INF, WPT_INF, WPT_INF};
+      if (nc > 0) { id[0] = ch.x; d[0] = box_hit_x4(x0.x, y0.x, z0.x, x1.x, y1.x, z1.x, ray); }
+      if (nc > 1) { id[1] = ch.y; d[1] = box_hit_x4(x0.y, y0.y, z0.y, x1.y, y1.y, z1.y, ray); }
+      if (nc > 2) { id[2] = ch.z; d[2] = box_hit_x4(x0.z, y0.z, z0.z, x1.z, y1.z, z1.z, ray); }
+      if (nc > 3) { id[3] = ch.w; d[3] = box_hit_x4(x0.w, y0.w, z0.w, x1.w, y1.w, z1.w, ray); }
+      sort_small(id, d, nc);
+#pragma unroll
+      for (int i = 3; i >= 0; i--)
+        if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > bound)) { stack_n[sp] = (uint32_t)id[i]; stack_d[sp] = d[i]; sp++; }
+    }
+    bool found = false;
+    while (sp > 0) {
+      sp--;
+      if (stack_d[sp] > bound) continue;
+      node = (int)stack_n[sp];
+      found = true;
+      break;
+    }
+    if (!found) return;
+  }
+}
+
+WPT_DEV GHit trace_g(const DScene& sc, const Ray& ray) {
+  // trace_shapes over the infinite shapes (scene.rs:426-445): first hit accepted as is
+  bool have = false; float it = 0.0f; int iid = -1;
+  for (uint32_t i = 0; i < sc.num_inf; i++) {
+    float t;
+    if (shape_trace_simple(sc.shapes, i, ray, have ? it : WPT_INF, have, &t)) { have = true; it = t; iid = (int)i; }
+  }
+  float bound = have ? it : WPT_INF;
+  int bid = -1;
+  uint32_t visits = 0;
+  uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
+  if (sc.bvh_kind == 4) traverse_bvh4(sc, ray, bound, bid, visits, stack_n, stack_d);
+  else traverse_bvh2(sc, ray, bound, bid, visits, stack_n, stack_d);
+  GHit g;
+  g.visits = visits;
+  // closest (scene.rs:406-422): the BVH hit wins unless the plane hit is strictly closer. Any
+  // BVH hit satisfies t <= plane distance, so it wins whenever it exists.
+  if (bid >= 0) { g.t = bound; g.id = bid; }
+  else { g.t = it; g.id = iid; }
+  return g;
+}
+
+}  // namespace wpt

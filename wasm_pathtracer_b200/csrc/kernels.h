@@ -1,0 +1,58 @@
+// Launch wrappers for the sm_100a kernels (kernels.cu). Plain structs and pointers only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "wpt_types.h"
+
+namespace wpt {
+
+// slot flags (PathState::misc.z)
+enum : uint32_t { SL_ACTIVE = 1, SL_BOUNCED = 2, SL_SHADOW = 4, SL_TAIL = 8, SL_DONE = 16, SL_FRESH = 32 };
+
+// Wavefront state, SoA over slots. One slot owns one pixel and runs that pixel's samples
+// one after the other (path regeneration), so per-pixel accumulation order is the sample
+// order — bit-exact against the oracle and independent of scheduling.
+struct PathState {
+  float4* ray_o;      // origin.xyz, throughput.x
+  float4* ray_d;      // dir.xyz,    throughput.y
+  float4* col;        // colour.xyz, throughput.z
+  uint4* misc;        // rng state, current sample index, flags, end sample index
+  float2* hit;        // t, bits(shape id)  (id < 0: miss)
+  float4* sh_o;       // shadow-ray origin.xyz, distance to the light point
+  float4* sh_d;       // shadow-ray dir.xyz, bits(light shape id)
+  float4* sh_c;       // contribution if unoccluded .xyz, bits(occluded) written by the trace kernel
+  float4* tail;       // colour of a finished path that still waits for its last shadow ray
+  uint32_t* pixel;    // viewport pixel index (y * W + x) of the slot
+  uint32_t n;         // number of slots
+};
+
+struct RenderParams {
+  DScene scene;
+  DCamera cam;
+  DPhotonTree photons;
+  uint32_t W, H;
+  uint32_t render_type;    // 0 NoNEE, 1 NormalNEE, 2 PNEE
+  uint32_t light_debug;
+  uint32_t base_seed;
+};
+
+// counters[0] = rays, [1] = node visits, [2] = paths finished (u64 each)
+struct WaveBuffers {
+  uint32_t* shadow_q[2];      // slot indices with a shadow ray this iteration (double buffered)
+  uint32_t* shadow_n;         // [2] queue lengths
+  uint32_t* active_ring;      // [64] live-slot count per iteration (ring)
+  unsigned long long* counters;
+  float4* accum;              // per pixel: rgb sums, bits(sample count)
+};
+
+void launch_setup_slots(const PathState& st, const uint32_t* spp_per_slot, uint32_t uniform_spp, const float4* accum, cudaStream_t s);
+void launch_trace(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
+void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
+void launch_resolve_rgba(const float4* accum, uint8_t* rgba, uint32_t n, cudaStream_t s);
+void launch_primary_probe(const RenderParams& rp, int32_t* ids, uint32_t* visits, float* dist, cudaStream_t s);
+void launch_trace_batch(const RenderParams& rp, const float* o, const float* d, uint64_t n, int32_t* ids, float* dist, uint32_t* visits, float* normals, cudaStream_t s);
+void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t rank, uint32_t world, cudaStream_t s);
+
+int device_sm_count();
+
+}  // namespace wpt

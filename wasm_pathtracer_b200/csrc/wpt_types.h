@@ -1,0 +1,73 @@
+// Device data layout shared by the host flattener and the CUDA kernels.
+// Everything is laid out for 128-bit (__ldg float4) fetches; see DESIGN.md "Data layout".
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>
+
+namespace wpt {
+
+// src/math/mod.rs:11
+#define WPT_EPSILON 0.0002f
+#define WPT_PI 3.14159265358979323846f
+
+enum ShapeType : uint32_t { SH_TRIANGLE = 0, SH_PLANE = 1, SH_TORUS = 2, SH_AARECT = 3 };
+
+// BVH2 node, 32 B like the reference's BVHNode (bvh.rs:14-20); siblings are adjacent so the
+// two child boxes tested at scene.rs:242-243 are one 64 B fetch.
+//   a = (x_min, y_min, z_min, x_max)   b = (y_max, z_max, bits(left_first), bits(count))
+struct DNode2 { float4 a, b; };
+
+// BVH4 node, 128 B = one cache line like BVHNode4 (bvh4.rs:17-26), SoA lanes.
+struct DNode4 {
+  float4 x_min, y_min, z_min, x_max, y_max, z_max;
+  int4 children;          // >= 0 inner node index; < 0 leaf code (bit31, count<<27, first)
+  uint32_t num_children, pad0, pad1, pad2;
+};
+
+// Shape record, 64 B. meta = type | (material index << 8)
+//   triangle: q0=(v0, meta) q1=(v1, n.x) q2=(v2, n.y) q3=(n.z, nn.x, nn.y, nn.z)
+//             n = (v1-v0)x(v2-v0) un-normalised, nn = n.normalize()   (triangle.rs:164,182)
+//   plane   : q0=(location, meta) q1=(normal, normal.location)        (plane.rs:80-99)
+//   torus   : q0=(location, meta) q1=(big_r, small_r, 0, 0)           (torus.rs:11-16)
+//   aa_rect : q0=(x_min,y_min,z_min, meta) q1=(x_max,y_max,z_max,0)   (aa_rect.rs:8-16)
+struct DShape { float4 q0, q1, q2, q3; };
+
+// Material (material.rs:16-20): c = (r,g,b, emissive ? 1 : 0); r,g,b = colour or intensity
+struct DMaterial { float4 c; };
+
+// Area light = emissive triangle (scene.rs:62-66): shape index, Heron area (triangle.rs:70-78),
+// unit normal (triangle.rs:104) and intensity.
+struct DLight {
+  float4 n_area;      // normal.xyz, area
+  float4 intensity;   // rgb, bits(shape index)
+};
+
+struct DCamera {
+  float ox, oy, oz;
+  float cx, sx, cy, sy;     // cos/sin of rot_x, rot_y — evaluated once on the host (vec3.rs:95-119)
+  float w_inv, h_inv, ar;   // tracer.rs:163-172
+};
+
+// Flattened photon octree (photon_tree.rs). Node i: child_base[i] = index of its first child
+// (8 children contiguous, octant order) or 0xFFFFFFFF for a leaf; cum[i*L .. i*L+L) = CDF.
+struct DPhotonTree {
+  const uint32_t* child_base;
+  const float* cum;
+  uint32_t num_lights;
+  uint32_t num_nodes;
+};
+
+struct DScene {
+  const DNode2* nodes2;
+  const DNode4* nodes4;
+  const DShape* shapes;
+  const DMaterial* mats;
+  const DLight* lights;
+  uint32_t num_inf, num_shapes, num_lights, bvh_kind;
+  float bg_r, bg_g, bg_b, pad;
+};
+
+// xorshift32 stream contract (DESIGN.md "RNG contract")
+enum : uint32_t { STREAM_PATH = 1, STREAM_PHOTON = 2, STREAM_PIXEL = 3 };
+
+}  // namespace wpt

@@ -162,6 +162,19 @@ int wpt_ctx_photon_sample(wpt_ctx* ctx, const float* pts3, const uint32_t* seeds
 int wpt_ctx_error_map(wpt_ctx* ctx, float* mse, float stats3[3]);
 int wpt_ctx_round_spp(wpt_ctx* ctx, uint32_t* spp);
 
+/* Use an externally owned CUDA stream (e.g. torch's current stream) for all GPU work of
+ * this session; 0 restores the session's own stream. */
+int wpt_ctx_set_stream(wpt_ctx* ctx, uint64_t cuda_stream);
+/* Re-send the flattened scene (nodes, shapes, materials, lights) from pinned host memory to
+ * the device; returns the bytes copied. Lets a caller time host->device traffic honestly. */
+int64_t wpt_ctx_upload_scene(wpt_ctx* ctx);
+/* Per-launch CUDA-event timing of the wavefront kernels. After wpt_ctx_profile(ctx, 1):
+ * out[0]=trace-kernel ms, [1]=trace launches, [2]=shade-kernel ms, [3]=shade launches,
+ * [4]=leaf primitive tests, [5]=rays, [6]=node visits, [7]=reserved — accumulated since the
+ * last wpt_ctx_profile call. */
+int wpt_ctx_profile(wpt_ctx* ctx, int enable);
+int wpt_ctx_profile_read(wpt_ctx* ctx, double out[8]);
+
 /* Device pointers for zero-copy collectives (multi-GPU plumbing lives above this ABI). */
 int wpt_ctx_device_buffers(wpt_ctx* ctx, uint64_t ptrs[8], uint64_t sizes[8]);
 /* After an external exchange wrote other ranks' rows into the accumulators / RGBA buffer. */

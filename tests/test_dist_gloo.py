@@ -1,0 +1,56 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: row partition + framebuffer exchange."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, H, W_, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wasm_pathtracer_b200.dist import exchange_rows, rows_of_rank
+    frame = torch.zeros((H, W_, 4), dtype=torch.float32)
+    for y in rows_of_rank(H, rank, world):
+        frame[y] = float(rank + 1) * 1000 + y
+    exchange_rows(frame, rank, world)
+    q.put((rank, frame.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(world, H):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, H, 5, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs: p.join(60)
+    want = np.zeros((H, 5, 4), np.float32)
+    for y in range(H):
+        want[y] = float(y % world + 1) * 1000 + y
+    for r in range(world):
+        assert np.array_equal(res[r], want)
+
+
+def test_exchange_rows_even():
+    _run(2, 8)
+
+
+def test_exchange_rows_ragged():
+    _run(2, 7)     # odd height: rank 0 owns one more row than rank 1
+
+
+def test_rows_of_rank_cover_the_region():
+    from wasm_pathtracer_b200.dist import rows_of_rank
+    for H in (1, 7, 1080):
+        for world in (1, 2, 3, 8):
+            rows = sorted(sum((rows_of_rank(H, r, world, 10) for r in range(world)), []))
+            assert rows == list(range(10, 10 + H))

@@ -99,6 +99,10 @@ def load_library():
         "wpt_ctx_error_map": (i32, [vp, P(f32), P(f32)]),
         "wpt_ctx_round_spp": (i32, [vp, P(u32)]),
         "wpt_ctx_device_buffers": (i32, [vp, P(u64), P(u64)]),
+        "wpt_ctx_set_stream": (i32, [vp, u64]),
+        "wpt_ctx_upload_scene": (C.c_int64, [vp]),
+        "wpt_ctx_profile": (i32, [vp, i32]),
+        "wpt_ctx_profile_read": (i32, [vp, P(C.c_double)]),
         "wpt_ctx_mark_accum_dirty": (i32, [vp]),
         "wpt_ctx_load_obj": (C.c_int64, [vp, u32, C.c_char_p, i32]),
         "wpt_parse_obj": (C.c_int64, [C.c_char_p, u64, i32, P(f32), u64]),
@@ -333,6 +337,21 @@ class PathTracer:
         ptrs = np.zeros(8, np.uint64); sizes = np.zeros(8, np.uint64)
         self._chk(self.L.wpt_ctx_device_buffers(self.h, _p(ptrs, C.c_uint64), _p(sizes, C.c_uint64)))
         return dict(accum=(int(ptrs[0]), int(sizes[0])), rgba=(int(ptrs[1]), int(sizes[1])), sampling=(int(ptrs[2]), int(sizes[2])), stream=int(ptrs[3]))
+
+    def set_stream(self, cuda_stream):
+        self._chk(self.L.wpt_ctx_set_stream(self.h, int(cuda_stream)))
+
+    def upload_scene(self):
+        return self._chk(self.L.wpt_ctx_upload_scene(self.h))
+
+    def profile(self, enable=True):
+        self._chk(self.L.wpt_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        out = np.zeros(8, np.float64)
+        self._chk(self.L.wpt_ctx_profile_read(self.h, _p(out, C.c_double)))
+        return dict(trace_ms=out[0], trace_launches=int(out[1]), shade_ms=out[2], shade_launches=int(out[3]),
+                    prim_tests=int(out[4]), rays=int(out[5]), node_visits=int(out[6]))
 
     def mark_accum_dirty(self):
         self._chk(self.L.wpt_ctx_mark_accum_dirty(self.h))

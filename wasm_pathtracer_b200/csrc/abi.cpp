@@ -268,6 +268,22 @@ int wpt_ctx_photon_sample(wpt_ctx* ctx, const float* pts3, const uint32_t* seeds
 int wpt_ctx_error_map(wpt_ctx* ctx, float* mse, float stats3[3]) { return guard([&] { C(ctx)->error_map(mse, stats3); }); }
 int wpt_ctx_round_spp(wpt_ctx* ctx, uint32_t* spp) { return guard([&] { C(ctx)->round_spp(spp); }); }
 
+int wpt_ctx_set_stream(wpt_ctx* ctx, uint64_t cuda_stream) {
+  return guard([&] {
+    Context* c = C(ctx);
+    c->require_device();
+    WPT_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>((uintptr_t)cuda_stream) : c->own_stream;
+  });
+}
+int64_t wpt_ctx_upload_scene(wpt_ctx* ctx) {
+  int64_t n = -1;
+  guard([&] { n = C(ctx)->reupload_scene(); });
+  return n;
+}
+int wpt_ctx_profile(wpt_ctx* ctx, int enable) { return guard([&] { C(ctx)->set_profiling(enable != 0); }); }
+int wpt_ctx_profile_read(wpt_ctx* ctx, double out[8]) { return guard([&] { C(ctx)->profile_read(out); }); }
+
 int wpt_ctx_device_buffers(wpt_ctx* ctx, uint64_t ptrs[8], uint64_t sizes[8]) {
   return guard([&] {
     Context* c = C(ctx);

@@ -26,7 +26,8 @@ Context::Context(int dev, uint32_t w, uint32_t h, uint32_t sid, const float cam5
   if (dev < 0) WPT_CUDA(cudaGetDevice(&dev));
   device = dev;
   WPT_CUDA(cudaSetDevice(device));
-  WPT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  WPT_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  stream = own_stream;
   W = w; H = h;
   std::memcpy(cam, cam5, sizeof cam);
   wpt_default_config(&cfg);
@@ -41,7 +42,11 @@ Context::Context(int dev, uint32_t w, uint32_t h, uint32_t sid, const float cam5
 Context::~Context() {
   if (!has_device) return;
   cudaSetDevice(device);
-  if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+  if (stream) cudaStreamSynchronize(stream);
+  for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto& e : ev_free) cudaEventDestroy(e);
+  if (own_stream) cudaStreamDestroy(own_stream);
+  if (h_scene_blob) cudaFreeHost(h_scene_blob);
   if (h_rgba) cudaFreeHost(h_rgba);
   if (h_sampling) cudaFreeHost(h_sampling);
   if (h_ring) cudaFreeHost(h_ring);
@@ -74,6 +79,9 @@ void Context::clear_targets() {   // RenderTarget::clear / new, render_target.rs
 void Context::reset() {   // wasm_interface.rs:137-148
   if (!has_device) return;
   clear_targets();
+  unsigned long long now[4];
+  read_counters(now);
+  for (int i = 0; i < 4; i++) life[i] += now[i];
   WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 8 * sizeof(unsigned long long), stream));
   iterations = launches = 0;
   photons_shot_total = photons_stored_total = 0;
@@ -100,8 +108,67 @@ void Context::upload_scene() {
   std::vector<DNode2> n2; std::vector<DNode4> n4; std::vector<DShape> shp; std::vector<DMaterial> mats; std::vector<DLight> lights;
   flatten_scene(scene, n2, n4, shp, mats, lights);
   WPT_CUDA(cudaStreamSynchronize(stream));   // nothing may still read the old buffers
-  d_nodes2.upload(n2, stream); d_nodes4.upload(n4, stream); d_shapes.upload(shp, stream); d_mats.upload(mats, stream); d_lights.upload(lights, stream);
-  WPT_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
+  // keep one pinned host blob of the flattened scene: [nodes2 | nodes4 | shapes | mats | lights]
+  const void* src[5] = {n2.data(), n4.data(), shp.data(), mats.data(), lights.data()};
+  size_t len[5] = {n2.size() * sizeof(DNode2), n4.size() * sizeof(DNode4), shp.size() * sizeof(DShape), mats.size() * sizeof(DMaterial), lights.size() * sizeof(DLight)};
+  size_t total = 0;
+  for (int i = 0; i < 5; i++) { blob_off[i] = total; blob_len[i] = len[i]; total += (len[i] + 255) & ~(size_t)255; }
+  if (h_scene_blob) { cudaFreeHost(h_scene_blob); h_scene_blob = nullptr; }
+  WPT_CUDA(cudaMallocHost(&h_scene_blob, total ? total : 256));
+  h_scene_bytes = total;
+  for (int i = 0; i < 5; i++) if (len[i]) std::memcpy((char*)h_scene_blob + blob_off[i], src[i], len[i]);
+  d_nodes2.alloc(n2.size()); d_nodes4.alloc(n4.size()); d_shapes.alloc(shp.size()); d_mats.alloc(mats.size()); d_lights.alloc(lights.size());
+  reupload_scene();
+  WPT_CUDA(cudaStreamSynchronize(stream));
+}
+
+int64_t Context::reupload_scene() {
+  require_device();
+  void* dst[5] = {d_nodes2.p, d_nodes4.p, d_shapes.p, d_mats.p, d_lights.p};
+  int64_t bytes = 0;
+  for (int i = 0; i < 5; i++)
+    if (blob_len[i]) { WPT_CUDA(cudaMemcpyAsync(dst[i], (char*)h_scene_blob + blob_off[i], blob_len[i], cudaMemcpyHostToDevice, stream)); bytes += (int64_t)blob_len[i]; }
+  return bytes;
+}
+
+void Context::read_counters(unsigned long long out[4]) {
+  WPT_CUDA(cudaMemcpyAsync(h_counters, w_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaStreamSynchronize(stream));
+  for (int i = 0; i < 4; i++) out[i] = h_counters[i];
+}
+
+cudaEvent_t Context::ev_get() {
+  if (!ev_free.empty()) { cudaEvent_t e = ev_free.back(); ev_free.pop_back(); return e; }
+  cudaEvent_t e;
+  WPT_CUDA(cudaEventCreate(&e));
+  return e;
+}
+void Context::ev_harvest() {   // call after a stream synchronize
+  for (auto& p : ev_pending) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { prof_ms[p.kind] += ms; prof_n[p.kind]++; }
+    ev_free.push_back(p.a); ev_free.push_back(p.b);
+  }
+  ev_pending.clear();
+}
+void Context::set_profiling(bool on) {
+  require_device();
+  WPT_CUDA(cudaStreamSynchronize(stream));
+  ev_harvest();
+  profiling = on;
+  prof_ms[0] = prof_ms[1] = 0; prof_n[0] = prof_n[1] = 0;
+  read_counters(prof_base);
+  for (int i = 0; i < 4; i++) prof_base[i] += life[i];
+}
+void Context::profile_read(double out[8]) {
+  require_device();
+  WPT_CUDA(cudaStreamSynchronize(stream));
+  ev_harvest();
+  unsigned long long now[4];
+  read_counters(now);
+  for (int i = 0; i < 4; i++) now[i] += life[i];
+  out[0] = prof_ms[0]; out[1] = (double)prof_n[0]; out[2] = prof_ms[1]; out[3] = (double)prof_n[1];
+  out[4] = (double)(now[3] - prof_base[3]); out[5] = (double)(now[0] - prof_base[0]); out[6] = (double)(now[1] - prof_base[1]); out[7] = 0;
 }
 
 RenderParams Context::params(uint32_t render_type) const {
@@ -179,12 +246,24 @@ void Context::run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot
   for (;;) {
     for (uint32_t k = 0; k < poll; k++) {
       iter++;
-      launch_trace(rp, st, wb, iter, grid, stream);
-      launch_shade(rp, st, wb, iter, grid, stream);
+      if (profiling) {
+        EvPair t{ev_get(), ev_get(), 0}, sh{ev_get(), ev_get(), 1};
+        WPT_CUDA(cudaEventRecord(t.a, stream));
+        launch_trace(rp, st, wb, iter, grid, stream);
+        WPT_CUDA(cudaEventRecord(t.b, stream));
+        WPT_CUDA(cudaEventRecord(sh.a, stream));
+        launch_shade(rp, st, wb, iter, grid, stream);
+        WPT_CUDA(cudaEventRecord(sh.b, stream));
+        ev_pending.push_back(t); ev_pending.push_back(sh);
+      } else {
+        launch_trace(rp, st, wb, iter, grid, stream);
+        launch_shade(rp, st, wb, iter, grid, stream);
+      }
       launches += 2;
     }
     WPT_CUDA(cudaMemcpyAsync(h_ring, w_ring.p, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     WPT_CUDA(cudaStreamSynchronize(stream));
+    if (profiling) ev_harvest();
     if (h_ring[iter & 63u] == 0) break;
   }
   iterations += iter;

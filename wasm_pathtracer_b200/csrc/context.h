@@ -40,7 +40,8 @@ struct Context {
   int device = 0;
   bool has_device = true;                  // false: host-only session (scene / BVH inspection)
   void require_device() const { if (!has_device) throw CudaError("no CUDA device in a host-only session (libwpt has no CPU fallback)"); }
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // stream all work is issued on
+  cudaStream_t own_stream = nullptr;   // created by the session; `stream` may point elsewhere (set_stream)
   uint32_t W = 0, H = 0, scene_id = 0;
   float cam[5] = {0, 0, 0, 0, 0};
   wpt_config cfg;
@@ -85,6 +86,25 @@ struct Context {
   uint64_t photon_shots = 0, photon_count = 0;
   std::vector<uint32_t> ph_light; std::vector<float> ph_loc, ph_w;     // host copies (read-backs)
   std::vector<uint32_t> pt_meta; std::vector<float> pt_cum, pt_bins;   // flattened tree (read-backs)
+
+  // pinned host copies of the flattened scene (re-upload without rebuilding)
+  void* h_scene_blob = nullptr; size_t h_scene_bytes = 0;
+  size_t blob_off[5] = {0, 0, 0, 0, 0}, blob_len[5] = {0, 0, 0, 0, 0};
+  int64_t reupload_scene();
+
+  // per-launch event timing (bench / profiling)
+  bool profiling = false;
+  struct EvPair { cudaEvent_t a, b; int kind; };
+  std::vector<EvPair> ev_pending;
+  std::vector<cudaEvent_t> ev_free;
+  double prof_ms[2] = {0, 0}; uint64_t prof_n[2] = {0, 0};
+  unsigned long long prof_base[4] = {0, 0, 0, 0};
+  unsigned long long life[4] = {0, 0, 0, 0};   // counters folded in by reset()
+  void read_counters(unsigned long long out[4]);
+  cudaEvent_t ev_get();
+  void ev_harvest();
+  void set_profiling(bool on);
+  void profile_read(double out[8]);
 
   // counters since the last reset
   uint64_t iterations = 0, launches = 0, photons_shot_total = 0, photons_stored_total = 0;

@@ -367,11 +367,12 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
 }
 
 // ------------------------------------------------------------------ Scene::trace_g (scene.rs:162-184)
-struct GHit { float t; int id; uint32_t visits; };
+struct GHit { float t; int id; uint32_t visits; uint32_t prims; };
 
 // trace_shapes_md over a leaf (scene.rs:450-472); updates (best_t, best_id) if the leaf
 // reports a hit — a later leaf wins exact ties because the test is t <= max_dis.
-WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const Ray& ray, float& bound, int& best_id) {
+WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const Ray& ray, float& bound, int& best_id, uint32_t& prims) {
+  prims += count;
   bool have = false; float bt = 0.0f; uint32_t bi = 0;
   for (uint32_t i = 0; i < count; i++) {
     float t;
@@ -383,7 +384,7 @@ WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const R
 // traverse_bvh_guarded + traverse_bvh (scene.rs:191-288), iterative with an explicit stack of
 // (node, entry distance): a popped node is skipped iff the current bound is < its entry
 // distance — exactly the `lshape_dis < right_dis` early-outs of the recursion.
-WPT_DEV void traverse_bvh2(const DScene& sc, const Ray& ray, float& bound, int& best_id, uint32_t& visits, uint32_t* stack_n, float* stack_d) {
+WPT_DEV void traverse_bvh2(const DScene& sc, const Ray& ray, float& bound, int& best_id, uint32_t& visits, uint32_t& prims, uint32_t* stack_n, float* stack_d) {
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
   float4 ra = __ldg(nodes), rb = __ldg(nodes + 1);
   visits += 1;   // the root guard (scene.rs:207,210)
@@ -394,7 +395,7 @@ WPT_DEV void traverse_bvh2(const DScene& sc, const Ray& ray, float& bound, int& 
   for (;;) {
     visits += 1;
     if (cnt != 0) {
-      leaf_scan(sc, sc.num_inf + lf, cnt, ray, bound, best_id);
+      leaf_scan(sc, sc.num_inf + lf, cnt, ray, bound, best_id, prims);
     } else {
       const float4* c = nodes + (size_t)lf * 2;
       float4 la = __ldg(c), lb = __ldg(c + 1), qa = __ldg(c + 2), qb = __ldg(c + 3);
@@ -462,14 +463,14 @@ WPT_DEV void sort_small(int* id, float* d, uint32_t n) {
 // traverse_bvh4 (scene.rs:292-342), iterative: children are pushed in reverse sorted order; a
 // popped child is dropped iff its box distance is > the current bound, which is what the
 // recursion's early `return` does for it and all later (farther) siblings.
-WPT_DEV void traverse_bvh4(const DScene& sc, const Ray& ray, float& bound, int& best_id, uint32_t& visits, uint32_t* stack_n, float* stack_d) {
+WPT_DEV void traverse_bvh4(const DScene& sc, const Ray& ray, float& bound, int& best_id, uint32_t& visits, uint32_t& prims, uint32_t* stack_n, float* stack_d) {
   int sp = 0;
   int node = 0;
   for (;;) {
     visits += 1;
     if (node < 0) {
       uint32_t code = (uint32_t)node;
-      leaf_scan(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, bound, best_id);
+      leaf_scan(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, bound, best_id, prims);
     } else {
       const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + node);
       float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
@@ -506,12 +507,13 @@ WPT_DEV GHit trace_g(const DScene& sc, const Ray& ray) {
   }
   float bound = have ? it : WPT_INF;
   int bid = -1;
-  uint32_t visits = 0;
+  uint32_t visits = 0, prims = 0;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
-  if (sc.bvh_kind == 4) traverse_bvh4(sc, ray, bound, bid, visits, stack_n, stack_d);
-  else traverse_bvh2(sc, ray, bound, bid, visits, stack_n, stack_d);
+  if (sc.bvh_kind == 4) traverse_bvh4(sc, ray, bound, bid, visits, prims, stack_n, stack_d);
+  else traverse_bvh2(sc, ray, bound, bid, visits, prims, stack_n, stack_d);
   GHit g;
   g.visits = visits;
+  g.prims = prims;
   // closest (scene.rs:406-422): the BVH hit wins unless the plane hit is strictly closer. Any
   // BVH hit satisfies t <= plane distance, so it wins whenever it exists.
   if (bid >= 0) { g.t = bound; g.id = bid; }

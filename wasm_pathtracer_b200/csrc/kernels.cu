@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(RenderParams rp, PathSt
     wb.shadow_n[iter & 1u] = 0;                   // queue the next shade pass fills
     wb.active_ring[iter & 63u] = 0;
   }
-  unsigned long long rays = 0, visits = 0;
+  unsigned long long rays = 0, visits = 0, prims = 0;
   const uint32_t* __restrict__ sq = wb.shadow_q[qsel];
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     if (i < st.n) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(RenderParams rp, PathSt
       Ray ray = make_ray(xyz(o), xyz(d));
       GHit g = trace_g(rp.scene, ray);
       st.hit[i] = make_float2(g.t, __int_as_float(g.id));
-      rays += 1; visits += g.visits;
+      rays += 1; visits += g.visits; prims += g.prims;
     } else {
       uint32_t slot = sq[i - st.n];
       float4 o = st.sh_o[slot], d = st.sh_d[slot];
@@ -191,18 +191,19 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(RenderParams rp, PathSt
       // Scene::shadow_ray, scene.rs:114-132
       bool occluded = g.id >= 0 && g.t < o.w && g.id != __float_as_int(d.w);
       st.sh_c[slot].w = __uint_as_float(occluded ? 1u : 0u);
-      rays += 1; visits += g.visits;
+      rays += 1; visits += g.visits; prims += g.prims;
     }
   }
   rays = warp_sum_u64(rays);
   visits = warp_sum_u64(visits);
-  __shared__ unsigned long long s_r[TRACE_THREADS / 32], s_v[TRACE_THREADS / 32];
-  if ((threadIdx.x & 31) == 0) { s_r[threadIdx.x >> 5] = rays; s_v[threadIdx.x >> 5] = visits; }
+  prims = warp_sum_u64(prims);
+  __shared__ unsigned long long s_r[TRACE_THREADS / 32], s_v[TRACE_THREADS / 32], s_p[TRACE_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) { s_r[threadIdx.x >> 5] = rays; s_v[threadIdx.x >> 5] = visits; s_p[threadIdx.x >> 5] = prims; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long r = 0, v = 0;
-    for (int k = 0; k < TRACE_THREADS / 32; k++) { r += s_r[k]; v += s_v[k]; }
-    if (r) { atomicAdd(&wb.counters[0], r); atomicAdd(&wb.counters[1], v); }
+    unsigned long long r = 0, v = 0, pc = 0;
+    for (int k = 0; k < TRACE_THREADS / 32; k++) { r += s_r[k]; v += s_v[k]; pc += s_p[k]; }
+    if (r) { atomicAdd(&wb.counters[0], r); atomicAdd(&wb.counters[1], v); atomicAdd(&wb.counters[3], pc); }
   }
 }
 void launch_trace(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s) {

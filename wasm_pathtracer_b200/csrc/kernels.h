@@ -36,7 +36,7 @@ struct RenderParams {
   uint32_t base_seed;
 };
 
-// counters[0] = rays, [1] = node visits, [2] = paths finished (u64 each)
+// counters[0] = rays, [1] = node visits, [2] = paths finished, [3] = leaf primitive tests (u64 each)
 struct WaveBuffers {
   uint32_t* shadow_q[2];      // slot indices with a shadow ray this iteration (double buffered)
   uint32_t* shadow_n;         // [2] queue lengths

@@ -1,0 +1,57 @@
+"""One process per GPU: row partition + framebuffer exchange over torch.distributed.
+
+The reference splits work by pixels (README.md:87: WebWorkers with pixel subsets; today a
+left/right viewport split, src/wasm_interface.rs:78). Here rank r of `world` renders the
+rows y with (y - region_y) % world == r; paths are independent given the scene replica, so
+the only data-path exchange is the accumulator all-gather below (plus the photon and
+adaptive reductions in `DistributedPathTracer`). Collectives run on the session's stream.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def rows_of_rank(height, rank, world, y0=0):
+    """Viewport rows owned by `rank` (interleaved)."""
+    return list(range(y0 + rank, y0 + height, world))
+
+
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, shape, dtype=torch.float32):
+    typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.uint32: "<u4", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device="cuda")
+
+
+def exchange_rows(frame, rank, world, group=None):
+    """All-gather interleaved rows of `frame` ((H, ...) tensor, CPU or CUDA) in place.
+
+    On entry rank r holds valid data in rows r, r + world, ...; on exit every rank holds all rows.
+    """
+    if world == 1:
+        return frame
+    H = frame.shape[0]
+    per = (H + world - 1) // world
+    mine = frame[rank::world]
+    send = torch.zeros((per,) + tuple(frame.shape[1:]), dtype=frame.dtype, device=frame.device)
+    send[: mine.shape[0]] = mine
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    for r in range(world):
+        n = frame[r::world].shape[0]
+        frame[r::world] = recv[r][:n]
+    return frame
+
+
+def allgather_rows(pt, rank, world, group=None):
+    """Exchange the accumulators (rgb sums + sample counts) of a PathTracer session."""
+    ptr, _ = pt.device_buffers()["accum"]
+    acc = device_tensor(ptr, (pt.H, pt.W, 4), torch.float32)
+    exchange_rows(acc, rank, world, group)
+    pt.mark_accum_dirty()
+    return acc

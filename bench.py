@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--bvh", type=int, default=2)
+    ap.add_argument("--engine", type=int, default=0, help="0 = persistent path kernel, 1 = multi-kernel wavefront")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -166,7 +167,7 @@ def main():
     verts = W.parse_obj(open(mesh_path()).read(), True)
     pt = W.PathTracer(W_, H_, W.SCENE_BUNNY, *W.CAM_BUNNY, device=local)
     pt.store_mesh(W.api.MESH_BUNNY_HIGH, verts)
-    pt.set_config(bvh_kind=args.bvh, render_type=W.NORMAL_NEE, rank=rank, world=world)
+    pt.set_config(bvh_kind=args.bvh, render_type=W.NORMAL_NEE, rank=rank, world=world, engine=args.engine)
     stream = torch.cuda.current_stream()
     pt.set_stream(stream.cuda_stream)
     bufs = pt.device_buffers()
@@ -256,7 +257,7 @@ def main():
         alg_bytes = 32.0 * prof["node_visits"] + 36.0 * prof["prim_tests"] + (24.0 * 2 + 36 + 16) * prof["rays"]
         trace_s = prof["trace_ms"] * 1e-3
         achieved = alg_bytes / trace_s / 1e9 if trace_s > 0 else None
-        roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+        roofline = {"bound": "hbm", "kernel": "k_trace" if args.engine == 1 else "k_mega", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                     "traffic": None, "peak_source": peak_src,
                     "alg_bytes_per_launch": alg_bytes / max(1, prof["trace_launches"]), "avg_launch_ms": prof["trace_ms"] / max(1, prof["trace_launches"]),
                     "trace_share_of_step": prof["trace_ms"] / ms if ms else None, "shade_share_of_step": prof["shade_ms"] / ms if ms else None,
@@ -267,6 +268,7 @@ def main():
                 "data": "synthetic (procedural stand-in mesh, 81920 triangles; reference bunny2.obj is a stripped blob)",
                 "config": {"workload": "bunny scene, stand-in mesh 81920 tris, BVH%d 16 bins, 1920x1080, %d spp per GPU (%d total), NormalNEE, diffuse+emissive, mode-B per-path streams" % (args.bvh, args.spp, spp_total),
                            "partition": "rows interleaved over %d rank(s), NCCL all_gather of accumulators" % world,
+                           "engine": "persistent path kernel (k_mega)" if args.engine == 0 else "multi-kernel wavefront (k_trace + k_shade)",
                            "l2": "each step rewrites >300 MB of path state + accumulators (> 126 MB L2)"},
                 "mpaths_per_s": mpaths, "rays_per_step": rays_all, "paths_per_step": paths_all,
                 "roofline": roofline,

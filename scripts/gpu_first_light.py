@@ -8,9 +8,12 @@ import oracle_lib as O
 
 def bits(a): return np.ascontiguousarray(a).view(np.uint32)
 
+ENGINE = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+
 def check_scene(name, scene, cam, verts, w, h, bvh4, types, spp):
     print("==", name, "bvh4" if bvh4 else "bvh2", w, h)
     pt = W.PathTracer(w, h, scene, *cam, device=0)
+    pt.set_config(engine=ENGINE)
     orc = O.Oracle(w, h, scene, cam)
     if verts is not None:
         pt.store_mesh(1, verts); orc.load_mesh(1, verts)

@@ -25,7 +25,7 @@ class WptError(RuntimeError):
 class WptConfig(C.Structure):
     _fields_ = [("bvh_kind", C.c_uint32), ("render_type", C.c_uint32), ("light_debug", C.c_uint32), ("base_seed", C.c_uint32),
                 ("photon_target", C.c_uint64), ("region_x", C.c_uint32), ("region_y", C.c_uint32), ("region_w", C.c_uint32),
-                ("region_h", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("region_h", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32), ("engine", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 def library_path():

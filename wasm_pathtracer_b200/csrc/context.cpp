@@ -33,7 +33,7 @@ Context::Context(int dev, uint32_t w, uint32_t h, uint32_t sid, const float cam5
   wpt_default_config(&cfg);
   WPT_CUDA(cudaMallocHost((void**)&h_ring, 64 * sizeof(uint32_t)));
   WPT_CUDA(cudaMallocHost((void**)&h_counters, 8 * sizeof(unsigned long long)));
-  w_shadow_n.alloc(2); w_ring.alloc(64); w_counters.alloc(8);
+  w_shadow_n.alloc(2); w_ring.alloc(64); w_counters.alloc(8); w_work.alloc(4);
   WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 8 * sizeof(unsigned long long), stream));
   alloc_targets();
   select_scene(sid);
@@ -270,12 +270,37 @@ void Context::run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot
   rgba_stale = true;
 }
 
+// The persistent engine: one launch renders every requested sample of every slot.
+void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp) {
+  require_device();
+  if (!slots) return;
+  if (render_type == WPT_PNEE && !photons_ready) throw std::runtime_error("photon tree not built");
+  MegaParams P{};
+  P.rp = params(render_type);
+  P.accum = d_accum.p; P.pixel = s_pixel.p; P.spp_per_slot = d_spp_per_slot; P.uniform_spp = uniform_spp; P.nslots = slots;
+  P.work_counter = w_work.p; P.counters = w_counters.p;
+  WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
+  cudaEvent_t a = nullptr, b = nullptr;
+  if (profiling) { a = ev_get(); b = ev_get(); WPT_CUDA(cudaEventRecord(a, stream)); }
+  launch_mega(P, 4, stream);
+  if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
+  WPT_CUDA(cudaGetLastError());
+  launches += 1; iterations += 1;
+  rgba_stale = true;
+}
+
+// cfg.engine: 0 = persistent kernel (default), 1 = multi-kernel wavefront
+void Context::run_paths(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp) {
+  if (cfg.engine == 1) run_wavefront(render_type, d_spp_per_slot, uniform_spp);
+  else run_persistent(render_type, d_spp_per_slot, uniform_spp);
+}
+
 void Context::render_exact(uint32_t spp) {
   require_device();
   uint32_t rx, ry, rw, rh;
   region(&rx, &ry, &rw, &rh);
   ensure_slots(rx, ry, rw, rh);
-  run_wavefront(cfg.render_type, nullptr, spp);
+  run_paths(cfg.render_type, nullptr, spp);
 }
 
 const uint8_t* Context::results(uint32_t show_sampling) {   // wasm_interface.rs:120-134

@@ -72,7 +72,7 @@ struct Context {
   DevBuf<uint4> s_misc;
   DevBuf<float2> s_hit;
   DevBuf<uint32_t> s_pixel, s_spp;
-  DevBuf<uint32_t> w_shadow_q0, w_shadow_q1, w_shadow_n, w_ring;
+  DevBuf<uint32_t> w_shadow_q0, w_shadow_q1, w_shadow_n, w_ring, w_work;
   DevBuf<unsigned long long> w_counters;
   uint32_t* h_ring = nullptr;                 // pinned [64]
   unsigned long long* h_counters = nullptr;   // pinned [8]
@@ -125,6 +125,8 @@ struct Context {
 
   // drivers
   void run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp);
+  void run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp);
+  void run_paths(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp);   // engine switch
   void render_exact(uint32_t spp);
   uint64_t render_adaptive(uint64_t budget);
   void build_photons();

@@ -381,57 +381,24 @@ WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const R
   if (have) { bound = bt; best_id = (int)bi; }
 }
 
-// traverse_bvh_guarded + traverse_bvh (scene.rs:191-288), iterative with an explicit stack of
-// (node, entry distance): a popped node is skipped iff the current bound is < its entry
-// distance — exactly the `lshape_dis < right_dis` early-outs of the recursion.
-WPT_DEV void traverse_bvh2(const DScene& sc, const Ray& ray, float& bound, int& best_id, uint32_t& visits, uint32_t& prims, uint32_t* stack_n, float* stack_d) {
-  const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
-  float4 ra = __ldg(nodes), rb = __ldg(nodes + 1);
-  visits += 1;   // the root guard (scene.rs:207,210)
-  float h;
-  if (!(box_hit(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, ray, &h) && h < bound)) return;
-  int sp = 0;
-  uint32_t lf = __float_as_uint(rb.z), cnt = __float_as_uint(rb.w);
-  for (;;) {
-    visits += 1;
-    if (cnt != 0) {
-      leaf_scan(sc, sc.num_inf + lf, cnt, ray, bound, best_id, prims);
-    } else {
-      const float4* c = nodes + (size_t)lf * 2;
-      float4 la = __ldg(c), lb = __ldg(c + 1), qa = __ldg(c + 2), qb = __ldg(c + 3);
-      float dl, dr;
-      bool hl = box_hit(la.x, la.y, la.z, la.w, lb.x, lb.y, ray, &dl) && dl < bound;
-      if (!hl) {
-        // left misses: traverse_bvh_guarded(right) — counts the guard (scene.rs:283-286)
-        visits += 1;
-        bool hr = box_hit(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < bound;
-        if (hr) { lf = __float_as_uint(qb.z); cnt = __float_as_uint(qb.w); continue; }
-      } else {
-        bool hr = box_hit(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < bound;
-        if (!hr) { lf = __float_as_uint(lb.z); cnt = __float_as_uint(lb.w); continue; }
-        if (dl < dr) {   // left first; tie -> right first (scene.rs:244,261)
-          stack_n[sp] = lf + 1; stack_d[sp] = dr; sp++;
-          lf = __float_as_uint(lb.z); cnt = __float_as_uint(lb.w);
-        } else {
-          stack_n[sp] = lf; stack_d[sp] = dl; sp++;
-          lf = __float_as_uint(qb.z); cnt = __float_as_uint(qb.w);
-        }
-        continue;
-      }
-    }
-    // pop
-    bool found = false;
-    while (sp > 0) {
-      sp--;
-      if (bound < stack_d[sp]) continue;   // near hit closer than the far box: skip it
-      float4 nb = __ldg(nodes + (size_t)stack_n[sp] * 2 + 1);
-      lf = __float_as_uint(nb.z); cnt = __float_as_uint(nb.w);
-      found = true;
-      break;
-    }
-    if (!found) return;
-  }
-}
+// ------------------------------------------------------------------ resumable traversal
+// Scene::trace_g split into begin / step / result so that a persistent kernel can interleave
+// the traversal of different lanes (k_mega) while the wavefront kernel (k_trace) simply loops.
+//
+// BVH2: traverse_bvh_guarded + traverse_bvh (scene.rs:191-288), iterative with an explicit
+// stack of (node, entry distance): a popped node is skipped iff the current bound is < its
+// entry distance — exactly the `lshape_dis < right_dis` early-outs of the recursion.
+// BVH4: traverse_bvh4 (scene.rs:292-342): children are pushed in reverse sorted order; a popped
+// child is dropped iff its box distance is > the current bound, which is what the recursion's
+// early `return` does for it and for all later (farther) siblings.
+struct Trav {
+  uint32_t lf, cnt;      // BVH2: record of the node to enter next; BVH4: lf = node id / leaf code
+  int sp;                // stack size
+  float bound;           // min(plane hit, best BVH hit so far) = the recursion's max_dis
+  int best_id;           // best BVH hit (-1: none)
+  float inf_t; int inf_id;   // hit among the infinite shapes (scene.rs:168,176)
+  uint32_t visits, prims;
+};
 
 // scene.rs:346-388 — the exact compare-and-swap network (not stable for n == 4)
 WPT_DEV void sort_small(int* id, float* d, uint32_t n) {
@@ -460,65 +427,120 @@ WPT_DEV void sort_small(int* id, float* d, uint32_t n) {
 #undef WPT_SWAP
 }
 
-// traverse_bvh4 (scene.rs:292-342), iterative: children are pushed in reverse sorted order; a
-// popped child is dropped iff its box distance is > the current bound, which is what the
-// recursion's early `return` does for it and all later (farther) siblings.
-WPT_DEV void traverse_bvh4(const DScene& sc, const Ray& ray, float& bound, int& best_id, uint32_t& visits, uint32_t& prims, uint32_t* stack_n, float* stack_d) {
-  int sp = 0;
-  int node = 0;
-  for (;;) {
-    visits += 1;
-    if (node < 0) {
-      uint32_t code = (uint32_t)node;
-      leaf_scan(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, bound, best_id, prims);
-    } else {
-      const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + node);
-      float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
-      int4 ch = __ldg(reinterpret_cast<const int4*>(p + 6));
-      uint32_t nc = __ldg(reinterpret_cast<const uint32_t*>(p + 7));
-      int id[4] = {0, 0, 0, 0}; float d[4] = {WPT_INF, WPT_INF, WPT_INF, WPT_INF};
-      if (nc > 0) { id[0] = ch.x; d[0] = box_hit_x4(x0.x, y0.x, z0.x, x1.x, y1.x, z1.x, ray); }
-      if (nc > 1) { id[1] = ch.y; d[1] = box_hit_x4(x0.y, y0.y, z0.y, x1.y, y1.y, z1.y, ray); }
-      if (nc > 2) { id[2] = ch.z; d[2] = box_hit_x4(x0.z, y0.z, z0.z, x1.z, y1.z, z1.z, ray); }
-      if (nc > 3) { id[3] = ch.w; d[3] = box_hit_x4(x0.w, y0.w, z0.w, x1.w, y1.w, z1.w, ray); }
-      sort_small(id, d, nc);
-#pragma unroll
-      for (int i = 3; i >= 0; i--)
-        if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > bound)) { stack_n[sp] = (uint32_t)id[i]; stack_d[sp] = d[i]; sp++; }
-    }
-    bool found = false;
-    while (sp > 0) {
-      sp--;
-      if (stack_d[sp] > bound) continue;
-      node = (int)stack_n[sp];
-      found = true;
-      break;
-    }
-    if (!found) return;
-  }
-}
-
-WPT_DEV GHit trace_g(const DScene& sc, const Ray& ray) {
-  // trace_shapes over the infinite shapes (scene.rs:426-445): first hit accepted as is
+// trace_shapes over the infinite shapes + the root guard. Returns true if the BVH has to be
+// traversed (then call trav_step until it returns false).
+WPT_DEV bool trav_begin(const DScene& sc, const Ray& ray, Trav& tv) {
   bool have = false; float it = 0.0f; int iid = -1;
-  for (uint32_t i = 0; i < sc.num_inf; i++) {
+  for (uint32_t i = 0; i < sc.num_inf; i++) {   // scene.rs:426-445: first hit accepted as is
     float t;
     if (shape_trace_simple(sc.shapes, i, ray, have ? it : WPT_INF, have, &t)) { have = true; it = t; iid = (int)i; }
   }
-  float bound = have ? it : WPT_INF;
-  int bid = -1;
-  uint32_t visits = 0, prims = 0;
-  uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
-  if (sc.bvh_kind == 4) traverse_bvh4(sc, ray, bound, bid, visits, prims, stack_n, stack_d);
-  else traverse_bvh2(sc, ray, bound, bid, visits, prims, stack_n, stack_d);
+  tv.inf_t = it; tv.inf_id = iid;
+  tv.bound = have ? it : WPT_INF;
+  tv.best_id = -1;
+  tv.visits = 0; tv.prims = 0; tv.sp = 0;
+  if (sc.bvh_kind == 4) { tv.lf = 0u; tv.cnt = 0u; return true; }   // no root box test (scene.rs:292-342)
+  const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
+  float4 ra = __ldg(nodes), rb = __ldg(nodes + 1);
+  tv.visits = 1;   // the root guard (scene.rs:207,210)
+  float h;
+  if (!(box_hit(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, ray, &h) && h < tv.bound)) return false;
+  tv.lf = __float_as_uint(rb.z); tv.cnt = __float_as_uint(rb.w);
+  return true;
+}
+
+// Enter one BVH2 node. Returns false when the traversal is finished.
+WPT_DEV bool trav_step2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
+  tv.visits += 1;
+  if (tv.cnt != 0) {
+    leaf_scan(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
+  } else {
+    const float4* c = nodes + (size_t)tv.lf * 2;
+    float4 la = __ldg(c), lb = __ldg(c + 1), qa = __ldg(c + 2), qb = __ldg(c + 3);
+    float dl, dr;
+    bool hl = box_hit(la.x, la.y, la.z, la.w, lb.x, lb.y, ray, &dl) && dl < tv.bound;
+    bool hr = box_hit(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < tv.bound;
+    if (!hl) {
+      // left misses: traverse_bvh_guarded(right) — counts the guard (scene.rs:283-286)
+      tv.visits += 1;
+      if (hr) { tv.lf = __float_as_uint(qb.z); tv.cnt = __float_as_uint(qb.w); return true; }
+    } else if (!hr) {
+      tv.lf = __float_as_uint(lb.z); tv.cnt = __float_as_uint(lb.w); return true;
+    } else {
+      if (dl < dr) {   // left first; tie -> right first (scene.rs:244,261)
+        stack_n[tv.sp] = tv.lf + 1; stack_d[tv.sp] = dr; tv.sp++;
+        tv.lf = __float_as_uint(lb.z); tv.cnt = __float_as_uint(lb.w);
+      } else {
+        stack_n[tv.sp] = tv.lf; stack_d[tv.sp] = dl; tv.sp++;
+        tv.lf = __float_as_uint(qb.z); tv.cnt = __float_as_uint(qb.w);
+      }
+      return true;
+    }
+  }
+  while (tv.sp > 0) {   // pop
+    tv.sp--;
+    if (tv.bound < stack_d[tv.sp]) continue;   // near hit closer than the far box: skip it
+    float4 nb = __ldg(nodes + (size_t)stack_n[tv.sp] * 2 + 1);
+    tv.lf = __float_as_uint(nb.z); tv.cnt = __float_as_uint(nb.w);
+    return true;
+  }
+  return false;
+}
+
+// Enter one BVH4 node or leaf.
+WPT_DEV bool trav_step4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  int node = (int)tv.lf;
+  tv.visits += 1;
+  if (node < 0) {
+    uint32_t code = (uint32_t)node;
+    leaf_scan(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims);
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + node);
+    float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
+    int4 ch = __ldg(reinterpret_cast<const int4*>(p + 6));
+    uint32_t nc = __ldg(reinterpret_cast<const uint32_t*>(p + 7));
+    int id[4] = {0, 0, 0, 0}; float d[4] = {WPT_INF, WPT_INF, WPT_INF, WPT_INF};
+    if (nc > 0) { id[0] = ch.x; d[0] = box_hit_x4(x0.x, y0.x, z0.x, x1.x, y1.x, z1.x, ray); }
+    if (nc > 1) { id[1] = ch.y; d[1] = box_hit_x4(x0.y, y0.y, z0.y, x1.y, y1.y, z1.y, ray); }
+    if (nc > 2) { id[2] = ch.z; d[2] = box_hit_x4(x0.z, y0.z, z0.z, x1.z, y1.z, z1.z, ray); }
+    if (nc > 3) { id[3] = ch.w; d[3] = box_hit_x4(x0.w, y0.w, z0.w, x1.w, y1.w, z1.w, ray); }
+    sort_small(id, d, nc);
+#pragma unroll
+    for (int i = 3; i >= 0; i--)
+      if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) { stack_n[tv.sp] = (uint32_t)id[i]; stack_d[tv.sp] = d[i]; tv.sp++; }
+  }
+  while (tv.sp > 0) {
+    tv.sp--;
+    if (stack_d[tv.sp] > tv.bound) continue;
+    tv.lf = stack_n[tv.sp];
+    return true;
+  }
+  return false;
+}
+
+WPT_DEV bool trav_step(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  return sc.bvh_kind == 4 ? trav_step4(sc, ray, tv, stack_n, stack_d) : trav_step2(sc, ray, tv, stack_n, stack_d);
+}
+
+WPT_DEV GHit trav_result(const Trav& tv) {
   GHit g;
-  g.visits = visits;
-  g.prims = prims;
+  g.visits = tv.visits; g.prims = tv.prims;
   // closest (scene.rs:406-422): the BVH hit wins unless the plane hit is strictly closer. Any
   // BVH hit satisfies t <= plane distance, so it wins whenever it exists.
-  if (bid >= 0) { g.t = bound; g.id = bid; }
-  else { g.t = it; g.id = iid; }
+  if (tv.best_id >= 0) { g.t = tv.bound; g.id = tv.best_id; }
+  else { g.t = tv.inf_t; g.id = tv.inf_id; }
   return g;
+}
+
+WPT_DEV GHit trace_g(const DScene& sc, const Ray& ray) {
+  Trav tv;
+  uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
+  if (trav_begin(sc, ray, tv)) {
+    if (sc.bvh_kind == 4) { while (trav_step4(sc, ray, tv, stack_n, stack_d)) {} }
+    else { while (trav_step2(sc, ray, tv, stack_n, stack_d)) {} }
+  }
+  return trav_result(tv);
 }
 
 }  // namespace wpt

@@ -138,6 +138,83 @@ WPT_DEV void pick_random(const DScene& sc, uint32_t li, Rng& rng, F3* p, F3* n, 
   *n = nn; *intensity = xyz(in); *area = na.w; *shape_id = sid;
 }
 
+// ------------------------------------------------------------------ shading of one hit
+// One bounce of trace_original_color (tracer.rs:237-329) after Scene::trace returned shape
+// `id` (-1: miss) for `ray`. Shared by the wavefront shade kernel and the persistent kernel so
+// that both evaluate exactly the same f32 expressions in the same order.
+struct PathRegs { F3 color, T; Rng rng; bool bounced; };
+struct ShadeOut {
+  bool finished;     // path ended at this vertex (miss / emitter): `color` is final
+  bool survive;      // Russian roulette outcome (only meaningful if !finished)
+  bool shadow;       // a shadow ray has to be traced; `contrib` is added if it is unoccluded
+  F3 next_o, next_d; // the bounce ray
+  F3 sh_o, sh_d; float sh_len; int sh_light; F3 contrib;
+};
+WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, PathRegs& ps, ShadeOut& out) {
+  const bool has_nee = rp.render_type != 0;
+  out.finished = false; out.survive = false; out.shadow = false;
+  bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
+  if (id >= 0) some = shape_trace_full(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat);   // scene.rs:140
+  if (!some) {   // tracer.rs:325-328
+    ps.color = ps.color + ps.T * f3(rp.scene.bg_r, rp.scene.bg_g, rp.scene.bg_b);
+    out.finished = true;
+    return;
+  }
+  float4 mc = __ldg(&rp.scene.mats[mat].c);
+  F3 hit_point = ray.o + t * ray.d;
+  if (mc.w != 0.0f) {   // emissive, tracer.rs:245-254
+    if (rp.light_debug ? !ps.bounced : (!has_nee || !ps.bounced)) ps.color = ps.color + ps.T * xyz(mc);
+    out.finished = true;
+    return;
+  }
+  // material.rs:97-118 cosine-weighted bounce
+  float r1 = ps.rng.f32();
+  float r2 = ps.rng.f32();
+  float sa, ca;
+  shared_sincos(2.0f * WPT_PI * r1, &sa, &ca);
+  float x = ca * sqrtf(1.0f - r2);
+  float y = sqrtf(r2);
+  float z = sa * sqrtf(1.0f - r2);
+  F3 xn = orthogonal(n);
+  F3 zn = cross(n, xn);
+  F3 wi = normalize(x * xn + y * n + z * zn);
+  float pdf = dot(wi, n) / WPT_PI;
+  const float inv_pi = 1.0f / WPT_PI;   // Color3 / f32 = self * (1/v), clamped (color3.rs:54-95)
+  F3 brdf = f3(fminf(1.0f, fmaxf(0.0f, inv_pi * mc.x)), fminf(1.0f, fmaxf(0.0f, inv_pi * mc.y)), fminf(1.0f, fmaxf(0.0f, inv_pi * mc.z)));
+  float cos_i = dot(wi, n);
+  ps.T = ps.T * brdf * cos_i / pdf;   // tracer.rs:262
+  out.next_o = hit_point + wi * WPT_EPSILON;
+  out.next_d = wi;
+  ps.bounced = true;
+  if (has_nee) {   // tracer.rs:267-313
+    uint32_t light_id; float chance;
+    if (rp.render_type == 2) photon_sample(rp.photons, ps.rng, hit_point, &light_id, &chance);
+    else { light_id = ps.rng.range(0, rp.scene.num_lights); chance = 1.0f / (float)rp.scene.num_lights; }
+    F3 pl, ln, inten; float area; uint32_t lsid;
+    pick_random(rp.scene, light_id, ps.rng, &pl, &ln, &inten, &area, &lsid);
+    F3 to_light = pl - hit_point;
+    float dsq = dot(to_light, to_light);
+    float dlen = sqrtf(dsq);
+    to_light = to_light / dlen;
+    float cos_i2 = dot(to_light, n);
+    float cos_o = dot(-to_light, ln);
+    if (cos_i2 > 0.0f && cos_o > 0.0f) {
+      if (rp.light_debug) ps.color = ps.color + ps.T * inten;
+      else {
+        float solid_angle = (area * cos_o) / dsq;
+        out.contrib = ps.T * inten * solid_angle * cos_i2 * (1.0f / chance);
+        out.sh_o = hit_point + to_light * WPT_EPSILON;   // scene.rs:108
+        out.sh_d = to_light; out.sh_len = dlen; out.sh_light = (int)lsid;
+        out.shadow = true;
+      }
+    }
+  }
+  // Russian roulette, tracer.rs:318-324
+  float keep = fmaxf(fminf(fmaxf(fmaxf(ps.T.x, ps.T.y), ps.T.z), 0.9f), 0.1f);
+  out.survive = ps.rng.f32() < keep;
+  if (out.survive) ps.T = ps.T * (1.0f / keep);
+}
+
 // ------------------------------------------------------------------ slot setup
 __global__ void k_setup_slots(PathState st, const uint32_t* __restrict__ spp_per_slot, uint32_t uniform_spp, const float4* __restrict__ accum) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,7 +312,6 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(RenderParams rp, PathSt
       F3 color = xyz(cl);
       F3 T = f3(ro.w, rd.w, cl.w);
       Rng rng; rng.s = m.x;
-      const bool has_nee = rp.render_type != 0;
       // 1. last iteration's shadow ray (tracer.rs:299-308)
       if (flags & (SL_SHADOW | SL_TAIL)) {
         float4 c = st.sh_c[i];
@@ -254,79 +330,25 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(RenderParams rp, PathSt
       else {
         // 2. shade the extension hit
         float2 h = st.hit[i];
-        int id = __float_as_int(h.y);
         Ray ray = make_ray(xyz(ro), xyz(rd));
-        bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
-        if (id >= 0) some = shape_trace_full(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat);   // scene.rs:140
-        if (!some) {   // tracer.rs:325-328
-          color = color + T * f3(rp.scene.bg_r, rp.scene.bg_g, rp.scene.bg_b);
-          finished = true;
-        } else {
-          float4 mc = __ldg(&rp.scene.mats[mat].c);
-          F3 hit_point = ray.o + t * ray.d;
-          if (mc.w != 0.0f) {   // emissive, tracer.rs:245-254
-            bool bounced = flags & SL_BOUNCED;
-            if (rp.light_debug ? !bounced : (!has_nee || !bounced)) color = color + T * xyz(mc);
-            finished = true;
-          } else {
-            // material.rs:97-118 cosine-weighted bounce
-            float r1 = rng.f32();
-            float r2 = rng.f32();
-            float sa, ca;
-            shared_sincos(2.0f * WPT_PI * r1, &sa, &ca);
-            float x = ca * sqrtf(1.0f - r2);
-            float y = sqrtf(r2);
-            float z = sa * sqrtf(1.0f - r2);
-            F3 xn = orthogonal(n);
-            F3 zn = cross(n, xn);
-            F3 wi = normalize(x * xn + y * n + z * zn);
-            float pdf = dot(wi, n) / WPT_PI;
-            const float inv_pi = 1.0f / WPT_PI;   // Color3 / f32 = self * (1/v), clamped (color3.rs:54-95)
-            F3 brdf = f3(fminf(1.0f, fmaxf(0.0f, inv_pi * mc.x)), fminf(1.0f, fmaxf(0.0f, inv_pi * mc.y)), fminf(1.0f, fmaxf(0.0f, inv_pi * mc.z)));
-            float cos_i = dot(wi, n);
-            T = T * brdf * cos_i / pdf;   // tracer.rs:262
-            ro = make_float4(0, 0, 0, 0);
-            F3 no = hit_point + wi * WPT_EPSILON;
-            ro.x = no.x; ro.y = no.y; ro.z = no.z;
-            rd.x = wi.x; rd.y = wi.y; rd.z = wi.z;
-            flags |= SL_BOUNCED;
-            bool shadow = false;
-            if (has_nee) {   // tracer.rs:267-313
-              uint32_t light_id; float chance;
-              if (rp.render_type == 2) photon_sample(rp.photons, rng, hit_point, &light_id, &chance);
-              else { light_id = rng.range(0, rp.scene.num_lights); chance = 1.0f / (float)rp.scene.num_lights; }
-              F3 pl, ln, inten; float area; uint32_t lsid;
-              pick_random(rp.scene, light_id, rng, &pl, &ln, &inten, &area, &lsid);
-              F3 to_light = pl - hit_point;
-              float dsq = dot(to_light, to_light);
-              float dlen = sqrtf(dsq);
-              to_light = to_light / dlen;
-              float cos_i2 = dot(to_light, n);
-              float cos_o = dot(-to_light, ln);
-              if (cos_i2 > 0.0f && cos_o > 0.0f) {
-                if (rp.light_debug) color = color + T * inten;
-                else {
-                  float solid_angle = (area * cos_o) / dsq;
-                  F3 contrib = T * inten * solid_angle * cos_i2 * (1.0f / chance);
-                  F3 so = hit_point + to_light * WPT_EPSILON;   // scene.rs:108
-                  st.sh_o[i] = make_float4(so.x, so.y, so.z, dlen);
-                  st.sh_d[i] = make_float4(to_light.x, to_light.y, to_light.z, __int_as_float((int)lsid));
-                  st.sh_c[i] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
-                  shadow = true;
-                }
-              }
-            }
-            // Russian roulette, tracer.rs:318-324
-            float keep = fmaxf(fminf(fmaxf(fmaxf(T.x, T.y), T.z), 0.9f), 0.1f);
-            bool survive = rng.f32() < keep;
-            if (survive) T = T * (1.0f / keep);
-            if (shadow) {
-              uint32_t q = atomicAdd(&wb.shadow_n[iter & 1u], 1u);
-              wb.shadow_q[iter & 1u][q] = i;
-              if (survive) flags |= SL_SHADOW;
-              else { st.tail[i] = make_float4(color.x, color.y, color.z, 0.0f); flags |= SL_TAIL; need_regen = true; }
-            } else if (!survive) finished = true;
-          }
+        PathRegs ps; ps.color = color; ps.T = T; ps.rng = rng; ps.bounced = (flags & SL_BOUNCED) != 0;
+        ShadeOut so;
+        shade_hit(rp, ray, __float_as_int(h.y), ps, so);
+        color = ps.color; T = ps.T; rng = ps.rng;
+        if (so.finished) finished = true;
+        else {
+          ro.x = so.next_o.x; ro.y = so.next_o.y; ro.z = so.next_o.z;
+          rd.x = so.next_d.x; rd.y = so.next_d.y; rd.z = so.next_d.z;
+          flags |= SL_BOUNCED;
+          if (so.shadow) {
+            st.sh_o[i] = make_float4(so.sh_o.x, so.sh_o.y, so.sh_o.z, so.sh_len);
+            st.sh_d[i] = make_float4(so.sh_d.x, so.sh_d.y, so.sh_d.z, __int_as_float(so.sh_light));
+            st.sh_c[i] = make_float4(so.contrib.x, so.contrib.y, so.contrib.z, 0.0f);
+            uint32_t q = atomicAdd(&wb.shadow_n[iter & 1u], 1u);
+            wb.shadow_q[iter & 1u][q] = i;
+            if (so.survive) flags |= SL_SHADOW;
+            else { st.tail[i] = make_float4(color.x, color.y, color.z, 0.0f); flags |= SL_TAIL; need_regen = true; }
+          } else if (!so.survive) finished = true;
         }
       }
       if (finished) { acc.add(pix, color); paths_done++; need_regen = true; }
@@ -367,6 +389,124 @@ void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers
   (void)grid;
   if (!st.n) return;
   k_shade<<<(st.n + SHADE_THREADS - 1) / SHADE_THREADS, SHADE_THREADS, 0, s>>>(rp, st, wb, iter);
+}
+
+// ------------------------------------------------------------------ persistent path kernel
+// k_mega: the same path tracer as k_trace + k_shade, but the wavefront lives in registers.
+// Every lane owns one pixel at a time and runs its samples one after the other (so the
+// per-pixel accumulation order is the sample order, as in the wavefront engine); a lane is
+// always in one of two stages — LOGIC (consume a finished trace: shade / resolve the shadow
+// ray / finish the sample; generate the next camera ray; start the next trace with the plane
+// tests and the root guard) or TRAV (one BVH node per step). The warp votes with __ballot_sync
+// which stage to run: traversal bursts start when at least MEGA_T_HI lanes wait in TRAV (or no
+// lane has logic to do) and stop when fewer than MEGA_T_LO are left, then the idle lanes refill
+// themselves through LOGIC — the warp-ballot refill of Aila & Laine's persistent while-while
+// kernel. Rays that end at the root guard (most rays of the bunny scene) never enter a burst.
+#define MEGA_THREADS 128
+#ifndef MEGA_T_HI
+#define MEGA_T_HI 20
+#endif
+#ifndef MEGA_T_LO
+#define MEGA_T_LO 10
+#endif
+enum : int { PH_NEED = 0, PH_LOGIC = 1, PH_TRAV = 2, PH_DONE = 3 };
+enum : int { ST_GEN = 0, ST_EXTEND = 1, ST_SHADOW = 2 };
+
+__global__ void __launch_bounds__(MEGA_THREADS, 4) k_mega(MegaParams P) {
+  const DScene& sc = P.rp.scene;
+  uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
+  const unsigned FULL = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31u;
+  int phase = PH_NEED, what = ST_GEN;
+  uint32_t pix = 0, s = 0, s_end = 0;
+  PathRegs ps; ps.color = f3(0, 0, 0); ps.T = f3(1, 1, 1); ps.rng.s = 1u; ps.bounced = false;
+  Ray ray = make_ray(f3(0, 0, 0), f3(1, 1, 1));
+  Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0;
+  F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
+  float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
+  uint32_t c_rays = 0, c_visits = 0, c_prims = 0, c_paths = 0;
+  Accum acc{P.accum};
+
+  for (;;) {
+    // ---- pixel fetch: one atomic per warp
+    unsigned need = __ballot_sync(FULL, phase == PH_NEED);
+    if (need) {
+      uint32_t base = 0;
+      int leader = __ffs(need) - 1;
+      if ((int)lane == leader) base = atomicAdd(P.work_counter, (uint32_t)__popc(need));
+      base = __shfl_sync(FULL, base, leader);
+      if (phase == PH_NEED) {
+        uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+        if (idx < P.nslots) {
+          pix = P.pixel[idx];
+          uint32_t spp = P.spp_per_slot ? P.spp_per_slot[idx] : P.uniform_spp;
+          s = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
+          s_end = s + spp;
+          what = ST_GEN; phase = PH_LOGIC;
+        } else phase = PH_DONE;
+      }
+    }
+    unsigned trav = __ballot_sync(FULL, phase == PH_TRAV);
+    unsigned logic = __ballot_sync(FULL, phase == PH_LOGIC);
+    if (!(trav | logic)) break;
+    if (__popc(trav) >= MEGA_T_HI || !logic) {
+      // ---- traversal burst
+      do {
+        if (phase == PH_TRAV) { if (!trav_step(sc, ray, tv, stack_n, stack_d)) phase = PH_LOGIC; }
+        trav = __ballot_sync(FULL, phase == PH_TRAV);
+      } while (__popc(trav) >= MEGA_T_LO);
+      continue;
+    }
+    if (phase != PH_LOGIC) continue;
+    // ---- logic pass
+    bool start = false;
+    if (what != ST_GEN) {
+      GHit g = trav_result(tv);
+      c_rays += 1; c_visits += g.visits; c_prims += g.prims;
+      bool finish = false;
+      if (what == ST_SHADOW) {   // Scene::shadow_ray, scene.rs:114-132
+        bool occluded = g.id >= 0 && g.t < sh_len && g.id != sh_light;
+        if (!occluded) ps.color = ps.color + contrib;
+        if (alive_after_shadow) { ray = make_ray(ext_o, ext_d); what = ST_EXTEND; start = true; }
+        else finish = true;
+      } else {
+        ShadeOut so;
+        shade_hit(P.rp, ray, g.id, ps, so);
+        if (so.finished) finish = true;
+        else if (so.shadow) {
+          ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
+          alive_after_shadow = so.survive;
+          ray = make_ray(so.sh_o, so.sh_d); what = ST_SHADOW; start = true;
+        } else if (so.survive) { ray = make_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
+        else finish = true;
+      }
+      if (finish) { acc.add(pix, ps.color); c_paths += 1; s += 1; what = ST_GEN; }
+    }
+    if (what == ST_GEN) {
+      if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream
+        ps.rng.s = stream_seed(pix, s, STREAM_PATH, P.rp.base_seed);
+        float j1 = ps.rng.f32();
+        float j2 = ps.rng.f32();
+        uint32_t py = pix / P.rp.W, px = pix - py * P.rp.W;
+        ray = camera_ray(P.rp.cam, px, py, j1, j2);
+        ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
+        what = ST_EXTEND; start = true;
+      } else phase = PH_NEED;
+    }
+    if (start && trav_begin(sc, ray, tv)) phase = PH_TRAV;
+  }
+  // ---- counters
+  unsigned long long r = warp_sum_u64(c_rays), v = warp_sum_u64(c_visits), pr = warp_sum_u64(c_prims), pa = warp_sum_u64(c_paths);
+  if (lane == 0 && r) {
+    atomicAdd(&P.counters[0], r); atomicAdd(&P.counters[1], v); atomicAdd(&P.counters[2], pa); atomicAdd(&P.counters[3], pr);
+  }
+}
+void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
+  if (!P.nslots) return;
+  int grid = device_sm_count() * blocks_per_sm;
+  int need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS);
+  if (grid > need) grid = need;
+  k_mega<<<grid, MEGA_THREADS, 0, s>>>(P);
 }
 
 // ------------------------------------------------------------------ resolve (render_target.rs:59-64)

@@ -45,6 +45,18 @@ struct WaveBuffers {
   float4* accum;              // per pixel: rgb sums, bits(sample count)
 };
 
+// Persistent path kernel (k_mega): slots are fetched from `work_counter`.
+struct MegaParams {
+  RenderParams rp;
+  float4* accum;
+  const uint32_t* pixel;          // slot -> viewport pixel index
+  const uint32_t* spp_per_slot;   // may be null: `uniform_spp` for every slot
+  uint32_t uniform_spp, nslots;
+  uint32_t* work_counter;         // zeroed before the launch
+  unsigned long long* counters;
+};
+void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s);
+
 void launch_setup_slots(const PathState& st, const uint32_t* spp_per_slot, uint32_t uniform_spp, const float4* accum, cudaStream_t s);
 void launch_trace(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
 void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);

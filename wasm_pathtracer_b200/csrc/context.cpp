@@ -4,6 +4,8 @@
 #include "context.h"
 #include <cstring>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 namespace wpt {
 
@@ -32,9 +34,9 @@ Context::Context(int dev, uint32_t w, uint32_t h, uint32_t sid, const float cam5
   std::memcpy(cam, cam5, sizeof cam);
   wpt_default_config(&cfg);
   WPT_CUDA(cudaMallocHost((void**)&h_ring, 64 * sizeof(uint32_t)));
-  WPT_CUDA(cudaMallocHost((void**)&h_counters, 8 * sizeof(unsigned long long)));
-  w_shadow_n.alloc(2); w_ring.alloc(64); w_counters.alloc(8); w_work.alloc(4);
-  WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 8 * sizeof(unsigned long long), stream));
+  WPT_CUDA(cudaMallocHost((void**)&h_counters, 16 * sizeof(unsigned long long)));
+  w_shadow_n.alloc(2); w_ring.alloc(64); w_counters.alloc(16); w_work.alloc(4);
+  WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 16 * sizeof(unsigned long long), stream));
   alloc_targets();
   select_scene(sid);
 }
@@ -82,7 +84,7 @@ void Context::reset() {   // wasm_interface.rs:137-148
   unsigned long long now[4];
   read_counters(now);
   for (int i = 0; i < 4; i++) life[i] += now[i];
-  WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 8 * sizeof(unsigned long long), stream));
+  WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 16 * sizeof(unsigned long long), stream));
   iterations = launches = 0;
   photons_shot_total = photons_stored_total = 0;
 }
@@ -132,7 +134,7 @@ int64_t Context::reupload_scene() {
 }
 
 void Context::read_counters(unsigned long long out[4]) {
-  WPT_CUDA(cudaMemcpyAsync(h_counters, w_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaMemcpyAsync(h_counters, w_counters.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
   WPT_CUDA(cudaStreamSynchronize(stream));
   for (int i = 0; i < 4; i++) out[i] = h_counters[i];
 }
@@ -282,7 +284,12 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
   cudaEvent_t a = nullptr, b = nullptr;
   if (profiling) { a = ev_get(); b = ev_get(); WPT_CUDA(cudaEventRecord(a, stream)); }
-  launch_mega(P, 4, stream);
+  static const int env_hi = std::getenv("WPT_MEGA_THI") ? std::atoi(std::getenv("WPT_MEGA_THI")) : 16;
+  static const int env_lo = std::getenv("WPT_MEGA_TLO") ? std::atoi(std::getenv("WPT_MEGA_TLO")) : 8;
+  static const int env_minb = std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 4;
+  static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 4;
+  P.t_hi = (uint32_t)env_hi; P.t_lo = (uint32_t)env_lo; P.t_inner = (uint32_t)env_ti;
+  launch_mega(P, env_minb, stream);
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());
   launches += 1; iterations += 1;
@@ -322,8 +329,13 @@ const uint8_t* Context::results(uint32_t show_sampling) {   // wasm_interface.rs
 
 void Context::stats(uint64_t out[8]) {
   require_device();
-  WPT_CUDA(cudaMemcpyAsync(h_counters, w_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaMemcpyAsync(h_counters, w_counters.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
   WPT_CUDA(cudaStreamSynchronize(stream));
+  if (std::getenv("WPT_DEBUG_COUNTERS")) {
+    std::fprintf(stderr, "wpt counters:");
+    for (int i = 0; i < 12; i++) std::fprintf(stderr, " %llu", h_counters[i]);
+    std::fprintf(stderr, "\n");
+  }
   out[0] = h_counters[0]; out[1] = h_counters[2]; out[2] = h_counters[1];
   out[3] = photons_shot_total; out[4] = photons_stored_total; out[5] = iterations; out[6] = launches; out[7] = 0;
 }

@@ -449,36 +449,10 @@ WPT_DEV bool trav_begin(const DScene& sc, const Ray& ray, Trav& tv) {
   return true;
 }
 
-// Enter one BVH2 node. Returns false when the traversal is finished.
-WPT_DEV bool trav_step2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+// pop: next node to enter, skipping entries the current bound has made unreachable
+WPT_DEV bool trav_pop2(const DScene& sc, Trav& tv, const uint32_t* stack_n, const float* stack_d) {
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
-  tv.visits += 1;
-  if (tv.cnt != 0) {
-    leaf_scan(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
-  } else {
-    const float4* c = nodes + (size_t)tv.lf * 2;
-    float4 la = __ldg(c), lb = __ldg(c + 1), qa = __ldg(c + 2), qb = __ldg(c + 3);
-    float dl, dr;
-    bool hl = box_hit(la.x, la.y, la.z, la.w, lb.x, lb.y, ray, &dl) && dl < tv.bound;
-    bool hr = box_hit(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < tv.bound;
-    if (!hl) {
-      // left misses: traverse_bvh_guarded(right) — counts the guard (scene.rs:283-286)
-      tv.visits += 1;
-      if (hr) { tv.lf = __float_as_uint(qb.z); tv.cnt = __float_as_uint(qb.w); return true; }
-    } else if (!hr) {
-      tv.lf = __float_as_uint(lb.z); tv.cnt = __float_as_uint(lb.w); return true;
-    } else {
-      if (dl < dr) {   // left first; tie -> right first (scene.rs:244,261)
-        stack_n[tv.sp] = tv.lf + 1; stack_d[tv.sp] = dr; tv.sp++;
-        tv.lf = __float_as_uint(lb.z); tv.cnt = __float_as_uint(lb.w);
-      } else {
-        stack_n[tv.sp] = tv.lf; stack_d[tv.sp] = dl; tv.sp++;
-        tv.lf = __float_as_uint(qb.z); tv.cnt = __float_as_uint(qb.w);
-      }
-      return true;
-    }
-  }
-  while (tv.sp > 0) {   // pop
+  while (tv.sp > 0) {
     tv.sp--;
     if (tv.bound < stack_d[tv.sp]) continue;   // near hit closer than the far box: skip it
     float4 nb = __ldg(nodes + (size_t)stack_n[tv.sp] * 2 + 1);
@@ -487,29 +461,42 @@ WPT_DEV bool trav_step2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* st
   }
   return false;
 }
-
-// Enter one BVH4 node or leaf.
-WPT_DEV bool trav_step4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
-  int node = (int)tv.lf;
+// Enter the inner BVH2 node tv.lf (tv.cnt == 0). Returns false when the traversal is finished.
+WPT_DEV bool trav_inner2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
   tv.visits += 1;
-  if (node < 0) {
-    uint32_t code = (uint32_t)node;
-    leaf_scan(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims);
-  } else {
-    const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + node);
-    float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
-    int4 ch = __ldg(reinterpret_cast<const int4*>(p + 6));
-    uint32_t nc = __ldg(reinterpret_cast<const uint32_t*>(p + 7));
-    int id[4] = {0, 0, 0, 0}; float d[4] = {WPT_INF, WPT_INF, WPT_INF, WPT_INF};
-    if (nc > 0) { id[0] = ch.x; d[0] = box_hit_x4(x0.x, y0.x, z0.x, x1.x, y1.x, z1.x, ray); }
-    if (nc > 1) { id[1] = ch.y; d[1] = box_hit_x4(x0.y, y0.y, z0.y, x1.y, y1.y, z1.y, ray); }
-    if (nc > 2) { id[2] = ch.z; d[2] = box_hit_x4(x0.z, y0.z, z0.z, x1.z, y1.z, z1.z, ray); }
-    if (nc > 3) { id[3] = ch.w; d[3] = box_hit_x4(x0.w, y0.w, z0.w, x1.w, y1.w, z1.w, ray); }
-    sort_small(id, d, nc);
-#pragma unroll
-    for (int i = 3; i >= 0; i--)
-      if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) { stack_n[tv.sp] = (uint32_t)id[i]; stack_d[tv.sp] = d[i]; tv.sp++; }
+  const float4* c = nodes + (size_t)tv.lf * 2;
+  float4 la = __ldg(c), lb = __ldg(c + 1), qa = __ldg(c + 2), qb = __ldg(c + 3);
+  float dl, dr;
+  bool hl = box_hit(la.x, la.y, la.z, la.w, lb.x, lb.y, ray, &dl) && dl < tv.bound;
+  bool hr = box_hit(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < tv.bound;
+  if (!hl) {
+    // left misses: traverse_bvh_guarded(right) — counts the guard (scene.rs:283-286)
+    tv.visits += 1;
+    if (hr) { tv.lf = __float_as_uint(qb.z); tv.cnt = __float_as_uint(qb.w); return true; }
+    return trav_pop2(sc, tv, stack_n, stack_d);
   }
+  if (!hr) { tv.lf = __float_as_uint(lb.z); tv.cnt = __float_as_uint(lb.w); return true; }
+  if (dl < dr) {   // left first; tie -> right first (scene.rs:244,261)
+    stack_n[tv.sp] = tv.lf + 1; stack_d[tv.sp] = dr; tv.sp++;
+    tv.lf = __float_as_uint(lb.z); tv.cnt = __float_as_uint(lb.w);
+  } else {
+    stack_n[tv.sp] = tv.lf; stack_d[tv.sp] = dl; tv.sp++;
+    tv.lf = __float_as_uint(qb.z); tv.cnt = __float_as_uint(qb.w);
+  }
+  return true;
+}
+// Enter the BVH2 leaf (tv.lf, tv.cnt != 0).
+WPT_DEV bool trav_leaf2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  tv.visits += 1;
+  leaf_scan(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
+  return trav_pop2(sc, tv, stack_n, stack_d);
+}
+WPT_DEV bool trav_step2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  return tv.cnt != 0 ? trav_leaf2(sc, ray, tv, stack_n, stack_d) : trav_inner2(sc, ray, tv, stack_n, stack_d);
+}
+
+WPT_DEV bool trav_pop4(Trav& tv, const uint32_t* stack_n, const float* stack_d) {
   while (tv.sp > 0) {
     tv.sp--;
     if (stack_d[tv.sp] > tv.bound) continue;
@@ -518,6 +505,35 @@ WPT_DEV bool trav_step4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* st
   }
   return false;
 }
+// Enter the inner BVH4 node tv.lf (>= 0 as int).
+WPT_DEV bool trav_inner4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  tv.visits += 1;
+  const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + (int)tv.lf);
+  float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
+  int4 ch = __ldg(reinterpret_cast<const int4*>(p + 6));
+  uint32_t nc = __ldg(reinterpret_cast<const uint32_t*>(p + 7));
+  int id[4] = {0, 0, 0, 0}; float d[4] = {WPT_INF, WPT_INF, WPT_INF, WPT_INF};
+  if (nc > 0) { id[0] = ch.x; d[0] = box_hit_x4(x0.x, y0.x, z0.x, x1.x, y1.x, z1.x, ray); }
+  if (nc > 1) { id[1] = ch.y; d[1] = box_hit_x4(x0.y, y0.y, z0.y, x1.y, y1.y, z1.y, ray); }
+  if (nc > 2) { id[2] = ch.z; d[2] = box_hit_x4(x0.z, y0.z, z0.z, x1.z, y1.z, z1.z, ray); }
+  if (nc > 3) { id[3] = ch.w; d[3] = box_hit_x4(x0.w, y0.w, z0.w, x1.w, y1.w, z1.w, ray); }
+  sort_small(id, d, nc);
+#pragma unroll
+  for (int i = 3; i >= 0; i--)
+    if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) { stack_n[tv.sp] = (uint32_t)id[i]; stack_d[tv.sp] = d[i]; tv.sp++; }
+  return trav_pop4(tv, stack_n, stack_d);
+}
+WPT_DEV bool trav_leaf4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  tv.visits += 1;
+  uint32_t code = tv.lf;
+  leaf_scan(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims);
+  return trav_pop4(tv, stack_n, stack_d);
+}
+WPT_DEV bool trav_step4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  return (int)tv.lf < 0 ? trav_leaf4(sc, ray, tv, stack_n, stack_d) : trav_inner4(sc, ray, tv, stack_n, stack_d);
+}
+// true if the node the lane is about to enter is a leaf
+WPT_DEV bool trav_at_leaf(const DScene& sc, const Trav& tv) { return sc.bvh_kind == 4 ? (int)tv.lf < 0 : tv.cnt != 0; }
 
 WPT_DEV bool trav_step(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
   return sc.bvh_kind == 4 ? trav_step4(sc, ray, tv, stack_n, stack_d) : trav_step2(sc, ray, tv, stack_n, stack_d);

@@ -412,7 +412,8 @@ void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers
 enum : int { PH_NEED = 0, PH_LOGIC = 1, PH_TRAV = 2, PH_DONE = 3 };
 enum : int { ST_GEN = 0, ST_EXTEND = 1, ST_SHADOW = 2 };
 
-__global__ void __launch_bounds__(MEGA_THREADS, 4) k_mega(MegaParams P) {
+template <int MINB>
+__global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
   const unsigned FULL = 0xFFFFFFFFu;
@@ -426,6 +427,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 4) k_mega(MegaParams P) {
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
   uint32_t c_rays = 0, c_visits = 0, c_prims = 0, c_paths = 0;
   Accum acc{P.accum};
+#ifdef MEGA_INSTR
+  unsigned long long i_lp = 0, i_ll = 0, i_ts = 0, i_tl = 0, i_sh = 0;   // logic passes, logic lanes, trav steps, trav lanes, shade lanes
+#endif
 
   for (;;) {
     // ---- pixel fetch: one atomic per warp
@@ -449,14 +453,36 @@ __global__ void __launch_bounds__(MEGA_THREADS, 4) k_mega(MegaParams P) {
     unsigned trav = __ballot_sync(FULL, phase == PH_TRAV);
     unsigned logic = __ballot_sync(FULL, phase == PH_LOGIC);
     if (!(trav | logic)) break;
-    if (__popc(trav) >= MEGA_T_HI || !logic) {
-      // ---- traversal burst
+    if (__popc(trav) >= (int)P.t_hi || !logic) {
+      // ---- traversal burst, while-while: cheap inner steps until (almost) every lane of the
+      // burst waits at a leaf, then one leaf step with all of them (triangle tests are the
+      // expensive body: run them with as many lanes as possible)
       do {
-        if (phase == PH_TRAV) { if (!trav_step(sc, ray, tv, stack_n, stack_d)) phase = PH_LOGIC; }
+        const int n_trav = __popc(trav);
+        for (;;) {
+          bool at_inner = phase == PH_TRAV && !trav_at_leaf(sc, tv);
+          int n_inner = __popc(__ballot_sync(FULL, at_inner));
+          if (n_inner == 0) break;
+#ifdef MEGA_INSTR
+          i_ts += 1; i_tl += n_inner;
+#endif
+          if (at_inner) {
+            bool cont = sc.bvh_kind == 4 ? trav_inner4(sc, ray, tv, stack_n, stack_d) : trav_inner2(sc, ray, tv, stack_n, stack_d);
+            if (!cont) phase = PH_LOGIC;
+          }
+          if (n_inner * P.t_inner <= n_trav) break;   // few lanes left at inner nodes: let them wait
+        }
+        if (phase == PH_TRAV && trav_at_leaf(sc, tv)) {
+          bool cont = sc.bvh_kind == 4 ? trav_leaf4(sc, ray, tv, stack_n, stack_d) : trav_leaf2(sc, ray, tv, stack_n, stack_d);
+          if (!cont) phase = PH_LOGIC;
+        }
         trav = __ballot_sync(FULL, phase == PH_TRAV);
-      } while (__popc(trav) >= MEGA_T_LO);
+      } while (__popc(trav) >= (int)P.t_lo);
       continue;
     }
+#ifdef MEGA_INSTR
+    i_lp += 1; i_ll += __popc(logic); i_sh += __popc(__ballot_sync(FULL, phase == PH_LOGIC && what == ST_EXTEND));
+#endif
     if (phase != PH_LOGIC) continue;
     // ---- logic pass
     bool start = false;
@@ -500,13 +526,20 @@ __global__ void __launch_bounds__(MEGA_THREADS, 4) k_mega(MegaParams P) {
   if (lane == 0 && r) {
     atomicAdd(&P.counters[0], r); atomicAdd(&P.counters[1], v); atomicAdd(&P.counters[2], pa); atomicAdd(&P.counters[3], pr);
   }
+#ifdef MEGA_INSTR
+  if (lane == 0) { atomicAdd(&P.counters[4], i_lp); atomicAdd(&P.counters[5], i_ll); atomicAdd(&P.counters[6], i_ts); atomicAdd(&P.counters[7], i_tl); }
+  if (lane == 1) atomicAdd(&P.counters[8], i_sh);
+#endif
 }
 void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   if (!P.nslots) return;
   int grid = device_sm_count() * blocks_per_sm;
   int need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS);
   if (grid > need) grid = need;
-  k_mega<<<grid, MEGA_THREADS, 0, s>>>(P);
+  if (blocks_per_sm >= 6) k_mega<6><<<grid, MEGA_THREADS, 0, s>>>(P);
+  else if (blocks_per_sm == 5) k_mega<5><<<grid, MEGA_THREADS, 0, s>>>(P);
+  else if (blocks_per_sm == 3) k_mega<3><<<grid, MEGA_THREADS, 0, s>>>(P);
+  else k_mega<4><<<grid, MEGA_THREADS, 0, s>>>(P);
 }
 
 // ------------------------------------------------------------------ resolve (render_target.rs:59-64)

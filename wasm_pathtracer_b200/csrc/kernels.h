@@ -52,6 +52,8 @@ struct MegaParams {
   const uint32_t* pixel;          // slot -> viewport pixel index
   const uint32_t* spp_per_slot;   // may be null: `uniform_spp` for every slot
   uint32_t uniform_spp, nslots;
+  uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
+  uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
   uint32_t* work_counter;         // zeroed before the launch
   unsigned long long* counters;
 };

@@ -123,8 +123,13 @@ int wpt_ctx_get_config(wpt_ctx* ctx, wpt_config* cfg);
 /* `spp` more samples for every pixel of this session's rows, exact counts (mode-B driver). */
 int wpt_ctx_render_exact(wpt_ctx* ctx, uint32_t spp);
 /* Adaptive sampling (sampling_strategy.rs:77-220) over the region with a tick budget;
- * returns ticks consumed by this session's rows, -1 on error. */
+ * returns the ticks consumed over the whole region (all ranks), -1 on error. */
 int64_t wpt_ctx_render_adaptive(wpt_ctx* ctx, uint64_t budget_ticks);
+/* Random strategy (sampling_strategy.rs:30-71): `ticks` uniform pixel picks with replacement. */
+int wpt_ctx_render_random(wpt_ctx* ctx, uint64_t ticks);
+/* Multi-GPU: called between adaptive rounds so that the caller can exchange the accumulator
+ * rows of the other ranks (the next error map reads the whole region). NULL removes it. */
+int wpt_ctx_set_exchange_callback(wpt_ctx* ctx, void (*callback)(void* user), void* user);
 /* Photon warm-up (tracer.rs:103-152) + octree light-CDF build (photon_tree.rs). */
 int wpt_ctx_build_photons(wpt_ctx* ctx);
 /* Block until queued GPU work is finished. */

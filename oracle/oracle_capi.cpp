@@ -45,6 +45,7 @@ int orc_mb_config(void* s, int type, int light_debug, int trig, uint32_t seed, u
   S->mb.type = (RenderType)type; S->mb.light_debug = light_debug != 0; S->mb.trig = (TrigMode)trig;
   S->mb.base_seed = seed; S->mb.photon_target = (size_t)photon_target;
   S->mb.rx = rx; S->mb.ry = ry; S->mb.rw = rw ? rw : S->W; S->mb.rh = rh ? rh : S->H;
+  if (S->mb_round_left.size() != S->mb.rw * S->mb.rh) { S->mb_round_left.clear(); S->mb_adaptive_started = false; }
   if (rebuild_photons) { S->mb_photons.reset(); S->mb_photon_list.clear(); S->mb_shots = 0; }
   return 0;
   ORC_CATCH(-1)
@@ -52,6 +53,7 @@ int orc_mb_config(void* s, int type, int light_debug, int trig, uint32_t seed, u
 int orc_mb_build_photons(void* s, uint32_t threads) { ORC_TRY ((Session*)s)->mb_build_photons(threads ? threads : 1); return 0; ORC_CATCH(-1) }
 int orc_mb_render_exact(void* s, uint32_t spp, uint32_t threads) { ORC_TRY ((Session*)s)->mb_render_exact(spp, threads ? threads : 1); return 0; ORC_CATCH(-1) }
 int64_t orc_mb_render_adaptive(void* s, uint64_t budget, uint32_t threads) { ORC_TRY return (int64_t)((Session*)s)->mb_render_adaptive(budget, threads ? threads : 1); ORC_CATCH(-1) }
+int orc_mb_render_random(void* s, uint64_t ticks, uint32_t threads) { ORC_TRY ((Session*)s)->mb_render_random(ticks, threads ? threads : 1); return 0; ORC_CATCH(-1) }
 int orc_mb_primary_probe(void* s, int32_t* ids, uint32_t* visits, float* dist) { ORC_TRY ((Session*)s)->mb_primary_probe(ids, visits, dist); return 0; ORC_CATCH(-1) }
 int orc_mb_round_spp(void* s, uint32_t* out, uint64_t cap) {
   Session* S = (Session*)s;

@@ -69,7 +69,7 @@ struct Session {
   }
   void reset() {   // wasm_interface.rs:137-148
     target->clear(); sampling_target->clear(); left->reset(); right->reset();
-    mb_stats = Stats();
+    mb_stats = Stats(); mb_round_left.clear(); mb_adaptive_started = false; mb_random_ticks = 0;
   }
   void update_scene(uint32_t sid) {   // wasm_interface.rs:154-168
     scene_id = sid;
@@ -78,6 +78,7 @@ struct Session {
     left->update_scene(ns.get()); right->update_scene(ns.get());
     scene = std::move(ns);
     mb_photons.reset(); mb_photon_list.clear(); mb_shots = 0; mb_stats = Stats();
+    mb_round_left.clear(); mb_adaptive_started = false; mb_random_ticks = 0;
   }
   void update_settings(uint32_t lt, uint32_t rt, uint32_t la, uint32_t ra, uint32_t dbg) {   // wasm_interface.rs:173-214
     if (lt > 2 || rt > 2) throw std::runtime_error("Invalid RenderType magic number");
@@ -234,37 +235,48 @@ struct Session {
     *avg = (float)(((double)sum_fx * (1.0 / PHOTON_FX_SCALE)) / (double)(mb.rw * mb.rh));
   }
 
-  // Adaptive sampling with a tick budget. Phase 0: 4 spp for every pixel; then rounds of
-  // 1..33 spp per pixel. A budget that ends inside a phase is consumed in the reference's
-  // pop order for rounds — LIFO over raster-order pushes, i.e. from the last pixel of the
-  // region backwards (sampling_strategy.rs:122-126,164-166). Returns ticks consumed.
+  // Adaptive sampling with a tick budget (sampling_strategy.rs:77-220 in mode B).
+  // The queue of the reference becomes `mb_round_left[pixel]` = samples of the current round
+  // still to be taken. A new round starts when the queue is empty: the first round after a
+  // reset queues 4 samples per pixel (sampling_strategy.rs:194-203), later rounds 1..33 from
+  // the error map (:133-166). Ticks are consumed in the reference's pop order for rounds —
+  // LIFO over raster-order pushes, i.e. from the last pixel of the region backwards, each
+  // pixel's entries contiguous — so a budget that ends inside a round leaves the rest of the
+  // queue for the next call, exactly like compute(n) popping n entries. (The reference
+  // shuffles only the very first queue; with per-path streams the order inside a round does
+  // not change any sample, only which pixels a partial budget reaches.) Returns ticks used.
+  std::vector<uint32_t> mb_round_left;
+  bool mb_adaptive_started = false;
   uint64_t mb_render_adaptive(uint64_t budget, unsigned threads = 1) {
     if (mb.type == PNEE) mb_build_photons(threads);
     Integrator I = mb_integ();
     uint64_t used = 0;
     size_t N = mb.rw * mb.rh;
-    std::vector<uint32_t> spp(N);
-    bool first = true;
-    for (size_t i = 0; i < N && first; i++) { size_t x = mb.rx + i % mb.rw, y = mb.ry + i / mb.rw; if (target->acc_count[y * W + x] != 0) first = false; }
+    if (mb_round_left.size() != N) { mb_round_left.assign(N, 0); mb_adaptive_started = false; }
+    std::vector<uint32_t> take(N);
     while (used < budget) {
-      if (first) { std::fill(spp.begin(), spp.end(), 4u); first = false; }
-      else {
-        std::vector<float> mse; float mn, avg, mx;
-        mb_error_stats(mse, &mn, &avg, &mx);
-        for (size_t i = 0; i < N; i++) {
-          float s = scaled_error(mse[i], mn, avg, mx);
-          spp[i] = (uint32_t)spp_from_scaled(s);
-          size_t x = mb.rx + i % mb.rw, y = mb.ry + i / mb.rw;
-          if (mn == mx) sampling_target->write(x, y, Vec3()); else sampling_target->write(x, y, mix_color(s));
+      bool empty = true;
+      for (size_t i = 0; i < N && empty; i++) if (mb_round_left[i]) empty = false;
+      if (empty) {
+        if (!mb_adaptive_started) { std::fill(mb_round_left.begin(), mb_round_left.end(), 4u); mb_adaptive_started = true; }
+        else {
+          std::vector<float> mse; float mn, avg, mx;
+          mb_error_stats(mse, &mn, &avg, &mx);
+          for (size_t i = 0; i < N; i++) {
+            float sc = scaled_error(mse[i], mn, avg, mx);
+            mb_round_left[i] = (uint32_t)spp_from_scaled(sc);
+            size_t x = mb.rx + i % mb.rw, y = mb.ry + i / mb.rw;
+            if (mn == mx) sampling_target->write(x, y, Vec3()); else sampling_target->write(x, y, mix_color(sc));
+          }
         }
+        mb_round_spp = mb_round_left;
       }
       // budget cut, from the last pixel backwards
       uint64_t left_ticks = budget - used;
       for (size_t i = N; i-- > 0;) {
-        if ((uint64_t)spp[i] > left_ticks) spp[i] = (uint32_t)left_ticks;
-        left_ticks -= spp[i];
+        take[i] = (uint64_t)mb_round_left[i] > left_ticks ? (uint32_t)left_ticks : mb_round_left[i];
+        left_ticks -= take[i];
       }
-      mb_round_spp = spp;
       std::vector<Stats> tst(threads);
       auto work = [&](unsigned t) {
         tl_prim_tests() = 0;
@@ -272,15 +284,46 @@ struct Session {
           for (size_t xx = 0; xx < mb.rw; xx++) {
             size_t x = mb.rx + xx, y = mb.ry + yy;
             uint32_t s0 = (uint32_t)target->acc_count[y * W + x];
-            for (uint32_t s = 0; s < spp[yy * mb.rw + xx]; s++) mb_sample(I, x, y, s0 + s, tst[t]);
+            for (uint32_t s = 0; s < take[yy * mb.rw + xx]; s++) mb_sample(I, x, y, s0 + s, tst[t]);
           }
         tst[t].prim_tests = tl_prim_tests();
       };
       run_threads(threads, work);
-      for (auto& s : tst) { mb_stats.add(s); }
-      for (size_t i = 0; i < N; i++) used += spp[i];
+      for (auto& s : tst) mb_stats.add(s);
+      for (size_t i = 0; i < N; i++) { used += take[i]; mb_round_left[i] -= take[i]; }
     }
     return used;
+  }
+
+  // Random strategy in mode B (sampling_strategy.rs:56-59): tick t of the region picks its
+  // pixel from stream (t, 0, STREAM_PIXEL) with the reference's two next_in_range draws; the
+  // ticks of one call only decide HOW MANY samples each pixel receives, the samples themselves
+  // are the pixel's next sample indices (per-path streams), accumulated in index order.
+  uint64_t mb_random_ticks = 0;
+  void mb_render_random(uint64_t ticks, unsigned threads = 1) {
+    if (mb.type == PNEE) mb_build_photons(threads);
+    Integrator I = mb_integ();
+    size_t N = mb.rw * mb.rh;
+    std::vector<uint32_t> take(N, 0);
+    for (uint64_t k = 0; k < ticks; k++) {
+      Rng r(stream_seed((uint32_t)(mb_random_ticks + k), (uint32_t)((mb_random_ticks + k) >> 32), STREAM_PIXEL, mb.base_seed ^ (uint32_t)(mb.rx * 0x9E3779B1u + mb.ry)));
+      size_t x = r.next_in_range(0, mb.rw);
+      size_t y = r.next_in_range(0, mb.rh);
+      take[y * mb.rw + x]++;
+    }
+    mb_random_ticks += ticks;
+    mb_round_spp = take;
+    std::vector<Stats> tst(threads);
+    auto work = [&](unsigned t) {
+      for (size_t yy = t; yy < mb.rh; yy += threads)
+        for (size_t xx = 0; xx < mb.rw; xx++) {
+          size_t x = mb.rx + xx, y = mb.ry + yy;
+          uint32_t s0 = (uint32_t)target->acc_count[y * W + x];
+          for (uint32_t s = 0; s < take[yy * mb.rw + xx]; s++) mb_sample(I, x, y, s0 + s, tst[t]);
+        }
+    };
+    run_threads(threads, work);
+    for (auto& s : tst) mb_stats.add(s);
   }
 
   // Primary-ray probe for the bit-exact gate: sample 0 of every pixel of the viewport.

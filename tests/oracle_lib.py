@@ -120,6 +120,8 @@ class Oracle:
     def mb_render_exact(self, spp, threads=1): self._chk(self.L.orc_mb_render_exact(self.h, spp, threads))
     def mb_render_adaptive(self, budget, threads=1): return self._chk(self.L.orc_mb_render_adaptive(self.h, C.c_uint64(budget), threads))
 
+    def mb_render_random(self, ticks, threads=1): self._chk(self.L.orc_mb_render_random(self.h, C.c_uint64(ticks), threads))
+
     def mb_primary_probe(self):
         n = self.W * self.H
         ids = np.empty(n, np.int32); vis = np.empty(n, np.uint32); dist = np.empty(n, np.float32)

@@ -82,6 +82,8 @@ def load_library():
         "wpt_ctx_render_exact": (i32, [vp, u32]),
         "wpt_ctx_render_adaptive": (C.c_int64, [vp, u64]),
         "wpt_ctx_build_photons": (i32, [vp]),
+        "wpt_ctx_render_random": (i32, [vp, u64]),
+        "wpt_ctx_set_exchange_callback": (i32, [vp, C.c_void_p, vp]),
         "wpt_ctx_synchronize": (i32, [vp]),
         "wpt_ctx_stats": (i32, [vp, P(u64)]),
         "wpt_ctx_primary_probe": (i32, [vp, P(C.c_int32), P(u32), P(f32)]),
@@ -235,6 +237,18 @@ class PathTracer:
 
     def render_adaptive(self, budget_ticks):
         return self._chk(self.L.wpt_ctx_render_adaptive(self.h, budget_ticks))
+
+    def render_random(self, ticks):
+        self._chk(self.L.wpt_ctx_render_random(self.h, ticks))
+
+    def set_exchange_callback(self, fn):
+        """fn() is called between adaptive rounds (multi-GPU accumulator exchange); None removes it."""
+        if fn is None:
+            self._cb = None
+            self._chk(self.L.wpt_ctx_set_exchange_callback(self.h, None, None))
+            return
+        self._cb = C.CFUNCTYPE(None, C.c_void_p)(lambda _u: fn())
+        self._chk(self.L.wpt_ctx_set_exchange_callback(self.h, C.cast(self._cb, C.c_void_p), None))
 
     def build_photons(self):
         self._chk(self.L.wpt_ctx_build_photons(self.h))

@@ -150,6 +150,12 @@ int64_t wpt_ctx_render_adaptive(wpt_ctx* ctx, uint64_t budget) {
   guard([&] { Context* c = C(ctx); if (c->cfg.render_type == WPT_PNEE) c->build_photons(); used = (int64_t)c->render_adaptive(budget); });
   return used;
 }
+int wpt_ctx_render_random(wpt_ctx* ctx, uint64_t ticks) {
+  return guard([&] { Context* c = C(ctx); if (c->cfg.render_type == WPT_PNEE) c->build_photons(); c->render_random(ticks); });
+}
+int wpt_ctx_set_exchange_callback(wpt_ctx* ctx, void (*cb)(void*), void* user) {
+  return guard([&] { Context* c = C(ctx); if (cb) c->exchange_hook = [cb, user] { cb(user); }; else c->exchange_hook = nullptr; });
+}
 int wpt_ctx_build_photons(wpt_ctx* ctx) { return guard([&] { C(ctx)->build_photons(); }); }
 int wpt_ctx_synchronize(wpt_ctx* ctx) { return guard([&] { Context* c = C(ctx); c->require_device(); WPT_CUDA(cudaStreamSynchronize(c->stream)); }); }
 int wpt_ctx_stats(wpt_ctx* ctx, uint64_t out[8]) { return guard([&] { C(ctx)->stats(out); }); }

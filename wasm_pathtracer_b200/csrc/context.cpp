@@ -81,10 +81,12 @@ void Context::clear_targets() {   // RenderTarget::clear / new, render_target.rs
 void Context::reset() {   // wasm_interface.rs:137-148
   if (!has_device) return;
   clear_targets();
+  clear_strategies();
   unsigned long long now[4];
   read_counters(now);
   for (int i = 0; i < 4; i++) life[i] += now[i];
   WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 16 * sizeof(unsigned long long), stream));
+  photon_rays = photon_visits = 0;
   iterations = launches = 0;
   photons_shot_total = photons_stored_total = 0;
 }
@@ -185,7 +187,7 @@ RenderParams Context::params(uint32_t render_type) const {
   float fw = (float)W, fh = (float)H;
   rp.cam.w_inv = 1.0f / fw; rp.cam.h_inv = 1.0f / fh; rp.cam.ar = fw / fh;   // tracer.rs:168-172
   rp.photons.child_base = p_child_base.p; rp.photons.cum = p_cum.p;
-  rp.photons.num_lights = (uint32_t)scene.lights.size(); rp.photons.num_nodes = (uint32_t)p_child_base.n;
+  rp.photons.num_lights = (uint32_t)scene.lights.size(); rp.photons.num_nodes = p_nodes;
   rp.W = W; rp.H = H;
   rp.render_type = render_type; rp.light_debug = cfg.light_debug; rp.base_seed = cfg.base_seed;
   return rp;
@@ -336,7 +338,7 @@ void Context::stats(uint64_t out[8]) {
     for (int i = 0; i < 12; i++) std::fprintf(stderr, " %llu", h_counters[i]);
     std::fprintf(stderr, "\n");
   }
-  out[0] = h_counters[0]; out[1] = h_counters[2]; out[2] = h_counters[1];
+  out[0] = h_counters[0] + photon_rays; out[1] = h_counters[2]; out[2] = h_counters[1] + photon_visits;
   out[3] = photons_shot_total; out[4] = photons_stored_total; out[5] = iterations; out[6] = launches; out[7] = 0;
 }
 

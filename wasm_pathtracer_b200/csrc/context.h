@@ -2,7 +2,9 @@
 // at a time (the reference is single-threaded per instance, wasm_interface.rs:59-62).
 #pragma once
 #include <cuda_runtime.h>
+#include <functional>
 #include <map>
+#include <list>
 #include <string>
 #include <vector>
 #include "../../include/wpt.h"
@@ -79,9 +81,14 @@ struct Context {
   uint32_t slots = 0;                         // slots of the current partition
   uint32_t slot_region[6] = {0, 0, 0, 0, 0, 0};   // region + rank/world the pixel map was built for
 
-  // photons
+  // photons: records (loc.xyz, weight) + (light, shot), octree build scratch, flattened tree
+  DevBuf<float4> ph_loc_w;
+  DevBuf<uint2> ph_light_shot;
+  DevBuf<uint32_t> ph_meta, ph_count, oc_node_of, oc_child_base, oc_count;
+  DevBuf<unsigned long long> oc_fx;
   DevBuf<uint32_t> p_child_base;
-  DevBuf<float> p_cum;
+  DevBuf<float> p_cum, p_bins;
+  uint32_t p_nodes = 0;
   bool photons_ready = false;
   uint64_t photon_shots = 0, photon_count = 0;
   std::vector<uint32_t> ph_light; std::vector<float> ph_loc, ph_w;     // host copies (read-backs)
@@ -106,8 +113,32 @@ struct Context {
   void set_profiling(bool on);
   void profile_read(double out[8]);
 
+  // sampling strategies (sampling_strategy.rs) per logical region
+  struct Strategy {
+    uint32_t rx = 0, ry = 0, rw = 0, rh = 0;
+    DevBuf<uint32_t> round_left, take, round_spp;   // region-indexed
+    DevBuf<float> mse;
+    uint64_t left_total = 0;      // samples still queued in the current adaptive round
+    bool started = false;         // the initial 4-spp queue has been issued
+    bool painted = false;
+    uint64_t random_ticks = 0;    // ticks consumed by the random strategy so far
+    Strategy() = default;
+    Strategy(const Strategy&) = delete;
+  };
+  std::list<Strategy> strategies;
+  DevBuf<unsigned long long> a_stats, a_block_tot, a_block_suffix;
+  std::function<void()> exchange_hook;   // multi-GPU: gather all rows' accumulators between adaptive rounds
+  Strategy& strategy_for(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh);
+  void clear_strategies();
+  void region_error(Strategy& s, float stats3[3]);
+  void render_take(Strategy& s, uint32_t render_type);
+  uint64_t run_adaptive(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange);
+  void run_random(Strategy& s, uint32_t render_type, uint64_t ticks);
+  void render_random(uint64_t ticks);
+
   // counters since the last reset
   uint64_t iterations = 0, launches = 0, photons_shot_total = 0, photons_stored_total = 0;
+  uint64_t photon_rays = 0, photon_visits = 0;   // rays / node visits of the photon warm-up (counted on the host)
 
   Context(int device, uint32_t w, uint32_t h, uint32_t scene_id, const float cam5[5]);
   ~Context();

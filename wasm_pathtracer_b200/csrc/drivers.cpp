@@ -1,13 +1,314 @@
-// Photon warm-up, adaptive sampling and the reference-style compute() tick driver.
+// Photon warm-up + octree light-CDF build, adaptive / random sampling drivers and the
+// reference-style compute() tick driver. All rendering goes through Context::run_paths.
 #include "context.h"
+#include <algorithm>
+#include <cstring>
+#include <numeric>
 
 namespace wpt {
 
-uint64_t Context::render_adaptive(uint64_t) { throw std::runtime_error("render_adaptive: not implemented yet"); }
-void Context::build_photons() { throw std::runtime_error("build_photons: not implemented yet"); }
-void Context::compute(uint64_t) { throw std::runtime_error("compute: not implemented yet"); }
-void Context::photon_sample_batch(const float*, const uint32_t*, uint64_t, uint32_t*, float*) { throw std::runtime_error("photon_sample: not implemented yet"); }
-void Context::error_map(float*, float*) { throw std::runtime_error("error_map: not implemented yet"); }
-void Context::round_spp(uint32_t*) { throw std::runtime_error("round_spp: not implemented yet"); }
+// ------------------------------------------------------------------ photons
+// tracer.rs:103-152 in mode B: shots k = 0,1,2,... on their own streams; the photon
+// set is every diffuse hit among the shots up to and including the one that produces photon
+// number `photon_target`. Shots run in batches on the device; only the last batch needs the
+// host to find the cut. Then the octree of photon_tree.rs is built level by level.
+void Context::build_photons() {
+  require_device();
+  if (photons_ready) return;
+  const uint32_t L = (uint32_t)scene.lights.size();
+  if (L == 0) throw std::runtime_error("Invalid range");   // rng.rs:27 — next_in_range(0, 0) panics
+  const uint64_t target = cfg.photon_target;
+  const uint32_t batch = 131072;
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(target + batch, 0x7FFFFFFFull);
+  ph_loc_w.alloc(cap); ph_light_shot.alloc(cap); ph_meta.alloc(batch); ph_count.alloc(1);
+  WPT_CUDA(cudaMemsetAsync(ph_count.p, 0, sizeof(uint32_t), stream));
+  RenderParams rp = params(WPT_NORMAL_NEE);
+  std::vector<uint32_t> meta(batch);
+  std::vector<uint32_t> shot_of;   // global shot index per stored photon (host order = device order)
+  uint64_t shots = 0, stored = 0, visits = 0;
+  uint32_t guard = 0;
+  while (stored < target) {
+    if (++guard > 100000) throw std::runtime_error("photon warm-up does not converge (no diffuse surface reachable)");
+    uint32_t before = (uint32_t)stored;
+    launch_photon_emit(rp, shots, batch, ph_meta.p, ph_loc_w.p, ph_light_shot.p, ph_count.p, cap, stream);
+    launches += 1;
+    WPT_CUDA(cudaMemcpyAsync(meta.data(), ph_meta.p, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+    uint32_t hits = 0, cut = batch;
+    for (uint32_t i = 0; i < batch; i++)
+      if (meta[i] & 0x80000000u) { hits++; if (before + hits == target) { cut = i + 1; break; } }
+    for (uint32_t i = 0; i < cut; i++) visits += meta[i] & 0x7FFFFFFFu;
+    // bring this batch's records to the host: keep those of shots < cut, in shot order
+    uint32_t appended = 0;
+    for (uint32_t i = 0; i < batch; i++) appended += (meta[i] >> 31);
+    std::vector<float4> lw(appended); std::vector<uint2> ls(appended);
+    if (appended) {
+      WPT_CUDA(cudaMemcpyAsync(lw.data(), ph_loc_w.p + before, appended * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+      WPT_CUDA(cudaMemcpyAsync(ls.data(), ph_light_shot.p + before, appended * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
+      WPT_CUDA(cudaStreamSynchronize(stream));
+    }
+    std::vector<uint32_t> order(appended);
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ls[a].y < ls[b].y; });
+    std::vector<float4> lw2; std::vector<uint2> ls2;
+    for (uint32_t k : order) if (ls[k].y < cut) { lw2.push_back(lw[k]); ls2.push_back(ls[k]); shot_of.push_back((uint32_t)(shots + ls[k].y)); }
+    if (!lw2.empty()) {
+      WPT_CUDA(cudaMemcpyAsync(ph_loc_w.p + before, lw2.data(), lw2.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
+      WPT_CUDA(cudaMemcpyAsync(ph_light_shot.p + before, ls2.data(), ls2.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream));
+    }
+    stored = before + lw2.size();
+    uint32_t st32 = (uint32_t)stored;
+    WPT_CUDA(cudaMemcpyAsync(ph_count.p, &st32, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+    // host copies for the read-back API
+    if (before == 0) { ph_light.clear(); ph_loc.clear(); ph_w.clear(); }
+    for (size_t k = 0; k < lw2.size(); k++) { ph_light.push_back(ls2[k].x); ph_loc.push_back(lw2[k].x); ph_loc.push_back(lw2[k].y); ph_loc.push_back(lw2[k].z); ph_w.push_back(lw2[k].w); }
+    shots += cut;
+  }
+  photon_shots = shots; photon_count = stored;
+  photons_shot_total += shots; photons_stored_total += stored;
+  // the photon rays are rays of this session: rays += shots, node visits += their visits
+  photon_rays += shots; photon_visits += visits;
+  // ---- octree topology, level by level (photon_tree.rs:165-196)
+  const uint32_t N = (uint32_t)stored;
+  std::vector<uint32_t> child_base(1, 0xFFFFFFFFu), count(1, N), depth(1, 0);
+  oc_node_of.alloc(N);
+  WPT_CUDA(cudaMemsetAsync(oc_node_of.p, 0, N * sizeof(uint32_t), stream));
+  size_t frontier_begin = 0;
+  for (uint32_t level = 0;; level++) {
+    if (level > 48) throw std::runtime_error("photon octree too deep (more than 1024 photons at one point)");
+    size_t frontier_end = child_base.size();
+    bool any = false;
+    for (size_t n = frontier_begin; n < frontier_end; n++)
+      if (count[n] > 1024) {   // MAX_PHOTONS_IN_CELL, photon_tree.rs:29
+        child_base[n] = (uint32_t)child_base.size();
+        for (int c = 0; c < 8; c++) { child_base.push_back(0xFFFFFFFFu); count.push_back(0); depth.push_back(level + 1); }
+        any = true;
+      }
+    if (!any) break;
+    oc_child_base.alloc(child_base.size()); oc_count.alloc(child_base.size());
+    WPT_CUDA(cudaMemcpyAsync(oc_child_base.p, child_base.data(), child_base.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    WPT_CUDA(cudaMemsetAsync(oc_count.p, 0, child_base.size() * sizeof(uint32_t), stream));
+    launch_octree_assign(ph_loc_w.p, N, oc_node_of.p, oc_child_base.p, oc_count.p, stream);
+    launches += 1;
+    std::vector<uint32_t> cnt(child_base.size());
+    WPT_CUDA(cudaMemcpyAsync(cnt.data(), oc_count.p, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+    for (size_t n = frontier_end; n < child_base.size(); n++) count[n] = cnt[n];
+    frontier_begin = frontier_end;
+  }
+  const uint32_t nodes = (uint32_t)child_base.size();
+  // ---- bins (fixed point) and CDFs
+  p_child_base.alloc(nodes); p_cum.alloc((size_t)nodes * L); p_bins.alloc((size_t)nodes * L); oc_fx.alloc((size_t)nodes * L);
+  WPT_CUDA(cudaMemcpyAsync(p_child_base.p, child_base.data(), nodes * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  WPT_CUDA(cudaMemsetAsync(oc_fx.p, 0, (size_t)nodes * L * sizeof(unsigned long long), stream));
+  launch_octree_bins(ph_loc_w.p, ph_light_shot.p, N, p_child_base.p, oc_fx.p, L, stream);
+  launch_octree_cdf(oc_fx.p, p_bins.p, p_cum.p, nodes, L, stream);
+  launches += 2;
+  p_nodes = nodes;
+  // ---- read-back copy in DFS pre-order (children in octant order), like the oracle's flattening
+  std::vector<float> cum((size_t)nodes * L), bins((size_t)nodes * L);
+  WPT_CUDA(cudaMemcpyAsync(cum.data(), p_cum.p, cum.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaMemcpyAsync(bins.data(), p_bins.p, bins.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaStreamSynchronize(stream));
+  pt_meta.clear(); pt_cum.clear(); pt_bins.clear();
+  std::vector<uint32_t> st(1, 0);
+  while (!st.empty()) {
+    uint32_t n = st.back(); st.pop_back();
+    bool is_node = child_base[n] != 0xFFFFFFFFu;
+    pt_meta.push_back(depth[n]); pt_meta.push_back(is_node ? 1u : 0u); pt_meta.push_back(is_node ? 0u : count[n]);
+    pt_cum.insert(pt_cum.end(), cum.begin() + (size_t)n * L, cum.begin() + (size_t)(n + 1) * L);
+    pt_bins.insert(pt_bins.end(), bins.begin() + (size_t)n * L, bins.begin() + (size_t)(n + 1) * L);
+    if (is_node) for (int c = 7; c >= 0; c--) st.push_back(child_base[n] + c);
+  }
+  photons_ready = true;
+}
+
+void Context::photon_sample_batch(const float* pts3, const uint32_t* seeds, uint64_t n, uint32_t* light, float* pdf) {
+  require_device();
+  if (!photons_ready) throw std::runtime_error("photon tree not built");
+  if (!n) return;
+  DevBuf<float> d_p, d_pdf; DevBuf<uint32_t> d_s, d_l;
+  d_p.alloc(n * 3); d_pdf.alloc(n); d_s.alloc(n); d_l.alloc(n);
+  WPT_CUDA(cudaMemcpyAsync(d_p.p, pts3, n * 12, cudaMemcpyHostToDevice, stream));
+  WPT_CUDA(cudaMemcpyAsync(d_s.p, seeds, n * 4, cudaMemcpyHostToDevice, stream));
+  launch_photon_sample_batch(params(WPT_PNEE).photons, d_p.p, d_s.p, n, d_l.p, d_pdf.p, stream);
+  WPT_CUDA(cudaMemcpyAsync(light, d_l.p, n * 4, cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaMemcpyAsync(pdf, d_pdf.p, n * 4, cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaStreamSynchronize(stream));
+}
+
+// ------------------------------------------------------------------ sampling strategies
+Context::Strategy& Context::strategy_for(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh) {
+  for (auto& s : strategies) if (s.rx == rx && s.ry == ry && s.rw == rw && s.rh == rh) return s;
+  strategies.emplace_back();
+  Strategy& s = strategies.back();
+  s.rx = rx; s.ry = ry; s.rw = rw; s.rh = rh;
+  return s;
+}
+void Context::clear_strategies() { strategies.clear(); }
+
+// error map + {min, avg, max} of the region (sampling_strategy.rs:133-151, mode-B reduction)
+void Context::region_error(Strategy& s, float stats3[3]) {
+  const uint32_t N = s.rw * s.rh;
+  s.mse.alloc(N);
+  a_stats.alloc(4);
+  unsigned long long init[4] = {0ull, 0x7F800000ull, 0ull, 0ull};
+  WPT_CUDA(cudaMemcpyAsync(a_stats.p, init, sizeof init, cudaMemcpyHostToDevice, stream));
+  launch_error_map(d_accum.p, W, H, s.rx, s.ry, s.rw, s.rh, s.mse.p, a_stats.p, stream);
+  launches += 1;
+  unsigned long long out[4];
+  WPT_CUDA(cudaMemcpyAsync(out, a_stats.p, sizeof out, cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaStreamSynchronize(stream));
+  uint32_t mnb = (uint32_t)out[1], mxb = (uint32_t)out[2];
+  float mn, mx;
+  std::memcpy(&mn, &mnb, 4); std::memcpy(&mx, &mxb, 4);
+  stats3[0] = mn;
+  stats3[1] = (float)(((double)out[0] * (1.0 / 1099511627776.0)) / (double)N);
+  stats3[2] = mx;
+}
+
+void Context::error_map(float* mse, float stats3[3]) {
+  require_device();
+  uint32_t rx, ry, rw, rh;
+  region(&rx, &ry, &rw, &rh);
+  Strategy& s = strategy_for(rx, ry, rw, rh);
+  region_error(s, stats3);
+  if (mse) {
+    WPT_CUDA(cudaMemcpyAsync(mse, s.mse.p, (size_t)rw * rh * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+  }
+}
+void Context::round_spp(uint32_t* spp) {
+  require_device();
+  uint32_t rx, ry, rw, rh;
+  region(&rx, &ry, &rw, &rh);
+  Strategy& s = strategy_for(rx, ry, rw, rh);
+  if (s.round_spp.n < (size_t)rw * rh) throw std::runtime_error("no adaptive / random round has run on this region");
+  WPT_CUDA(cudaMemcpyAsync(spp, s.round_spp.p, (size_t)rw * rh * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  WPT_CUDA(cudaStreamSynchronize(stream));
+}
+
+// Render `take[]` (region-indexed samples per pixel) on this session's rows.
+void Context::render_take(Strategy& s, uint32_t render_type) {
+  ensure_slots(s.rx, s.ry, s.rw, s.rh);
+  launch_gather_slot_spp(s.take.p, s_pixel.p, slots, W, s.rx, s.ry, s.rw, s_spp.p, stream);
+  launches += 1;
+  run_paths(render_type, s_spp.p, 0);
+}
+
+// AdaptiveSamplingStrategy in mode B (see the oracle's mb_render_adaptive for the contract).
+// Every rank evaluates the (cheap) error map of the whole region from the gathered
+// accumulators, so no reduction is needed; each rank renders only its own rows.
+uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange) {
+  const uint32_t N = s.rw * s.rh;
+  if (!N) return 0;
+  if (s.round_left.n < N) { s.round_left.alloc(N); s.take.alloc(N); s.round_spp.alloc(N); launch_fill_u32(s.round_left.p, N, 0, stream); s.left_total = 0; s.started = false; }
+  const uint32_t blocks = (N + 1023) / 1024;
+  a_block_tot.alloc(blocks); a_block_suffix.alloc(blocks);
+  uint64_t used = 0;
+  while (used < budget) {
+    if (s.left_total == 0) {
+      if (!s.started) {   // first queue: 4 samples per pixel (sampling_strategy.rs:197-203)
+        launch_fill_u32(s.round_left.p, N, 4u, stream);
+        s.left_total = 4ull * N;
+        s.started = true;
+      } else {
+        float st3[3];
+        region_error(s, st3);
+        launch_adaptive_spp(s.mse.p, N, st3[0], st3[1], st3[2], s.round_left.p, d_sampling.p, W, s.rx, s.ry, s.rw, stream);
+        a_stats.alloc(4);
+        WPT_CUDA(cudaMemsetAsync(a_stats.p, 0, sizeof(unsigned long long), stream));
+        launch_sum_u32(s.round_left.p, N, a_stats.p, stream);
+        launches += 2;
+        unsigned long long tot = 0;
+        WPT_CUDA(cudaMemcpyAsync(&tot, a_stats.p, sizeof tot, cudaMemcpyDeviceToHost, stream));
+        WPT_CUDA(cudaStreamSynchronize(stream));
+        s.left_total = tot;
+      }
+      WPT_CUDA(cudaMemcpyAsync(s.round_spp.p, s.round_left.p, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    }
+    uint64_t room = budget - used;
+    uint64_t taken;
+    if (s.left_total <= room) {
+      WPT_CUDA(cudaMemcpyAsync(s.take.p, s.round_left.p, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+      taken = s.left_total;
+    } else {
+      // the budget ends inside the round: cut in pop order (from the last pixel backwards)
+      launch_cut(s.round_left.p, N, a_block_tot.p, nullptr, 0, nullptr, 0, stream);
+      std::vector<unsigned long long> tot(blocks), suf(blocks);
+      WPT_CUDA(cudaMemcpyAsync(tot.data(), a_block_tot.p, blocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      WPT_CUDA(cudaStreamSynchronize(stream));
+      unsigned long long run = 0;
+      for (uint32_t b = blocks; b-- > 0;) { suf[b] = run; run += tot[b]; }
+      WPT_CUDA(cudaMemcpyAsync(a_block_suffix.p, suf.data(), blocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+      launch_cut(s.round_left.p, N, nullptr, a_block_suffix.p, room, s.take.p, 1, stream);
+      launches += 2;
+      taken = room;
+    }
+    render_take(s, render_type);
+    launch_sub_u32(s.round_left.p, s.take.p, N, stream);
+    launches += 1;
+    s.left_total -= taken;
+    used += taken;
+    if (exchange) exchange();   // multi-GPU: gather the other ranks' rows before the next error map
+  }
+  return used;
+}
+
+// RandomSamplingStrategy in mode B: `ticks` pixel picks -> samples per pixel for this call.
+void Context::run_random(Strategy& s, uint32_t render_type, uint64_t ticks) {
+  const uint32_t N = s.rw * s.rh;
+  if (!N || !ticks) return;
+  s.take.alloc(N); s.round_spp.alloc(N);
+  launch_fill_u32(s.take.p, N, 0, stream);
+  uint32_t seed = cfg.base_seed ^ (uint32_t)(s.rx * 0x9E3779B1u + s.ry);
+  launch_random_ticks(s.random_ticks, ticks, seed, s.rw, s.rh, s.take.p, stream);
+  launches += 2;
+  s.random_ticks += ticks;
+  WPT_CUDA(cudaMemcpyAsync(s.round_spp.p, s.take.p, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+  render_take(s, render_type);
+}
+
+uint64_t Context::render_adaptive(uint64_t budget) {
+  require_device();
+  uint32_t rx, ry, rw, rh;
+  region(&rx, &ry, &rw, &rh);
+  return run_adaptive(strategy_for(rx, ry, rw, rh), cfg.render_type, budget, exchange_hook);
+}
+void Context::render_random(uint64_t ticks) {
+  require_device();
+  uint32_t rx, ry, rw, rh;
+  region(&rx, &ry, &rw, &rh);
+  run_random(strategy_for(rx, ry, rw, rh), cfg.render_type, ticks);
+}
+
+// wasm_interface.rs:374-384 + tracer.rs:103-123: n/2 ticks for the left half, the rest for the
+// right; a PNEE half first spends ticks on its photon warm-up at 32 shots per tick. Mode-B
+// deviation: the warm-up runs to completion in the first call that needs it and is
+// charged shots/32 ticks, capped at that call's budget.
+void Context::compute(uint64_t num_samples) {
+  require_device();
+  const uint32_t lw = W / 2;
+  struct Half { uint32_t x, w; HalfSettings hs; uint64_t ticks; };
+  Half halves[2] = {{0, lw, left, num_samples / 2}, {lw, W - lw, right, num_samples - num_samples / 2}};
+  for (const Half& h : halves) {
+    if (h.w == 0) continue;
+    uint64_t ticks = h.ticks;
+    if (h.hs.type == WPT_PNEE && !photons_ready) {
+      build_photons();
+      uint64_t cost = photon_shots / 32;
+      ticks = ticks > cost ? ticks - cost : 0;
+    }
+    if (!ticks) continue;
+    Strategy& s = strategy_for(h.x, 0, h.w, H);
+    if (!s.painted) {   // both strategies paint their half blue when created (sampling_strategy.rs:44-50,205-214)
+      launch_fill_region_rgba(d_sampling.p, W, h.x, 0, h.w, H, 0xFFFF0000u, stream);
+      s.painted = true;
+    }
+    if (h.hs.adaptive) run_adaptive(s, h.hs.type, ticks, nullptr);
+    else run_random(s, h.hs.type, ticks);
+  }
+}
 
 }  // namespace wpt

@@ -566,6 +566,310 @@ void launch_resolve_rgba(const float4* accum, uint8_t* rgba, uint32_t n, cudaStr
   k_resolve_rgba<<<(n + 255) / 256, 256, 0, s>>>(accum, reinterpret_cast<uint32_t*>(rgba), n);
 }
 
+// ------------------------------------------------------------------ photons (tracer.rs:126-152)
+// One thread per photon shot k (stream (k, 0, STREAM_PHOTON)): light pick, point on the light,
+// uniform hemisphere direction by rejection (rng.rs:50-68), one Scene::trace, store on a
+// diffuse hit. `meta[i]` = node visits | (stored ? 1<<31 : 0) for the host-side cut.
+WPT_DEV F3 next_hemisphere(Rng& rng, F3 normal) {
+  float x, y, z;
+  for (;;) {
+    x = rng.f32() * 2.0f - 1.0f;
+    y = rng.f32() * 2.0f - 1.0f;
+    z = rng.f32() * 2.0f - 1.0f;
+    float ls = x * x + y * y + z * z;
+    if (!(ls > 1.0f)) break;
+  }
+  F3 v = normalize(f3(x, y, z));
+  if (dot(v, normal) < 0.0f) return -v;
+  return v;
+}
+__global__ void __launch_bounds__(128) k_photon_emit(RenderParams rp, unsigned long long shot0, uint32_t n, uint32_t* meta, float4* rec_loc_w, uint2* rec_light_shot, uint32_t* rec_count, uint32_t rec_cap) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = shot0 + i;
+  Rng rng; rng.s = stream_seed((uint32_t)k, 0u, STREAM_PHOTON, rp.base_seed);
+  uint32_t light_id = rng.range(0, rp.scene.num_lights);
+  F3 pl, ln, inten; float area; uint32_t lsid;
+  pick_random(rp.scene, light_id, rng, &pl, &ln, &inten, &area, &lsid);
+  F3 dir = next_hemisphere(rng, ln);
+  Ray ray = make_ray(pl + dir * WPT_EPSILON, dir);
+  GHit g = trace_g(rp.scene, ray);
+  bool stored = false;
+  if (g.id >= 0) {
+    float t; F3 n; uint32_t mat;
+    if (shape_trace_full(rp.scene.shapes, (uint32_t)g.id, ray, &t, &n, &mat)) {
+      float4 mc = __ldg(&rp.scene.mats[mat].c);
+      if (mc.w == 0.0f) {   // hit.mat.is_diffuse(), tracer.rs:144
+        F3 hp = (ray.o + t * ray.d) + n * WPT_EPSILON;
+        float w = dot(ln, dir) * fmaxf(fmaxf(inten.x, inten.y), inten.z);
+        uint32_t slot = atomicAdd(rec_count, 1u);
+        if (slot < rec_cap) { rec_loc_w[slot] = make_float4(hp.x, hp.y, hp.z, w); rec_light_shot[slot] = make_uint2(light_id, (uint32_t)i); }
+        stored = true;
+      }
+    }
+  }
+  meta[i] = g.visits | (stored ? 0x80000000u : 0u);
+}
+void launch_photon_emit(const RenderParams& rp, unsigned long long shot0, uint32_t n, uint32_t* meta, float4* rec_loc_w, uint2* rec_light_shot, uint32_t* rec_count, uint32_t rec_cap, cudaStream_t s) {
+  if (!n) return;
+  k_photon_emit<<<(n + 127) / 128, 128, 0, s>>>(rp, shot0, n, meta, rec_loc_w, rec_light_shot, rec_count, rec_cap);
+}
+
+// ---- octree (photon_tree.rs). Cells are split level by level; a cell is split iff it finally
+// holds more than 1024 photons (photon_tree.rs:29,179), so the topology does not depend on
+// insertion order. node_of[p] = the deepest existing cell containing photon p.
+WPT_DEV uint32_t tree_descend_child(Cell& b, F3 v) { return octree_child(b, v); }
+__global__ void k_octree_assign(const float4* __restrict__ loc_w, uint32_t n, uint32_t* node_of, const uint32_t* __restrict__ child_base, uint32_t* count) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t node = node_of[p];
+  uint32_t cb = child_base[node];
+  if (cb == 0xFFFFFFFFu) return;   // still a leaf
+  // find the bounds of `node` by walking down from the root, then step into the child
+  F3 v = xyz(loc_w[p]);
+  Cell b = {-1024.0f, -1024.0f, -1024.0f, 1024.0f, 1024.0f, 1024.0f};
+  uint32_t cur = 0;
+  while (cur != node) cur = child_base[cur] + octree_child(b, v);
+  uint32_t child = cb + octree_child(b, v);
+  node_of[p] = child;
+  atomicAdd(&count[child], 1u);
+}
+void launch_octree_assign(const float4* loc_w, uint32_t n, uint32_t* node_of, const uint32_t* child_base, uint32_t* count, cudaStream_t s) {
+  if (!n) return;
+  k_octree_assign<<<(n + 255) / 256, 256, 0, s>>>(loc_w, n, node_of, child_base, count);
+}
+// per-node, per-light weight sums in 2^-40 fixed point (order independent): every
+// photon adds its weight to each cell on its root-to-leaf path (photon_tree.rs:168,176)
+WPT_DEV unsigned long long weight_fx(float w) {
+  double sc = (double)w * 1099511627776.0;
+  if (!(sc > 0.0)) return 0ull;
+  return (unsigned long long)__double2ll_rn(sc);
+}
+__global__ void k_octree_bins(const float4* __restrict__ loc_w, const uint2* __restrict__ light_shot, uint32_t n, const uint32_t* __restrict__ child_base, unsigned long long* fx, uint32_t num_lights) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float4 lw = loc_w[p];
+  F3 v = xyz(lw);
+  unsigned long long w = weight_fx(lw.w);
+  uint32_t light = light_shot[p].x;
+  Cell b = {-1024.0f, -1024.0f, -1024.0f, 1024.0f, 1024.0f, 1024.0f};
+  uint32_t cur = 0;
+  for (;;) {
+    atomicAdd(&fx[(size_t)cur * num_lights + light], w);
+    uint32_t cb = child_base[cur];
+    if (cb == 0xFFFFFFFFu) break;
+    cur = cb + octree_child(b, v);
+  }
+}
+void launch_octree_bins(const float4* loc_w, const uint2* light_shot, uint32_t n, const uint32_t* child_base, unsigned long long* fx, uint32_t num_lights, cudaStream_t s) {
+  if (!n) return;
+  k_octree_bins<<<(n + 255) / 256, 256, 0, s>>>(loc_w, light_shot, n, child_base, fx, num_lights);
+}
+// EmpiricalPDF::recheck_cdf (empirical_pdf.rs:79-93): bins start at 1.0 (:24)
+__global__ void k_octree_cdf(const unsigned long long* __restrict__ fx, float* bins, float* cum, uint32_t num_nodes, uint32_t num_lights) {
+  uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= num_nodes) return;
+  const unsigned long long* f = fx + (size_t)node * num_lights;
+  float* b = bins + (size_t)node * num_lights;
+  float* c = cum + (size_t)node * num_lights;
+  float bin_sum = 0.0f;
+  for (uint32_t i = 0; i < num_lights; i++) {
+    float v = 1.0f + (float)(__ull2double_rn(f[i]) * (1.0 / 1099511627776.0));
+    b[i] = v;
+    bin_sum += v;
+  }
+  c[0] = 0.0f;
+  for (uint32_t i = 1; i < num_lights; i++) c[i] = c[i - 1] + b[i - 1] / bin_sum;
+}
+void launch_octree_cdf(const unsigned long long* fx, float* bins, float* cum, uint32_t num_nodes, uint32_t num_lights, cudaStream_t s) {
+  if (!num_nodes) return;
+  k_octree_cdf<<<(num_nodes + 127) / 128, 128, 0, s>>>(fx, bins, cum, num_nodes, num_lights);
+}
+__global__ void k_photon_sample_batch(DPhotonTree t, const float* __restrict__ pts, const uint32_t* __restrict__ seeds, uint64_t n, uint32_t* light, float* pdf) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Rng rng; rng.s = seeds[i];
+  uint32_t l; float p;
+  photon_sample(t, rng, f3(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]), &l, &p);
+  light[i] = l; pdf[i] = p;
+}
+void launch_photon_sample_batch(const DPhotonTree& t, const float* pts, const uint32_t* seeds, uint64_t n, uint32_t* light, float* pdf, cudaStream_t s) {
+  if (!n) return;
+  k_photon_sample_batch<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(t, pts, seeds, n, light, pdf);
+}
+
+// ------------------------------------------------------------------ adaptive sampling (sampling_strategy.rs:122-182)
+WPT_DEV F3 read_clamped(const float4* __restrict__ accum, uint32_t W, int x, int y) {   // render_target.rs:74-77
+  float4 a = accum[(size_t)y * W + x];
+  float c = (float)__float_as_uint(a.w);
+  F3 v = f3(a.x / c, a.y / c, a.z / c);
+  return f3(fminf(fmaxf(v.x, 0.0f), 1.0f), fminf(fmaxf(v.y, 0.0f), 1.0f), fminf(fmaxf(v.z, 0.0f), 1.0f));
+}
+template <int K> WPT_DEV F3 gaussian(const float4* __restrict__ accum, uint32_t W, uint32_t H, int x, int y) {   // render_target.rs:88-138
+  const float g3[9] = {1, 2, 1, 2, 4, 2, 1, 2, 1};
+  const float g5[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
+  float sum = 0.0f; F3 acc = f3(0, 0, 0);
+  for (int vy = 0; vy < K; vy++)
+    for (int vx = 0; vx < K; vx++) {
+      int px = x + vx - K / 2, py = y + vy - K / 2;
+      float m = K == 3 ? g3[vy * 3 + vx] : g5[vy * 5 + vx];
+      if (px < 0 || py < 0 || px >= (int)W || py >= (int)H) { acc = acc + f3(0, 0, 0); sum += 0.0f; }
+      else { acc = acc + m * read_clamped(accum, W, px, py); sum += m; }
+    }
+  return acc / sum;
+}
+// error per pixel of the region + {sum in 2^-40 fixed point, min, max}; stats[0]=sum (u64),
+// stats[1]=min bits, stats[2]=max bits (errors are >= 0, so uint order == float order)
+__global__ void k_error_map(const float4* __restrict__ accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long fx = 0; uint32_t mn = 0x7F800000u, mx = 0u;
+  if (i < rw * rh) {
+    int x = (int)(rx + i % rw), y = (int)(ry + i / rw);
+    F3 v0 = read_clamped(accum, W, x, y), v1 = gaussian<3>(accum, W, H, x, y), v2 = gaussian<5>(accum, W, H, x, y);
+    F3 d1 = v0 - v1, d2 = v0 - v2;
+    float e = fmaxf(dot(d1, d1), dot(d2, d2));
+    mse[i] = e;
+    fx = weight_fx(e); mn = __float_as_uint(e); mx = mn;
+  }
+  fx = warp_sum_u64(fx);
+  for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_down_sync(0xFFFFFFFFu, mn, o)); mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, o)); }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&stats[0], fx);
+    atomicMin(reinterpret_cast<unsigned int*>(&stats[1]), mn);
+    atomicMax(reinterpret_cast<unsigned int*>(&stats[2]), mx);
+  }
+}
+void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, cudaStream_t s) {
+  uint32_t n = rw * rh;
+  if (!n) return;
+  k_error_map<<<(n + 127) / 128, 128, 0, s>>>(accum, W, H, rx, ry, rw, rh, mse, stats);
+}
+WPT_DEV uint32_t sampling_rgba(F3 v) { return 0xFF000000u | to_u8(v.x) | (to_u8(v.y) << 8) | (to_u8(v.z) << 16); }
+// error -> samples this round (1..33) + the sampling-density view (sampling_strategy.rs:154-174)
+__global__ void k_adaptive_spp(const float* __restrict__ mse, uint32_t n, float mn, float avg, float mx, uint32_t* round_left, uint32_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float e = mse[i];
+  float sc = (e < avg) ? 0.5f * ((e - mn) / (avg - mn)) : 0.5f + 0.5f * ((e - avg) / (mx - avg));
+  sc = fmaxf(fminf(sc, 1.0f), 0.0f);
+  float c = ceilf(1.0f + sc * 32.0f);
+  round_left[i] = c > 0.0f ? (uint32_t)c : 0u;
+  F3 col;
+  if (mn == mx) col = f3(0, 0, 0);
+  else if (sc < 0.5f) col = f3(0.0f, 1.0f, 0.0f) * (1.0f - 2.0f * sc) + f3(0.0f, 0.0f, 1.0f) * 2.0f * sc;   // mix_color, :224-230
+  else col = f3(0.0f, 0.0f, 1.0f) * (1.0f - 2.0f * (sc - 0.5f)) + f3(1.0f, 0.0f, 0.0f) * 2.0f * (sc - 0.5f);
+  sampling_rgba8[(size_t)(ry + i / rw) * W + rx + i % rw] = sampling_rgba(col);
+}
+void launch_adaptive_spp(const float* mse, uint32_t n, float mn, float avg, float mx, uint32_t* round_left, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, cudaStream_t s) {
+  if (!n) return;
+  k_adaptive_spp<<<(n + 255) / 256, 256, 0, s>>>(mse, n, mn, avg, mx, round_left, reinterpret_cast<uint32_t*>(sampling_rgba8), W, rx, ry, rw);
+}
+// fill a region of the sampling view / a u32 array
+__global__ void k_fill_region_rgba(uint32_t* rgba, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t value) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rw * rh) return;
+  rgba[(size_t)(ry + i / rw) * W + rx + i % rw] = value;
+}
+void launch_fill_region_rgba(uint8_t* rgba, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t value, cudaStream_t s) {
+  if (!(rw * rh)) return;
+  k_fill_region_rgba<<<(rw * rh + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t*>(rgba), W, rx, ry, rw, rh, value);
+}
+__global__ void k_fill_u32(uint32_t* a, uint32_t n, uint32_t v) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+void launch_fill_u32(uint32_t* a, uint32_t n, uint32_t v, cudaStream_t s) {
+  if (!n) return;
+  k_fill_u32<<<(n + 255) / 256, 256, 0, s>>>(a, n, v);
+}
+// total of round_left (u64) — decides whether a budget cut is needed
+__global__ void k_sum_u32(const uint32_t* __restrict__ a, uint32_t n, unsigned long long* out) {
+  unsigned long long v = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v += a[i];
+  v = warp_sum_u64(v);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+void launch_sum_u32(const uint32_t* a, uint32_t n, unsigned long long* out, cudaStream_t s) {
+  if (!n) return;
+  int grid = (int)min((n + 255u) / 256u, 1184u);
+  k_sum_u32<<<grid, 256, 0, s>>>(a, n, out);
+}
+// Budget cut in the reference's pop order (LIFO over raster pushes = from the last pixel
+// backwards): take[i] = clamp(budget - sum_{j>i} left[j], 0, left[i]). Two passes: per-block
+// totals, then a block-local reverse scan with the suffix of the later blocks.
+#define CUT_BLOCK 1024
+__global__ void k_cut_block_totals(const uint32_t* __restrict__ left, uint32_t n, unsigned long long* block_tot) {
+  __shared__ unsigned long long sh[CUT_BLOCK / 32];
+  uint32_t i = blockIdx.x * CUT_BLOCK + threadIdx.x;
+  unsigned long long v = i < n ? left[i] : 0;
+  v = warp_sum_u64(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned long long t = 0; for (int k = 0; k < CUT_BLOCK / 32; k++) t += sh[k]; block_tot[blockIdx.x] = t; }
+}
+__global__ void k_cut_apply(const uint32_t* __restrict__ left, uint32_t n, const unsigned long long* __restrict__ block_suffix, unsigned long long budget, uint32_t* take) {
+  // block_suffix[b] = sum of left[] over all blocks after b
+  __shared__ unsigned long long sh[CUT_BLOCK];
+  uint32_t i = blockIdx.x * CUT_BLOCK + threadIdx.x;
+  sh[threadIdx.x] = i < n ? left[i] : 0;
+  __syncthreads();
+  // reverse inclusive scan in shared memory (Hillis-Steele on the reversed index)
+  for (int off = 1; off < CUT_BLOCK; off <<= 1) {
+    unsigned long long add = (threadIdx.x + off < CUT_BLOCK) ? sh[threadIdx.x + off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += add;
+    __syncthreads();
+  }
+  if (i < n) {
+    unsigned long long own = left[i];
+    unsigned long long after = block_suffix[blockIdx.x] + (sh[threadIdx.x] - own);   // samples queued behind this pixel
+    unsigned long long room = budget > after ? budget - after : 0;
+    take[i] = (uint32_t)(own < room ? own : room);
+  }
+}
+void launch_cut(const uint32_t* left, uint32_t n, unsigned long long* block_tot, const unsigned long long* block_suffix, unsigned long long budget, uint32_t* take, int pass, cudaStream_t s) {
+  if (!n) return;
+  uint32_t blocks = (n + CUT_BLOCK - 1) / CUT_BLOCK;
+  if (pass == 0) k_cut_block_totals<<<blocks, CUT_BLOCK, 0, s>>>(left, n, block_tot);
+  else k_cut_apply<<<blocks, CUT_BLOCK, 0, s>>>(left, n, block_suffix, budget, take);
+}
+// slot spp from the region-indexed take[]; round_left -= take for this session's rows only is
+// done by the caller on the region array (all ranks hold the same region arrays)
+__global__ void k_gather_slot_spp(const uint32_t* __restrict__ take, const uint32_t* __restrict__ pixel, uint32_t nslots, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t* slot_spp) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots) return;
+  uint32_t pix = pixel[i];
+  uint32_t y = pix / W, x = pix - y * W;
+  slot_spp[i] = take[(y - ry) * rw + (x - rx)];
+}
+void launch_gather_slot_spp(const uint32_t* take, const uint32_t* pixel, uint32_t nslots, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t* slot_spp, cudaStream_t s) {
+  if (!nslots) return;
+  k_gather_slot_spp<<<(nslots + 255) / 256, 256, 0, s>>>(take, pixel, nslots, W, rx, ry, rw, slot_spp);
+}
+__global__ void k_sub_u32(uint32_t* a, const uint32_t* __restrict__ b, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] -= b[i];
+}
+void launch_sub_u32(uint32_t* a, const uint32_t* b, uint32_t n, cudaStream_t s) {
+  if (!n) return;
+  k_sub_u32<<<(n + 255) / 256, 256, 0, s>>>(a, b, n);
+}
+// Random strategy (sampling_strategy.rs:56-59) in mode B: tick t picks its pixel from stream
+// (t, t>>32, STREAM_PIXEL); take[pixel] counts the ticks of this call.
+__global__ void k_random_ticks(unsigned long long t0, unsigned long long n, uint32_t seed, uint32_t rw, uint32_t rh, uint32_t* take) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long t = t0 + i;
+  Rng rng; rng.s = stream_seed((uint32_t)t, (uint32_t)(t >> 32), STREAM_PIXEL, seed);
+  uint32_t x = rng.range(0, rw);
+  uint32_t y = rng.range(0, rh);
+  atomicAdd(&take[y * rw + x], 1u);
+}
+void launch_random_ticks(unsigned long long t0, unsigned long long n, uint32_t seed, uint32_t rw, uint32_t rh, uint32_t* take, cudaStream_t s) {
+  if (!n) return;
+  k_random_ticks<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t0, n, seed, rw, rh, take);
+}
+
 // ------------------------------------------------------------------ probes
 __global__ void k_primary_probe(RenderParams rp, int32_t* ids, uint32_t* visits, float* dist) {
   uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;

@@ -67,6 +67,23 @@ void launch_primary_probe(const RenderParams& rp, int32_t* ids, uint32_t* visits
 void launch_trace_batch(const RenderParams& rp, const float* o, const float* d, uint64_t n, int32_t* ids, float* dist, uint32_t* visits, float* normals, cudaStream_t s);
 void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t rank, uint32_t world, cudaStream_t s);
 
+// photons
+void launch_photon_emit(const RenderParams& rp, unsigned long long shot0, uint32_t n, uint32_t* meta, float4* rec_loc_w, uint2* rec_light_shot, uint32_t* rec_count, uint32_t rec_cap, cudaStream_t s);
+void launch_octree_assign(const float4* loc_w, uint32_t n, uint32_t* node_of, const uint32_t* child_base, uint32_t* count, cudaStream_t s);
+void launch_octree_bins(const float4* loc_w, const uint2* light_shot, uint32_t n, const uint32_t* child_base, unsigned long long* fx, uint32_t num_lights, cudaStream_t s);
+void launch_octree_cdf(const unsigned long long* fx, float* bins, float* cum, uint32_t num_nodes, uint32_t num_lights, cudaStream_t s);
+void launch_photon_sample_batch(const DPhotonTree& t, const float* pts, const uint32_t* seeds, uint64_t n, uint32_t* light, float* pdf, cudaStream_t s);
+// adaptive / random strategies
+void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, cudaStream_t s);
+void launch_adaptive_spp(const float* mse, uint32_t n, float mn, float avg, float mx, uint32_t* round_left, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, cudaStream_t s);
+void launch_fill_region_rgba(uint8_t* rgba, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t value, cudaStream_t s);
+void launch_fill_u32(uint32_t* a, uint32_t n, uint32_t v, cudaStream_t s);
+void launch_sum_u32(const uint32_t* a, uint32_t n, unsigned long long* out, cudaStream_t s);
+void launch_cut(const uint32_t* left, uint32_t n, unsigned long long* block_tot, const unsigned long long* block_suffix, unsigned long long budget, uint32_t* take, int pass, cudaStream_t s);
+void launch_gather_slot_spp(const uint32_t* take, const uint32_t* pixel, uint32_t nslots, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t* slot_spp, cudaStream_t s);
+void launch_sub_u32(uint32_t* a, const uint32_t* b, uint32_t n, cudaStream_t s);
+void launch_random_ticks(unsigned long long t0, unsigned long long n, uint32_t seed, uint32_t rw, uint32_t rh, uint32_t* take, cudaStream_t s);
+
 int device_sm_count();
 
 }  // namespace wpt

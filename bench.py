@@ -189,6 +189,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from before the warm-up until after the e2e leg (all under load)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 3.0:
+            time.sleep(0.05)
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
         step()
@@ -196,10 +203,6 @@ def main():
     # ---- value: device-timed, inputs resident. Scene (~10 MB) + path state are far larger than
     # what survives in L2 between steps only in part; each step rewrites ~330 MB of path state and
     # accumulators, which exceeds the 126 MB L2 (flush by construction).
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
     pt.profile(True)
     st0 = pt.stats()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -213,7 +216,6 @@ def main():
     prof = pt.profile_read()
     pt.profile(False)
     st1 = pt.stats()
-    clocks = sampler.finish() if sampler else None
     rays_step = prof["rays"] / args.steps
     # stats() is reset by step(); take per-step counts from the last step
     paths_step = st1["paths"]
@@ -249,6 +251,7 @@ def main():
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = rays_all / float(te[0]) / 1e6
+    clocks = sampler.finish() if sampler else None
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -276,9 +279,15 @@ def main():
                 "gpu_launches": int(launches_step) * args.steps, "clocks": clocks}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            r, p, dt = cpu_reference(1, threads)
-            line["cpu_baseline"] = {"value": r / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                                    "sample": "same workload at 1 spp (1920x1080, %.1f s of CPU work on %d threads)" % (dt, threads), "mpaths_per_s": p / dt / 1e6}
+            tr = tp = 0
+            tt = 0.0
+            frames = 0
+            while tt < 10.0 and frames < 8:      # bounded sample: whole 16-spp frames until >= 10 s of CPU work
+                r, p, dt = cpu_reference(args.spp, threads)
+                tr += r; tp += p; tt += dt; frames += 1
+            line["cpu_baseline"] = {"value": tr / tt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                                    "sample": "%d full frame(s) of the same workload (1920x1080 x %d spp), %.1f s on %d threads" % (frames, args.spp, tt, threads),
+                                    "mpaths_per_s": tp / tt / 1e6}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -73,8 +73,7 @@ void Context::clear_targets() {   // RenderTarget::clear / new, render_target.rs
   if (!has_device) return;
   size_t n = (size_t)W * H;
   WPT_CUDA(cudaMemsetAsync(d_accum.p, 0, n * sizeof(float4), stream));
-  for (size_t i = 0; i < n; i++) { h_sampling[i * 4] = h_sampling[i * 4 + 1] = h_sampling[i * 4 + 2] = 0; h_sampling[i * 4 + 3] = 255; }
-  WPT_CUDA(cudaMemcpyAsync(d_sampling.p, h_sampling, n * 4, cudaMemcpyHostToDevice, stream));
+  launch_fill_region_rgba(d_sampling.p, W, 0, 0, W, H, 0xFF000000u, stream);   // black, A = 255
   rgba_stale = true;
 }
 

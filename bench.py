@@ -168,9 +168,8 @@ def main():
     pt = W.PathTracer(W_, H_, W.SCENE_BUNNY, *W.CAM_BUNNY, device=local)
     pt.store_mesh(W.api.MESH_BUNNY_HIGH, verts)
     pt.set_config(bvh_kind=args.bvh, render_type=W.NORMAL_NEE, rank=rank, world=world, engine=args.engine)
-    stream = torch.cuda.current_stream()
-    pt.set_stream(stream.cuda_stream)
-    bufs = pt.device_buffers()
+    # time on the stream the kernels are launched on (torch.cuda.Event only sees the stream it is recorded on)
+    stream = torch.cuda.ExternalStream(pt.device_buffers()["stream"])
 
     def gather_frame():
         """Framebuffer exchange: every rank ends up with every row's accumulators (NCCL all_gather)."""

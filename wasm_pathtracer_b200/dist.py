@@ -48,10 +48,19 @@ def exchange_rows(frame, rank, world, group=None):
     return frame
 
 
+def session_stream(pt):
+    """The CUDA stream the session issues its kernels on, as a torch stream."""
+    return torch.cuda.ExternalStream(pt.device_buffers()["stream"])
+
+
 def allgather_rows(pt, rank, world, group=None):
-    """Exchange the accumulators (rgb sums + sample counts) of a PathTracer session."""
+    """Exchange the accumulators (rgb sums + sample counts) of a PathTracer session.
+
+    The collective is issued on the session's own stream, so it is ordered after the render
+    kernels and before whatever the session launches next (no host synchronisation)."""
     ptr, _ = pt.device_buffers()["accum"]
-    acc = device_tensor(ptr, (pt.H, pt.W, 4), torch.float32)
-    exchange_rows(acc, rank, world, group)
+    with torch.cuda.stream(session_stream(pt)):
+        acc = device_tensor(ptr, (pt.H, pt.W, 4), torch.float32)
+        exchange_rows(acc, rank, world, group)
     pt.mark_accum_dirty()
     return acc

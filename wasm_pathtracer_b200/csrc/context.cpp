@@ -290,6 +290,9 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   static const int env_minb = std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 4;
   static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 4;
   P.t_hi = (uint32_t)env_hi; P.t_lo = (uint32_t)env_lo; P.t_inner = (uint32_t)env_ti;
+  P.simple_scene = 1;
+  for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { P.simple_scene = 0; break; }
+  if (std::getenv("WPT_NO_SIMPLE")) P.simple_scene = 0;
   launch_mega(P, env_minb, stream);
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());

@@ -261,6 +261,7 @@ __device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray& ray, f
 // Tracable::trace_simple for shape record `s`. `limit`/`strict` implement the acceptance test
 // of trace_shapes_md (scene.rs:450-472): the first candidate needs t <= max_dis, later ones
 // 0 < t < best. Rejecting on t before the edge tests does not change any result.
+template <bool SIMPLE>
 WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float limit, bool strict, float* t_out) {
   const float4* p = reinterpret_cast<const float4*>(shapes + idx);
   float4 q0 = __ldg(p), q1 = __ldg(p + 1);
@@ -285,7 +286,7 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
     return true;
   }
   float t;
-  if (type == SH_PLANE) {      // plane.rs:80-99
+  if (SIMPLE || type == SH_PLANE) {      // plane.rs:80-99 (SIMPLE scenes hold triangles and planes only)
     F3 nr = xyz(q1);
     float n_dot_dir = dot(nr, ray.d);
     if (n_dot_dir == 0.0f) return false;
@@ -311,6 +312,7 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
 
 // Tracable::trace for the winning shape (scene.rs:140): distance, Hit::new-normalised normal,
 // material index. Returns false if the full intersection reports no hit.
+template <bool SIMPLE>
 WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float* t_out, F3* n_out, uint32_t* mat_out) {
   const float4* p = reinterpret_cast<const float4*>(shapes + idx);
   float4 q0 = __ldg(p), q1 = __ldg(p + 1);
@@ -333,7 +335,7 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
     if (!(dot(nn, cross(v2 - v1, pt - v1)) + slack >= 0.0f)) return false;
     if (!(dot(nn, cross(v0 - v2, pt - v2)) + slack >= 0.0f)) return false;
     n = (n_dot_d > 0.0f) ? -nn : nn;
-  } else if (type == SH_PLANE) {   // plane.rs:45-77
+  } else if (SIMPLE || type == SH_PLANE) {   // plane.rs:45-77
     F3 nr = xyz(q1);
     float n_dot_dir = dot(nr, ray.d);
     if (n_dot_dir == 0.0f) return false;
@@ -371,12 +373,13 @@ struct GHit { float t; int id; uint32_t visits; uint32_t prims; };
 
 // trace_shapes_md over a leaf (scene.rs:450-472); updates (best_t, best_id) if the leaf
 // reports a hit — a later leaf wins exact ties because the test is t <= max_dis.
+template <bool SIMPLE>
 WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const Ray& ray, float& bound, int& best_id, uint32_t& prims) {
   prims += count;
   bool have = false; float bt = 0.0f; uint32_t bi = 0;
   for (uint32_t i = 0; i < count; i++) {
     float t;
-    if (shape_trace_simple(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) { have = true; bt = t; bi = first + i; }
+    if (shape_trace_simple<SIMPLE>(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) { have = true; bt = t; bi = first + i; }
   }
   if (have) { bound = bt; best_id = (int)bi; }
 }
@@ -429,17 +432,18 @@ WPT_DEV void sort_small(int* id, float* d, uint32_t n) {
 
 // trace_shapes over the infinite shapes + the root guard. Returns true if the BVH has to be
 // traversed (then call trav_step until it returns false).
+template <int BVH, bool SIMPLE>
 WPT_DEV bool trav_begin(const DScene& sc, const Ray& ray, Trav& tv) {
   bool have = false; float it = 0.0f; int iid = -1;
   for (uint32_t i = 0; i < sc.num_inf; i++) {   // scene.rs:426-445: first hit accepted as is
     float t;
-    if (shape_trace_simple(sc.shapes, i, ray, have ? it : WPT_INF, have, &t)) { have = true; it = t; iid = (int)i; }
+    if (shape_trace_simple<SIMPLE>(sc.shapes, i, ray, have ? it : WPT_INF, have, &t)) { have = true; it = t; iid = (int)i; }
   }
   tv.inf_t = it; tv.inf_id = iid;
   tv.bound = have ? it : WPT_INF;
   tv.best_id = -1;
   tv.visits = 0; tv.prims = 0; tv.sp = 0;
-  if (sc.bvh_kind == 4) { tv.lf = 0u; tv.cnt = 0u; return true; }   // no root box test (scene.rs:292-342)
+  if (BVH == 4) { tv.lf = 0u; tv.cnt = 0u; return true; }   // no root box test (scene.rs:292-342)
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
   float4 ra = __ldg(nodes), rb = __ldg(nodes + 1);
   tv.visits = 1;   // the root guard (scene.rs:207,210)
@@ -487,13 +491,15 @@ WPT_DEV bool trav_inner2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* s
   return true;
 }
 // Enter the BVH2 leaf (tv.lf, tv.cnt != 0).
+template <bool SIMPLE>
 WPT_DEV bool trav_leaf2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
   tv.visits += 1;
-  leaf_scan(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
+  leaf_scan<SIMPLE>(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
   return trav_pop2(sc, tv, stack_n, stack_d);
 }
+template <bool SIMPLE>
 WPT_DEV bool trav_step2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
-  return tv.cnt != 0 ? trav_leaf2(sc, ray, tv, stack_n, stack_d) : trav_inner2(sc, ray, tv, stack_n, stack_d);
+  return tv.cnt != 0 ? trav_leaf2<SIMPLE>(sc, ray, tv, stack_n, stack_d) : trav_inner2(sc, ray, tv, stack_n, stack_d);
 }
 
 WPT_DEV bool trav_pop4(Trav& tv, const uint32_t* stack_n, const float* stack_d) {
@@ -523,21 +529,20 @@ WPT_DEV bool trav_inner4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* s
     if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) { stack_n[tv.sp] = (uint32_t)id[i]; stack_d[tv.sp] = d[i]; tv.sp++; }
   return trav_pop4(tv, stack_n, stack_d);
 }
+template <bool SIMPLE>
 WPT_DEV bool trav_leaf4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
   tv.visits += 1;
   uint32_t code = tv.lf;
-  leaf_scan(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims);
+  leaf_scan<SIMPLE>(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims);
   return trav_pop4(tv, stack_n, stack_d);
 }
+template <bool SIMPLE>
 WPT_DEV bool trav_step4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
-  return (int)tv.lf < 0 ? trav_leaf4(sc, ray, tv, stack_n, stack_d) : trav_inner4(sc, ray, tv, stack_n, stack_d);
+  return (int)tv.lf < 0 ? trav_leaf4<SIMPLE>(sc, ray, tv, stack_n, stack_d) : trav_inner4(sc, ray, tv, stack_n, stack_d);
 }
 // true if the node the lane is about to enter is a leaf
-WPT_DEV bool trav_at_leaf(const DScene& sc, const Trav& tv) { return sc.bvh_kind == 4 ? (int)tv.lf < 0 : tv.cnt != 0; }
-
-WPT_DEV bool trav_step(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
-  return sc.bvh_kind == 4 ? trav_step4(sc, ray, tv, stack_n, stack_d) : trav_step2(sc, ray, tv, stack_n, stack_d);
-}
+template <int BVH>
+WPT_DEV bool trav_at_leaf(const Trav& tv) { return BVH == 4 ? (int)tv.lf < 0 : tv.cnt != 0; }
 
 WPT_DEV GHit trav_result(const Trav& tv) {
   GHit g;
@@ -549,14 +554,19 @@ WPT_DEV GHit trav_result(const Trav& tv) {
   return g;
 }
 
-WPT_DEV GHit trace_g(const DScene& sc, const Ray& ray) {
+template <int BVH, bool SIMPLE>
+WPT_DEV GHit trace_g_t(const DScene& sc, const Ray& ray) {
   Trav tv;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
-  if (trav_begin(sc, ray, tv)) {
-    if (sc.bvh_kind == 4) { while (trav_step4(sc, ray, tv, stack_n, stack_d)) {} }
-    else { while (trav_step2(sc, ray, tv, stack_n, stack_d)) {} }
+  if (trav_begin<BVH, SIMPLE>(sc, ray, tv)) {
+    if (BVH == 4) { while (trav_step4<SIMPLE>(sc, ray, tv, stack_n, stack_d)) {} }
+    else { while (trav_step2<SIMPLE>(sc, ray, tv, stack_n, stack_d)) {} }
   }
   return trav_result(tv);
+}
+// generic version (any scene, either BVH): probes, photon emission, the wavefront engine
+__device__ __noinline__ GHit trace_g(const DScene& sc, const Ray& ray) {
+  return sc.bvh_kind == 4 ? trace_g_t<4, false>(sc, ray) : trace_g_t<2, false>(sc, ray);
 }
 
 }  // namespace wpt

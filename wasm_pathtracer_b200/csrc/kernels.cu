@@ -150,11 +150,12 @@ struct ShadeOut {
   F3 next_o, next_d; // the bounce ray
   F3 sh_o, sh_d; float sh_len; int sh_light; F3 contrib;
 };
+template <bool SIMPLE>
 WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, PathRegs& ps, ShadeOut& out) {
   const bool has_nee = rp.render_type != 0;
   out.finished = false; out.survive = false; out.shadow = false;
   bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
-  if (id >= 0) some = shape_trace_full(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat);   // scene.rs:140
+  if (id >= 0) some = shape_trace_full<SIMPLE>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat);   // scene.rs:140
   if (!some) {   // tracer.rs:325-328
     ps.color = ps.color + ps.T * f3(rp.scene.bg_r, rp.scene.bg_g, rp.scene.bg_b);
     out.finished = true;
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(RenderParams rp, PathSt
         Ray ray = make_ray(xyz(ro), xyz(rd));
         PathRegs ps; ps.color = color; ps.T = T; ps.rng = rng; ps.bounced = (flags & SL_BOUNCED) != 0;
         ShadeOut so;
-        shade_hit(rp, ray, __float_as_int(h.y), ps, so);
+        shade_hit<false>(rp, ray, __float_as_int(h.y), ps, so);
         color = ps.color; T = ps.T; rng = ps.rng;
         if (so.finished) finished = true;
         else {
@@ -412,8 +413,8 @@ void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers
 enum : int { PH_NEED = 0, PH_LOGIC = 1, PH_TRAV = 2, PH_DONE = 3 };
 enum : int { ST_GEN = 0, ST_EXTEND = 1, ST_SHADOW = 2 };
 
-template <int MINB>
-__global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
+template <int BVH, bool SIMPLE>
+__global__ void __launch_bounds__(MEGA_THREADS, 4) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
   const unsigned FULL = 0xFFFFFFFFu;
@@ -460,20 +461,20 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
       do {
         const int n_trav = __popc(trav);
         for (;;) {
-          bool at_inner = phase == PH_TRAV && !trav_at_leaf(sc, tv);
+          bool at_inner = phase == PH_TRAV && !trav_at_leaf<BVH>(tv);
           int n_inner = __popc(__ballot_sync(FULL, at_inner));
           if (n_inner == 0) break;
 #ifdef MEGA_INSTR
           i_ts += 1; i_tl += n_inner;
 #endif
           if (at_inner) {
-            bool cont = sc.bvh_kind == 4 ? trav_inner4(sc, ray, tv, stack_n, stack_d) : trav_inner2(sc, ray, tv, stack_n, stack_d);
+            bool cont = BVH == 4 ? trav_inner4(sc, ray, tv, stack_n, stack_d) : trav_inner2(sc, ray, tv, stack_n, stack_d);
             if (!cont) phase = PH_LOGIC;
           }
           if (n_inner * P.t_inner <= n_trav) break;   // few lanes left at inner nodes: let them wait
         }
-        if (phase == PH_TRAV && trav_at_leaf(sc, tv)) {
-          bool cont = sc.bvh_kind == 4 ? trav_leaf4(sc, ray, tv, stack_n, stack_d) : trav_leaf2(sc, ray, tv, stack_n, stack_d);
+        if (phase == PH_TRAV && trav_at_leaf<BVH>(tv)) {
+          bool cont = BVH == 4 ? trav_leaf4<SIMPLE>(sc, ray, tv, stack_n, stack_d) : trav_leaf2<SIMPLE>(sc, ray, tv, stack_n, stack_d);
           if (!cont) phase = PH_LOGIC;
         }
         trav = __ballot_sync(FULL, phase == PH_TRAV);
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         else finish = true;
       } else {
         ShadeOut so;
-        shade_hit(P.rp, ray, g.id, ps, so);
+        shade_hit<SIMPLE>(P.rp, ray, g.id, ps, so);
         if (so.finished) finish = true;
         else if (so.shadow) {
           ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         what = ST_EXTEND; start = true;
       } else phase = PH_NEED;
     }
-    if (start && trav_begin(sc, ray, tv)) phase = PH_TRAV;
+    if (start && trav_begin<BVH, SIMPLE>(sc, ray, tv)) phase = PH_TRAV;
   }
   // ---- counters
   unsigned long long r = warp_sum_u64(c_rays), v = warp_sum_u64(c_visits), pr = warp_sum_u64(c_prims), pa = warp_sum_u64(c_paths);
@@ -536,10 +537,9 @@ void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   int grid = device_sm_count() * blocks_per_sm;
   int need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS);
   if (grid > need) grid = need;
-  if (blocks_per_sm >= 6) k_mega<6><<<grid, MEGA_THREADS, 0, s>>>(P);
-  else if (blocks_per_sm == 5) k_mega<5><<<grid, MEGA_THREADS, 0, s>>>(P);
-  else if (blocks_per_sm == 3) k_mega<3><<<grid, MEGA_THREADS, 0, s>>>(P);
-  else k_mega<4><<<grid, MEGA_THREADS, 0, s>>>(P);
+  const bool b4 = P.rp.scene.bvh_kind == 4;
+  if (P.simple_scene) { if (b4) k_mega<4, true><<<grid, MEGA_THREADS, 0, s>>>(P); else k_mega<2, true><<<grid, MEGA_THREADS, 0, s>>>(P); }
+  else { if (b4) k_mega<4, false><<<grid, MEGA_THREADS, 0, s>>>(P); else k_mega<2, false><<<grid, MEGA_THREADS, 0, s>>>(P); }
 }
 
 // ------------------------------------------------------------------ resolve (render_target.rs:59-64)
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(128) k_photon_emit(RenderParams rp, unsigned l
   bool stored = false;
   if (g.id >= 0) {
     float t; F3 n; uint32_t mat;
-    if (shape_trace_full(rp.scene.shapes, (uint32_t)g.id, ray, &t, &n, &mat)) {
+    if (shape_trace_full<false>(rp.scene.shapes, (uint32_t)g.id, ray, &t, &n, &mat)) {
       float4 mc = __ldg(&rp.scene.mats[mat].c);
       if (mc.w == 0.0f) {   // hit.mat.is_diffuse(), tracer.rs:144
         F3 hp = (ray.o + t * ray.d) + n * WPT_EPSILON;
@@ -899,7 +899,7 @@ __global__ void k_trace_batch(RenderParams rp, const float* __restrict__ o, cons
   visits[i] = g.visits;
   if (normals) {
     float t; F3 nn = f3(0, 0, 0); uint32_t mat;
-    bool ok = g.id >= 0 && shape_trace_full(rp.scene.shapes, (uint32_t)g.id, ray, &t, &nn, &mat);
+    bool ok = g.id >= 0 && shape_trace_full<false>(rp.scene.shapes, (uint32_t)g.id, ray, &t, &nn, &mat);
     normals[i * 3] = ok ? nn.x : 0.0f; normals[i * 3 + 1] = ok ? nn.y : 0.0f; normals[i * 3 + 2] = ok ? nn.z : 0.0f;
   }
 }

@@ -285,10 +285,10 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
   cudaEvent_t a = nullptr, b = nullptr;
   if (profiling) { a = ev_get(); b = ev_get(); WPT_CUDA(cudaEventRecord(a, stream)); }
-  static const int env_hi = std::getenv("WPT_MEGA_THI") ? std::atoi(std::getenv("WPT_MEGA_THI")) : 16;
-  static const int env_lo = std::getenv("WPT_MEGA_TLO") ? std::atoi(std::getenv("WPT_MEGA_TLO")) : 8;
-  static const int env_minb = std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 4;
-  static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 4;
+  static const int env_hi = std::getenv("WPT_MEGA_THI") ? std::atoi(std::getenv("WPT_MEGA_THI")) : 20;
+  static const int env_lo = std::getenv("WPT_MEGA_TLO") ? std::atoi(std::getenv("WPT_MEGA_TLO")) : 10;
+  static const int env_minb = std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 7;   // blocks per SM of the simple BVH2 variant
+  static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 2;
   P.t_hi = (uint32_t)env_hi; P.t_lo = (uint32_t)env_lo; P.t_inner = (uint32_t)env_ti;
   P.simple_scene = 1;
   for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { P.simple_scene = 0; break; }

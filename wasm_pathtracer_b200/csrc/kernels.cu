@@ -413,8 +413,8 @@ void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers
 enum : int { PH_NEED = 0, PH_LOGIC = 1, PH_TRAV = 2, PH_DONE = 3 };
 enum : int { ST_GEN = 0, ST_EXTEND = 1, ST_SHADOW = 2 };
 
-template <int BVH, bool SIMPLE>
-__global__ void __launch_bounds__(MEGA_THREADS, 4) k_mega(MegaParams P) {
+template <int BVH, bool SIMPLE, int MINB>
+__global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
   const unsigned FULL = 0xFFFFFFFFu;
@@ -534,12 +534,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 4) k_mega(MegaParams P) {
 }
 void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   if (!P.nslots) return;
+  if (!(P.simple_scene && P.rp.scene.bvh_kind == 2)) blocks_per_sm = 4;   // the other variants are built for 4 blocks / SM
   int grid = device_sm_count() * blocks_per_sm;
   int need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS);
   if (grid > need) grid = need;
   const bool b4 = P.rp.scene.bvh_kind == 4;
-  if (P.simple_scene) { if (b4) k_mega<4, true><<<grid, MEGA_THREADS, 0, s>>>(P); else k_mega<2, true><<<grid, MEGA_THREADS, 0, s>>>(P); }
-  else { if (b4) k_mega<4, false><<<grid, MEGA_THREADS, 0, s>>>(P); else k_mega<2, false><<<grid, MEGA_THREADS, 0, s>>>(P); }
+  if (P.simple_scene) {
+    if (b4) k_mega<4, true, 4><<<grid, MEGA_THREADS, 0, s>>>(P);
+    else if (blocks_per_sm == 5) k_mega<2, true, 5><<<grid, MEGA_THREADS, 0, s>>>(P);
+    else if (blocks_per_sm == 6) k_mega<2, true, 6><<<grid, MEGA_THREADS, 0, s>>>(P);
+    else if (blocks_per_sm == 7) k_mega<2, true, 7><<<grid, MEGA_THREADS, 0, s>>>(P);
+    else if (blocks_per_sm == 8) k_mega<2, true, 8><<<grid, MEGA_THREADS, 0, s>>>(P);
+    else k_mega<2, true, 4><<<grid, MEGA_THREADS, 0, s>>>(P);
+  } else { if (b4) k_mega<4, false, 4><<<grid, MEGA_THREADS, 0, s>>>(P); else k_mega<2, false, 4><<<grid, MEGA_THREADS, 0, s>>>(P); }
 }
 
 // ------------------------------------------------------------------ resolve (render_target.rs:59-64)

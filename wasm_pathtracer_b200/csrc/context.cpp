@@ -290,6 +290,8 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   static const int env_minb = std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 7;   // blocks per SM of the simple BVH2 variant
   static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 2;
   P.t_hi = (uint32_t)env_hi; P.t_lo = (uint32_t)env_lo; P.t_inner = (uint32_t)env_ti;
+  static const int env_chunk = std::getenv("WPT_MEGA_CHUNK") ? std::atoi(std::getenv("WPT_MEGA_CHUNK")) : 32;
+  P.chunk = (uint32_t)env_chunk;
   P.simple_scene = 1;
   for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { P.simple_scene = 0; break; }
   if (std::getenv("WPT_NO_SIMPLE")) P.simple_scene = 0;

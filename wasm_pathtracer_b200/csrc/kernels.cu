@@ -232,7 +232,21 @@ void launch_setup_slots(const PathState& st, const uint32_t* spp_per_slot, uint3
 __global__ void k_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, uint32_t w, uint32_t rows, uint32_t rank, uint32_t world) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= w * rows) return;
-  uint32_t row = i / w, col = i - row * w;
+  // slot order = 8x4 tiles over the full-tile area (a warp's 32 consecutive slots are one tile:
+  // coherent primary rays, neighbouring surface points afterwards), then the ragged right and
+  // bottom strips in raster order
+  const uint32_t W8 = w & ~7u, R4 = rows & ~3u, nA = W8 * R4, nB = (w - W8) * R4;
+  uint32_t row, col;
+  if (i < nA) {
+    uint32_t t = i >> 5, j = i & 31u, tiles_x = W8 >> 3;
+    col = (t % tiles_x) * 8 + (j & 7u); row = (t / tiles_x) * 4 + (j >> 3);
+  } else if (i < nA + nB) {
+    uint32_t k = i - nA, sw = w - W8;
+    row = k / sw; col = W8 + k % sw;
+  } else {
+    uint32_t k = i - nA - nB;
+    row = R4 + k / w; col = k % w;
+  }
   pixel[i] = (y0 + row * world + rank) * W + x0 + col;
 }
 void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t rank, uint32_t world, cudaStream_t s) {
@@ -427,28 +441,46 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
   uint32_t c_rays = 0, c_visits = 0, c_prims = 0, c_paths = 0;
+  uint32_t chunk_next = 0, chunk_end = 0, spare_next = 0, spare_end = 0; bool queue_empty = false;   // warp-uniform
   Accum acc{P.accum};
 #ifdef MEGA_INSTR
   unsigned long long i_lp = 0, i_ll = 0, i_ts = 0, i_tl = 0, i_sh = 0;   // logic passes, logic lanes, trav steps, trav lanes, shade lanes
 #endif
 
   for (;;) {
-    // ---- pixel fetch: one atomic per warp
+    // ---- pixel fetch: the warp owns a chunk of consecutive slots (= neighbouring tiles) and
+    // hands them to its lanes; one atomic per chunk
     unsigned need = __ballot_sync(FULL, phase == PH_NEED);
     if (need) {
-      uint32_t base = 0;
-      int leader = __ffs(need) - 1;
-      if ((int)lane == leader) base = atomicAdd(P.work_counter, (uint32_t)__popc(need));
-      base = __shfl_sync(FULL, base, leader);
+      uint32_t want = (uint32_t)__popc(need);
+      if (chunk_next + want > chunk_end && !queue_empty) {
+        // not enough left: the rest of the chunk is used first, then a new chunk is fetched
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(P.work_counter, P.chunk);
+        base = __shfl_sync(FULL, base, 0);
+        if (chunk_next >= chunk_end) { chunk_next = base; chunk_end = min(base + P.chunk, P.nslots); if (base >= P.nslots) { chunk_end = chunk_next = P.nslots; queue_empty = true; } }
+        else { spare_next = base; spare_end = min(base + P.chunk, P.nslots); if (base >= P.nslots) { spare_next = spare_end = P.nslots; queue_empty = true; } }
+      }
       if (phase == PH_NEED) {
-        uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
-        if (idx < P.nslots) {
+        uint32_t r = (uint32_t)__popc(need & ((1u << lane) - 1u));
+        uint32_t avail = chunk_end - chunk_next;
+        uint32_t idx = r < avail ? chunk_next + r : spare_next + (r - avail);
+        bool ok = r < avail ? true : (idx < spare_end);
+        if (ok) {
           pix = P.pixel[idx];
           uint32_t spp = P.spp_per_slot ? P.spp_per_slot[idx] : P.uniform_spp;
           s = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
           s_end = s + spp;
           what = ST_GEN; phase = PH_LOGIC;
-        } else phase = PH_DONE;
+        } else if (queue_empty) phase = PH_DONE;
+      }
+      {
+        uint32_t avail = chunk_end - chunk_next;
+        if (want <= avail) chunk_next += want;
+        else {
+          uint32_t from_spare = min(want - avail, spare_end - spare_next);
+          chunk_next = spare_next + from_spare; chunk_end = spare_end; spare_next = spare_end = 0;
+        }
       }
     }
     unsigned trav = __ballot_sync(FULL, phase == PH_TRAV);

@@ -54,6 +54,7 @@ struct MegaParams {
   uint32_t uniform_spp, nslots;
   uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
   uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
+  uint32_t chunk;                 // slots a warp fetches at a time (multiple of 32)
   uint32_t simple_scene;          // shapes are triangles and planes only: kernel variant without torus / box code
   uint32_t* work_counter;         // zeroed before the launch
   unsigned long long* counters;

@@ -185,7 +185,7 @@ RenderParams Context::params(uint32_t render_type) const {
   rp.cam.cx = std::cos(cam[3]); rp.cam.sx = std::sin(cam[3]); rp.cam.cy = std::cos(cam[4]); rp.cam.sy = std::sin(cam[4]);
   float fw = (float)W, fh = (float)H;
   rp.cam.w_inv = 1.0f / fw; rp.cam.h_inv = 1.0f / fh; rp.cam.ar = fw / fh;   // tracer.rs:168-172
-  rp.photons.child_base = p_child_base.p; rp.photons.cum = p_cum.p;
+  rp.photons.child_base = p_child_base.p; rp.photons.cum = p_cum.p; rp.photons.nbr = p_nbr.p;
   rp.photons.num_lights = (uint32_t)scene.lights.size(); rp.photons.num_nodes = p_nodes;
   rp.W = W; rp.H = H;
   rp.render_type = render_type; rp.light_debug = cfg.light_debug; rp.base_seed = cfg.base_seed;

@@ -86,7 +86,7 @@ struct Context {
   DevBuf<uint2> ph_light_shot;
   DevBuf<uint32_t> ph_meta, ph_count, oc_node_of, oc_child_base, oc_count;
   DevBuf<unsigned long long> oc_fx;
-  DevBuf<uint32_t> p_child_base;
+  DevBuf<uint32_t> p_child_base, p_nbr;
   DevBuf<float> p_cum, p_bins;
   uint32_t p_nodes = 0;
   bool photons_ready = false;

@@ -106,6 +106,57 @@ void Context::build_photons() {
   launch_octree_cdf(oc_fx.p, p_bins.p, p_cum.p, nodes, L, stream);
   launches += 2;
   p_nodes = nodes;
+  // ---- neighbour table for the leaves: the node the reference's walk to the leaf's depth
+  // ends in for a point one cell further in each of the 26 directions (same f32 halving as
+  // octree_child, photon_tree.rs:235-251)
+  {
+    struct HB { float lo[3], hi[3]; };
+    std::vector<HB> bounds(nodes);
+    bounds[0] = HB{{-1024.0f, -1024.0f, -1024.0f}, {1024.0f, 1024.0f, 1024.0f}};
+    for (uint32_t n = 0; n < nodes; n++) {   // children always have larger indices than their parent
+      if (child_base[n] == 0xFFFFFFFFu) continue;
+      const HB& b = bounds[n];
+      float c[3] = {0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2])};
+      for (int k = 0; k < 8; k++) {
+        HB cb;
+        int up[3] = {(k >> 2) & 1, (k >> 1) & 1, k & 1};   // octant = 4 [x>=cx] + 2 [y>=cy] + [z>=cz]
+        for (int a = 0; a < 3; a++) { cb.lo[a] = up[a] ? c[a] : b.lo[a]; cb.hi[a] = up[a] ? b.hi[a] : c[a]; }
+        bounds[child_base[n] + k] = cb;
+      }
+    }
+    auto walk = [&](uint32_t d, const float q[3]) {
+      HB b = bounds[0];
+      uint32_t nd = 0;
+      for (;;) {
+        uint32_t cbase = child_base[nd];
+        if (cbase == 0xFFFFFFFFu || d == 0) return nd;
+        uint32_t idx = 0;
+        for (int a = 0; a < 3; a++) {
+          float c = 0.5f * (b.lo[a] + b.hi[a]);
+          if (q[a] < c) b.hi[a] = c; else { b.lo[a] = c; idx += (a == 0 ? 4u : a == 1 ? 2u : 1u); }
+        }
+        nd = cbase + idx; d--;
+      }
+    };
+    std::vector<uint32_t> nbr((size_t)nodes * 27, 0u);
+    for (uint32_t n = 0; n < nodes; n++) {
+      if (child_base[n] != 0xFFFFFFFFu) continue;
+      const HB& b = bounds[n];
+      for (int k = 0; k < 27; k++) {
+        int d3[3] = {k % 3 - 1, (k / 3) % 3 - 1, k / 9 - 1};
+        float q[3];
+        for (int a = 0; a < 3; a++) {
+          float sz = b.hi[a] - b.lo[a];
+          float c = 0.5f * (b.lo[a] + b.hi[a]);
+          q[a] = c + (float)d3[a] * sz;   // centre of the neighbour cell: exact (dyadic)
+        }
+        nbr[(size_t)n * 27 + k] = walk(depth[n], q);
+      }
+    }
+    p_nbr.alloc(nbr.size());
+    WPT_CUDA(cudaMemcpyAsync(p_nbr.p, nbr.data(), nbr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+  }
   // ---- read-back copy in DFS pre-order (children in octant order), like the oracle's flattening
   std::vector<float> cum((size_t)nodes * L), bins((size_t)nodes * L);
   WPT_CUDA(cudaMemcpyAsync(cum.data(), p_cum.p, cum.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));

@@ -71,6 +71,24 @@ WPT_DEV void axis_weight(float v, float c, float lo, float hi, float sz, float* 
   if (v > c) { float lw = (hi - (v - sz * 0.5f)) / sz; *w = lw; *w_adj = 1.0f - lw; *off = 1.0f; }
   else { float rw = ((v + sz * 0.5f) - lo) / sz; *w = rw; *w_adj = 1.0f - rw; *off = -1.0f; }
 }
+// Same result as the reference's ten root-to-cell walks (find_leaf + find_node_cdf for the
+// sampled cell + 8 for the interpolated pdf) with one: find_leaf. The eight query points are
+// the corners of a box one cell wide, so each of the seven others lies in the face / edge /
+// corner neighbour of the leaf: `nbr[leaf][27]` holds, per direction, the node the reference's
+// walk to the leaf's depth ends in (same depth, or the shallower leaf covering it), computed on
+// the host with the same f32 halving. A corner is only taken from the table if its coordinate
+// really lies inside the neighbour interval (f32 rounding of v + size can put it on the far
+// boundary; cells touching the +-1024 cube are excluded too) — otherwise the walk is redone.
+WPT_DEV uint32_t tree_walk(const DPhotonTree& t, uint32_t depth, F3 q) {   // find_node_cdf, photon_tree.rs:216-231
+  Cell c = {-1024.0f, -1024.0f, -1024.0f, 1024.0f, 1024.0f, 1024.0f};
+  uint32_t nd = 0;
+  for (;;) {
+    uint32_t cb = __ldg(t.child_base + nd);
+    if (cb == 0xFFFFFFFFu || depth == 0) return nd;
+    nd = cb + octree_child(c, q);
+    depth--;
+  }
+}
 __device__ __noinline__ void photon_sample(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* light, float* pdf_out) {
   const float size = 1024.0f;
   if (v.x < -size || v.y < -size || v.z < -size || v.x > size || v.y > size || v.z > size) {
@@ -95,12 +113,28 @@ __device__ __noinline__ void photon_sample(const DPhotonTree& t, Rng& rng, F3 v,
   bool self_x = rng.f32() <= wx;
   bool self_y = rng.f32() <= wy;
   bool self_z = rng.f32() <= wz;
-  F3 sv = v;
-  sv = sv + (self_x ? f3(0.0f, 0.0f, 0.0f) : ox * f3(xs, 0.0f, 0.0f));
-  sv = sv + (self_y ? f3(0.0f, 0.0f, 0.0f) : oy * f3(0.0f, ys, 0.0f));
-  sv = sv + (self_z ? f3(0.0f, 0.0f, 0.0f) : oz * f3(0.0f, 0.0f, zs));
-  // EmpiricalPDF::sample (empirical_pdf.rs:43-61)
-  uint32_t sn = tree_find_node(t, depth, sv);
+  // neighbour coordinates: v + (ajx, 0, 0) etc. (photon_tree.rs:141-156); adding +-0.0 keeps v
+  const float X1 = v.x + xs * ox, Y1 = v.y + ys * oy, Z1 = v.z + zs * oz;
+  // is the shifted coordinate strictly inside the adjacent interval (and that inside the cube)?
+  bool okx = ox > 0.0f ? (X1 >= b.x1 && X1 < b.x1 + xs && b.x1 + xs <= size) : (X1 >= b.x0 - xs && X1 < b.x0 && b.x0 - xs >= -size);
+  bool oky = oy > 0.0f ? (Y1 >= b.y1 && Y1 < b.y1 + ys && b.y1 + ys <= size) : (Y1 >= b.y0 - ys && Y1 < b.y0 && b.y0 - ys >= -size);
+  bool okz = oz > 0.0f ? (Z1 >= b.z1 && Z1 < b.z1 + zs && b.z1 + zs <= size) : (Z1 >= b.z0 - zs && Z1 < b.z0 && b.z0 - zs >= -size);
+  const int dx = ox > 0.0f ? 2 : 0, dy = oy > 0.0f ? 2 : 0, dz = oz > 0.0f ? 2 : 0;   // direction index 0,1,2 = -1,0,+1
+  const uint32_t* nb = t.nbr + (size_t)node * 27;
+  uint32_t n8[8];
+  n8[0] = node;
+#pragma unroll
+  for (int k = 1; k < 8; k++) {
+    const bool bx = k & 1, by = k & 2, bz = k & 4;
+    bool ok = (!bx || okx) && (!by || oky) && (!bz || okz);
+    if (ok) n8[k] = __ldg(nb + (bx ? dx : 1) + 3 * (by ? dy : 1) + 9 * (bz ? dz : 1));
+    else n8[k] = tree_walk(t, depth, f3(bx ? X1 : v.x, by ? Y1 : v.y, bz ? Z1 : v.z));
+  }
+  // EmpiricalPDF::sample (empirical_pdf.rs:43-61) on the sampled cell
+  uint32_t sel = (self_x ? 0u : 1u) + (self_y ? 0u : 2u) + (self_z ? 0u : 4u);
+  uint32_t sn = n8[0];
+#pragma unroll
+  for (int k = 1; k < 8; k++) if (sel == (uint32_t)k) sn = n8[k];
   const float* cum = t.cum + (size_t)sn * t.num_lights;
   float r = rng.f32();
   uint32_t low = 0, high = t.num_lights;
@@ -109,16 +143,15 @@ __device__ __noinline__ void photon_sample(const DPhotonTree& t, Rng& rng, F3 v,
     if (__ldg(cum + mid) <= r) low = mid; else high = mid;
   }
   uint32_t res = low;
-  float ajx = xs * ox, ajy = ys * oy, ajz = zs * oz;
-  float pdf = 0.0f;
-  pdf += tree_bin_prob(t, tree_find_node(t, depth, v), res) * wx * wy * wz;
-  pdf += tree_bin_prob(t, tree_find_node(t, depth, v + f3(ajx, 0.0f, 0.0f)), res) * ax * wy * wz;
-  pdf += tree_bin_prob(t, tree_find_node(t, depth, v + f3(0.0f, ajy, 0.0f)), res) * wx * ay * wz;
-  pdf += tree_bin_prob(t, tree_find_node(t, depth, v + f3(0.0f, 0.0f, ajz)), res) * wx * wy * az;
-  pdf += tree_bin_prob(t, tree_find_node(t, depth, v + f3(ajx, ajy, 0.0f)), res) * ax * ay * wz;
-  pdf += tree_bin_prob(t, tree_find_node(t, depth, v + f3(0.0f, ajy, ajz)), res) * wx * ay * az;
-  pdf += tree_bin_prob(t, tree_find_node(t, depth, v + f3(ajx, 0.0f, ajz)), res) * ax * wy * az;
-  pdf += tree_bin_prob(t, tree_find_node(t, depth, v + f3(ajx, ajy, ajz)), res) * ax * ay * az;
+  float pdf = 0.0f;   // the reference's order of the eight terms (photon_tree.rs:149-156)
+  pdf += tree_bin_prob(t, n8[0], res) * wx * wy * wz;
+  pdf += tree_bin_prob(t, n8[1], res) * ax * wy * wz;
+  pdf += tree_bin_prob(t, n8[2], res) * wx * ay * wz;
+  pdf += tree_bin_prob(t, n8[4], res) * wx * wy * az;
+  pdf += tree_bin_prob(t, n8[3], res) * ax * ay * wz;
+  pdf += tree_bin_prob(t, n8[6], res) * wx * ay * az;
+  pdf += tree_bin_prob(t, n8[5], res) * ax * wy * az;
+  pdf += tree_bin_prob(t, n8[7], res) * ax * ay * az;
   *light = res;
   *pdf_out = pdf;
 }

@@ -52,6 +52,7 @@ struct DCamera {
 // (8 children contiguous, octant order) or 0xFFFFFFFF for a leaf; cum[i*L .. i*L+L) = CDF.
 struct DPhotonTree {
   const uint32_t* child_base;
+  const uint32_t* nbr;      // [node][27]: neighbour cell per direction (dx+1) + 3(dy+1) + 9(dz+1), leaves only
   const float* cum;
   uint32_t num_lights;
   uint32_t num_nodes;

@@ -259,12 +259,16 @@ def main():
         alg_bytes = 32.0 * prof["node_visits"] + 36.0 * prof["prim_tests"] + (24.0 * 2 + 36 + 16) * prof["rays"]
         trace_s = prof["trace_ms"] * 1e-3
         achieved = alg_bytes / trace_s / 1e9 if trace_s > 0 else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if args.engine == 0 and world == 1 and args.spp == SPP and args.bvh == 2 and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")   # dram read + write of one launch, ncu --set full
         roofline = {"bound": "hbm", "kernel": "k_trace" if args.engine == 1 else "k_mega", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": alg_bytes / max(1, prof["trace_launches"]), "avg_launch_ms": prof["trace_ms"] / max(1, prof["trace_launches"]),
-                    "trace_share_of_step": prof["trace_ms"] / ms if ms else None, "shade_share_of_step": prof["shade_ms"] / ms if ms else None,
+                    "kernel_share_of_step": prof["trace_ms"] / ms if ms else None, "shade_kernel_share_of_step": prof["shade_ms"] / ms if ms else None,
                     "visits_per_ray": prof["node_visits"] / max(1, prof["rays"]), "prims_per_ray": prof["prim_tests"] / max(1, prof["rays"]),
-                    "note": "scene (~10 MB) is L2-resident: the honest bounds are L2 bandwidth/latency and FP32 issue (DESIGN.md); HBM peak is the schema's denominator"}
+                    "note": "achieved = algorithmic bytes (SURVEY 8d) / kernel time; the scene (~10 MB) is cache resident, DRAM traffic is ~1.4% of that: the real bounds are issue rate and divergence (DESIGN.md 5)"}
         line = {"metric": "Mrays/s (bunny 1080p, 16 spp, NormalNEE, BVH%d)" % args.bvh, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (procedural stand-in mesh, 81920 triangles; reference bunny2.obj is a stripped blob)",

@@ -287,7 +287,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   if (profiling) { a = ev_get(); b = ev_get(); WPT_CUDA(cudaEventRecord(a, stream)); }
   static const int env_hi = std::getenv("WPT_MEGA_THI") ? std::atoi(std::getenv("WPT_MEGA_THI")) : 20;
   static const int env_lo = std::getenv("WPT_MEGA_TLO") ? std::atoi(std::getenv("WPT_MEGA_TLO")) : 10;
-  static const int env_minb = std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 7;   // blocks per SM of the simple BVH2 variant
+  static const int env_minb = std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 8;   // blocks per SM of the simple BVH2 variant
   static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 2;
   P.t_hi = (uint32_t)env_hi; P.t_lo = (uint32_t)env_lo; P.t_inner = (uint32_t)env_ti;
   static const int env_chunk = std::getenv("WPT_MEGA_CHUNK") ? std::atoi(std::getenv("WPT_MEGA_CHUNK")) : 32;

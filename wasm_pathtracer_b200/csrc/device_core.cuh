@@ -368,6 +368,28 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
   return true;
 }
 
+// Normal + material of a hit whose distance `t` is already known from the traversal. Scene::trace
+// re-intersects the winner with Tracable::trace (scene.rs:140); for triangles and planes that
+// recomputes exactly the same `t` and, since the shape was just hit, cannot miss — only the side
+// test n.d > 0 and the Hit::new normalisation are left (triangle.rs:143-147, plane.rs:61-75).
+WPT_DEV void shape_hit_normal_tri_plane(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, F3* n_out, uint32_t* mat_out) {
+  const float4* p = reinterpret_cast<const float4*>(shapes + idx);
+  float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+  uint32_t meta = __float_as_uint(q0.w);
+  *mat_out = meta >> 8;
+  F3 n;
+  if ((meta & 0xFFu) == SH_TRIANGLE) {
+    float4 q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    F3 nu = f3(q1.w, q2.w, q3.x);
+    F3 nn = f3(q3.y, q3.z, q3.w);
+    n = (dot(nu, ray.d) > 0.0f) ? -nn : nn;
+  } else {
+    F3 nr = xyz(q1);
+    n = (dot(nr, ray.d) > 0.0f) ? -nr : nr;
+  }
+  *n_out = normalize(n);   // Hit::new, ray.rs:59-62
+}
+
 // ------------------------------------------------------------------ Scene::trace_g (scene.rs:162-184)
 struct GHit { float t; int id; uint32_t visits; uint32_t prims; };
 

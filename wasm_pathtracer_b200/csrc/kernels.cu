@@ -184,11 +184,14 @@ struct ShadeOut {
   F3 sh_o, sh_d; float sh_len; int sh_light; F3 contrib;
 };
 template <bool SIMPLE>
-WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, PathRegs& ps, ShadeOut& out) {
+WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_hit, PathRegs& ps, ShadeOut& out) {
   const bool has_nee = rp.render_type != 0;
   out.finished = false; out.survive = false; out.shadow = false;
   bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
-  if (id >= 0) some = shape_trace_full<SIMPLE>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat);   // scene.rs:140
+  if (id >= 0) {   // scene.rs:140
+    if (SIMPLE) { shape_hit_normal_tri_plane(rp.scene.shapes, (uint32_t)id, ray, &n, &mat); t = t_hit; some = true; }
+    else some = shape_trace_full<false>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat);
+  }
   if (!some) {   // tracer.rs:325-328
     ps.color = ps.color + ps.T * f3(rp.scene.bg_r, rp.scene.bg_g, rp.scene.bg_b);
     out.finished = true;
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(RenderParams rp, PathSt
         Ray ray = make_ray(xyz(ro), xyz(rd));
         PathRegs ps; ps.color = color; ps.T = T; ps.rng = rng; ps.bounced = (flags & SL_BOUNCED) != 0;
         ShadeOut so;
-        shade_hit<false>(rp, ray, __float_as_int(h.y), ps, so);
+        shade_hit<false>(rp, ray, __float_as_int(h.y), h.x, ps, so);
         color = ps.color; T = ps.T; rng = ps.rng;
         if (so.finished) finished = true;
         else {
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
   uint32_t c_rays = 0, c_visits = 0, c_prims = 0, c_paths = 0;
   uint32_t chunk_next = 0, chunk_end = 0, spare_next = 0, spare_end = 0; bool queue_empty = false;   // warp-uniform
-  Accum acc{P.accum};
+  F3 acc_rgb = f3(0, 0, 0);   // this pixel's accumulator (render_target.rs:8): loaded at fetch, stored when the pixel is done
 #ifdef MEGA_INSTR
   unsigned long long i_lp = 0, i_ll = 0, i_ts = 0, i_tl = 0, i_sh = 0;   // logic passes, logic lanes, trav steps, trav lanes, shade lanes
 #endif
@@ -502,7 +505,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         if (ok) {
           pix = P.pixel[idx];
           uint32_t spp = P.spp_per_slot ? P.spp_per_slot[idx] : P.uniform_spp;
-          s = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
+          float4 a0 = P.accum[pix];
+          acc_rgb = xyz(a0);
+          s = __float_as_uint(a0.w);   // samples accumulated so far = next sample index
           s_end = s + spp;
           what = ST_GEN; phase = PH_LOGIC;
         } else if (queue_empty) phase = PH_DONE;
@@ -563,7 +568,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         else finish = true;
       } else {
         ShadeOut so;
-        shade_hit<SIMPLE>(P.rp, ray, g.id, ps, so);
+        shade_hit<SIMPLE>(P.rp, ray, g.id, g.t, ps, so);
         if (so.finished) finish = true;
         else if (so.shadow) {
           ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
@@ -572,7 +577,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         } else if (so.survive) { ray = make_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
         else finish = true;
       }
-      if (finish) { acc.add(pix, ps.color); c_paths += 1; s += 1; what = ST_GEN; }
+      if (finish) { acc_rgb = acc_rgb + ps.color; c_paths += 1; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
     }
     if (what == ST_GEN) {
       if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream
@@ -583,7 +588,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         ray = camera_ray(P.rp.cam, px, py, j1, j2);
         ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
         what = ST_EXTEND; start = true;
-      } else phase = PH_NEED;
+      } else {
+        P.accum[pix] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, __uint_as_float(s));
+        phase = PH_NEED;
+      }
     }
     if (start && trav_begin<BVH, SIMPLE>(sc, ray, tv)) phase = PH_TRAV;
   }

@@ -295,14 +295,23 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   P.simple_scene = 1;
   for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { P.simple_scene = 0; break; }
   if (std::getenv("WPT_NO_SIMPLE")) P.simple_scene = 0;
-  launch_mega(P, env_minb, stream);
+  if (cfg.engine == 2) {   // block-pool kernel: refill threshold of the traversal warps, slots and blocks per SM
+    static const int p_tlo = std::getenv("WPT_POOL_TLO") ? std::atoi(std::getenv("WPT_POOL_TLO")) : 20;
+    static const int p_minb = std::getenv("WPT_POOL_MINB") ? std::atoi(std::getenv("WPT_POOL_MINB")) : 4;
+    static const int p_slots = std::getenv("WPT_POOL_SLOTS") ? std::atoi(std::getenv("WPT_POOL_SLOTS")) : 384;
+    static const int p_chunk = std::getenv("WPT_POOL_CHUNK") ? std::atoi(std::getenv("WPT_POOL_CHUNK")) : 256;
+    static const int p_thi = std::getenv("WPT_POOL_THI") ? std::atoi(std::getenv("WPT_POOL_THI")) : 24;       // logic warps want at least this many paths
+    static const int p_tsw = std::getenv("WPT_POOL_TSWITCH") ? std::atoi(std::getenv("WPT_POOL_TSWITCH")) : 16;
+    P.t_lo = (uint32_t)p_tlo; P.t_hi = (uint32_t)p_thi; P.t_switch = (uint32_t)p_tsw; P.chunk = (uint32_t)p_chunk;
+    launch_pool(P, p_minb, (uint32_t)p_slots, stream);
+  } else launch_mega(P, env_minb, stream);
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());
   launches += 1; iterations += 1;
   rgba_stale = true;
 }
 
-// cfg.engine: 0 = persistent kernel (default), 1 = multi-kernel wavefront
+// cfg.engine: 0 = persistent kernel k_mega (default), 1 = multi-kernel wavefront, 2 = block-pool kernel k_pool
 void Context::run_paths(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp) {
   if (cfg.engine == 1) run_wavefront(render_type, d_spp_per_slot, uniform_spp);
   else run_persistent(render_type, d_spp_per_slot, uniform_spp);
@@ -339,7 +348,7 @@ void Context::stats(uint64_t out[8]) {
   WPT_CUDA(cudaStreamSynchronize(stream));
   if (std::getenv("WPT_DEBUG_COUNTERS")) {
     std::fprintf(stderr, "wpt counters:");
-    for (int i = 0; i < 12; i++) std::fprintf(stderr, " %llu", h_counters[i]);
+    for (int i = 0; i < 14; i++) std::fprintf(stderr, " %llu", h_counters[i]);
     std::fprintf(stderr, "\n");
   }
   out[0] = h_counters[0] + photon_rays; out[1] = h_counters[2]; out[2] = h_counters[1] + photon_visits;

@@ -475,8 +475,32 @@ WPT_DEV bool trav_begin(const DScene& sc, const Ray& ray, Trav& tv) {
   return true;
 }
 
-// pop: next node to enter, skipping entries the current bound has made unreachable
-WPT_DEV bool trav_pop2(const DScene& sc, Trav& tv, const uint32_t* stack_n, const float* stack_d) {
+// The traversal is cut into three kinds of step so that a warp can run each kind with all the
+// lanes that need it (one code site each): enter an inner node, scan a leaf, pop.
+// AABB::hit (aabb.rs:132-164) without early returns: same comparisons, same NaN behaviour.
+WPT_DEV bool box_hit_sel(float x0, float y0, float z0, float x1, float y1, float z1, const Ray& r, float* t) {
+  float tx1 = (x0 - r.o.x) * r.inv.x, tx2 = (x1 - r.o.x) * r.inv.x;
+  float ty1 = (y0 - r.o.y) * r.inv.y, ty2 = (y1 - r.o.y) * r.inv.y;
+  float tz1 = (z0 - r.o.z) * r.inv.z, tz2 = (z1 - r.o.z) * r.inv.z;
+  float tmin = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fminf(tz1, tz2));
+  float tmax = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+  bool front = tmin >= 0.0f;
+  *t = front ? tmin : 0.0f;
+  return !(tmin > tmax) && (front || tmax >= 0.0f);
+}
+// pop: next node to enter, skipping entries the current bound has made unreachable. Returns
+// false when the stack is empty (the traversal is finished).
+template <int BVH>
+WPT_DEV bool trav_pop(const DScene& sc, Trav& tv, const uint32_t* stack_n, const float* stack_d) {
+  if (BVH == 4) {
+    while (tv.sp > 0) {
+      tv.sp--;
+      if (stack_d[tv.sp] > tv.bound) continue;
+      tv.lf = stack_n[tv.sp];
+      return true;
+    }
+    return false;
+  }
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
   while (tv.sp > 0) {
     tv.sp--;
@@ -487,80 +511,50 @@ WPT_DEV bool trav_pop2(const DScene& sc, Trav& tv, const uint32_t* stack_n, cons
   }
   return false;
 }
-// Enter the inner BVH2 node tv.lf (tv.cnt == 0). Returns false when the traversal is finished.
-WPT_DEV bool trav_inner2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+// Enter the inner node tv.lf. Returns true if the lane has to pop next (BVH2: both children
+// missed; BVH4: always — the surviving children were pushed in reverse sorted order).
+template <int BVH>
+WPT_DEV bool trav_inner(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+  if (BVH == 4) {
+    tv.visits += 1;
+    const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + (int)tv.lf);
+    float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
+    int4 ch = __ldg(reinterpret_cast<const int4*>(p + 6));
+    uint32_t nc = __ldg(reinterpret_cast<const uint32_t*>(p + 7));
+    int id[4] = {0, 0, 0, 0}; float d[4] = {WPT_INF, WPT_INF, WPT_INF, WPT_INF};
+    if (nc > 0) { id[0] = ch.x; d[0] = box_hit_x4(x0.x, y0.x, z0.x, x1.x, y1.x, z1.x, ray); }
+    if (nc > 1) { id[1] = ch.y; d[1] = box_hit_x4(x0.y, y0.y, z0.y, x1.y, y1.y, z1.y, ray); }
+    if (nc > 2) { id[2] = ch.z; d[2] = box_hit_x4(x0.z, y0.z, z0.z, x1.z, y1.z, z1.z, ray); }
+    if (nc > 3) { id[3] = ch.w; d[3] = box_hit_x4(x0.w, y0.w, z0.w, x1.w, y1.w, z1.w, ray); }
+    sort_small(id, d, nc);
+#pragma unroll
+    for (int i = 3; i >= 0; i--)
+      if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) { stack_n[tv.sp] = (uint32_t)id[i]; stack_d[tv.sp] = d[i]; tv.sp++; }
+    return true;
+  }
+  // BVH2, scene.rs:241-287 written with selects instead of four branches:
+  //   left misses          -> traverse_bvh_guarded(right): the guard is counted (scene.rs:283-286)
+  //   only left hits       -> left
+  //   both hit             -> near first (tie -> right first, scene.rs:244,261), far pushed with its distance
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
-  tv.visits += 1;
   const float4* c = nodes + (size_t)tv.lf * 2;
   float4 la = __ldg(c), lb = __ldg(c + 1), qa = __ldg(c + 2), qb = __ldg(c + 3);
   float dl, dr;
-  bool hl = box_hit(la.x, la.y, la.z, la.w, lb.x, lb.y, ray, &dl) && dl < tv.bound;
-  bool hr = box_hit(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < tv.bound;
-  if (!hl) {
-    // left misses: traverse_bvh_guarded(right) — counts the guard (scene.rs:283-286)
-    tv.visits += 1;
-    if (hr) { tv.lf = __float_as_uint(qb.z); tv.cnt = __float_as_uint(qb.w); return true; }
-    return trav_pop2(sc, tv, stack_n, stack_d);
-  }
-  if (!hr) { tv.lf = __float_as_uint(lb.z); tv.cnt = __float_as_uint(lb.w); return true; }
-  if (dl < dr) {   // left first; tie -> right first (scene.rs:244,261)
-    stack_n[tv.sp] = tv.lf + 1; stack_d[tv.sp] = dr; tv.sp++;
-    tv.lf = __float_as_uint(lb.z); tv.cnt = __float_as_uint(lb.w);
-  } else {
-    stack_n[tv.sp] = tv.lf; stack_d[tv.sp] = dl; tv.sp++;
-    tv.lf = __float_as_uint(qb.z); tv.cnt = __float_as_uint(qb.w);
-  }
-  return true;
+  bool hl = box_hit_sel(la.x, la.y, la.z, la.w, lb.x, lb.y, ray, &dl) && dl < tv.bound;
+  bool hr = box_hit_sel(qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, ray, &dr) && dr < tv.bound;
+  tv.visits += hl ? 1u : 2u;
+  const bool lfirst = dl < dr;
+  const bool go_left = hl && (!hr || lfirst);
+  if (hl && hr) { stack_n[tv.sp] = lfirst ? tv.lf + 1 : tv.lf; stack_d[tv.sp] = lfirst ? dr : dl; tv.sp++; }
+  tv.lf = __float_as_uint(go_left ? lb.z : qb.z); tv.cnt = __float_as_uint(go_left ? lb.w : qb.w);
+  return !(hl || hr);
 }
-// Enter the BVH2 leaf (tv.lf, tv.cnt != 0).
-template <bool SIMPLE>
-WPT_DEV bool trav_leaf2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
+// Scan the leaf the lane waits at (the lane pops afterwards).
+template <int BVH, bool SIMPLE>
+WPT_DEV void trav_leaf(const DScene& sc, const Ray& ray, Trav& tv) {
   tv.visits += 1;
-  leaf_scan<SIMPLE>(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
-  return trav_pop2(sc, tv, stack_n, stack_d);
-}
-template <bool SIMPLE>
-WPT_DEV bool trav_step2(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
-  return tv.cnt != 0 ? trav_leaf2<SIMPLE>(sc, ray, tv, stack_n, stack_d) : trav_inner2(sc, ray, tv, stack_n, stack_d);
-}
-
-WPT_DEV bool trav_pop4(Trav& tv, const uint32_t* stack_n, const float* stack_d) {
-  while (tv.sp > 0) {
-    tv.sp--;
-    if (stack_d[tv.sp] > tv.bound) continue;
-    tv.lf = stack_n[tv.sp];
-    return true;
-  }
-  return false;
-}
-// Enter the inner BVH4 node tv.lf (>= 0 as int).
-WPT_DEV bool trav_inner4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
-  tv.visits += 1;
-  const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + (int)tv.lf);
-  float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
-  int4 ch = __ldg(reinterpret_cast<const int4*>(p + 6));
-  uint32_t nc = __ldg(reinterpret_cast<const uint32_t*>(p + 7));
-  int id[4] = {0, 0, 0, 0}; float d[4] = {WPT_INF, WPT_INF, WPT_INF, WPT_INF};
-  if (nc > 0) { id[0] = ch.x; d[0] = box_hit_x4(x0.x, y0.x, z0.x, x1.x, y1.x, z1.x, ray); }
-  if (nc > 1) { id[1] = ch.y; d[1] = box_hit_x4(x0.y, y0.y, z0.y, x1.y, y1.y, z1.y, ray); }
-  if (nc > 2) { id[2] = ch.z; d[2] = box_hit_x4(x0.z, y0.z, z0.z, x1.z, y1.z, z1.z, ray); }
-  if (nc > 3) { id[3] = ch.w; d[3] = box_hit_x4(x0.w, y0.w, z0.w, x1.w, y1.w, z1.w, ray); }
-  sort_small(id, d, nc);
-#pragma unroll
-  for (int i = 3; i >= 0; i--)
-    if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) { stack_n[tv.sp] = (uint32_t)id[i]; stack_d[tv.sp] = d[i]; tv.sp++; }
-  return trav_pop4(tv, stack_n, stack_d);
-}
-template <bool SIMPLE>
-WPT_DEV bool trav_leaf4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
-  tv.visits += 1;
-  uint32_t code = tv.lf;
-  leaf_scan<SIMPLE>(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims);
-  return trav_pop4(tv, stack_n, stack_d);
-}
-template <bool SIMPLE>
-WPT_DEV bool trav_step4(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
-  return (int)tv.lf < 0 ? trav_leaf4<SIMPLE>(sc, ray, tv, stack_n, stack_d) : trav_inner4(sc, ray, tv, stack_n, stack_d);
+  if (BVH == 4) { uint32_t code = tv.lf; leaf_scan<SIMPLE>(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims); }
+  else leaf_scan<SIMPLE>(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
 }
 // true if the node the lane is about to enter is a leaf
 template <int BVH>
@@ -581,8 +575,12 @@ WPT_DEV GHit trace_g_t(const DScene& sc, const Ray& ray) {
   Trav tv;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
   if (trav_begin<BVH, SIMPLE>(sc, ray, tv)) {
-    if (BVH == 4) { while (trav_step4<SIMPLE>(sc, ray, tv, stack_n, stack_d)) {} }
-    else { while (trav_step2<SIMPLE>(sc, ray, tv, stack_n, stack_d)) {} }
+    for (;;) {
+      bool need_pop = true;
+      if (trav_at_leaf<BVH>(tv)) trav_leaf<BVH, SIMPLE>(sc, ray, tv);
+      else need_pop = trav_inner<BVH>(sc, ray, tv, stack_n, stack_d);
+      if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) break;
+    }
   }
   return trav_result(tv);
 }

@@ -529,24 +529,20 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
       // burst waits at a leaf, then one leaf step with all of them (triangle tests are the
       // expensive body: run them with as many lanes as possible)
       do {
-        const int n_trav = __popc(trav);
-        for (;;) {
-          bool at_inner = phase == PH_TRAV && !trav_at_leaf<BVH>(tv);
-          int n_inner = __popc(__ballot_sync(FULL, at_inner));
-          if (n_inner == 0) break;
+        // one step per iteration: an inner-node step while enough of the burst's lanes are at
+        // inner nodes, else a leaf step with every lane that waits at a leaf (triangle tests are
+        // the expensive body: run them with as many lanes as possible); then one shared pop
+        const bool tr = phase == PH_TRAV;
+        const bool leaf = tr && trav_at_leaf<BVH>(tv);
+        const int n_inner = __popc(__ballot_sync(FULL, tr && !leaf));
+        bool need_pop = false;
+        if (n_inner == __popc(trav) || n_inner * (int)P.t_inner > __popc(trav)) {
 #ifdef MEGA_INSTR
           i_ts += 1; i_tl += n_inner;
 #endif
-          if (at_inner) {
-            bool cont = BVH == 4 ? trav_inner4(sc, ray, tv, stack_n, stack_d) : trav_inner2(sc, ray, tv, stack_n, stack_d);
-            if (!cont) phase = PH_LOGIC;
-          }
-          if (n_inner * P.t_inner <= n_trav) break;   // few lanes left at inner nodes: let them wait
-        }
-        if (phase == PH_TRAV && trav_at_leaf<BVH>(tv)) {
-          bool cont = BVH == 4 ? trav_leaf4<SIMPLE>(sc, ray, tv, stack_n, stack_d) : trav_leaf2<SIMPLE>(sc, ray, tv, stack_n, stack_d);
-          if (!cont) phase = PH_LOGIC;
-        }
+          if (tr && !leaf) need_pop = trav_inner<BVH>(sc, ray, tv, stack_n, stack_d);
+        } else if (leaf) { trav_leaf<BVH, SIMPLE>(sc, ray, tv); need_pop = true; }
+        if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
         trav = __ballot_sync(FULL, phase == PH_TRAV);
       } while (__popc(trav) >= (int)P.t_lo);
       continue;
@@ -554,46 +550,53 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 #ifdef MEGA_INSTR
     i_lp += 1; i_ll += __popc(logic); i_sh += __popc(__ballot_sync(FULL, phase == PH_LOGIC && what == ST_EXTEND));
 #endif
-    if (phase != PH_LOGIC) continue;
-    // ---- logic pass
-    bool start = false;
-    if (what != ST_GEN) {
-      GHit g = trav_result(tv);
-      c_rays += 1; c_visits += g.visits; c_prims += g.prims;
-      bool finish = false;
-      if (what == ST_SHADOW) {   // Scene::shadow_ray, scene.rs:114-132
-        bool occluded = g.id >= 0 && g.t < sh_len && g.id != sh_light;
-        if (!occluded) ps.color = ps.color + contrib;
-        if (alive_after_shadow) { ray = make_ray(ext_o, ext_d); what = ST_EXTEND; start = true; }
-        else finish = true;
-      } else {
-        ShadeOut so;
-        shade_hit<SIMPLE>(P.rp, ray, g.id, g.t, ps, so);
-        if (so.finished) finish = true;
-        else if (so.shadow) {
-          ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
-          alive_after_shadow = so.survive;
-          ray = make_ray(so.sh_o, so.sh_d); what = ST_SHADOW; start = true;
-        } else if (so.survive) { ray = make_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
-        else finish = true;
+    // ---- logic pass, two halves. Half 0: lanes holding a shadow-ray result resolve it and start
+    // their bounce ray; half 1: every lane holding a bounce/camera-ray result — including those
+    // whose ray of half 0 ended at the root guard — is shaded. Both halves regenerate finished
+    // lanes. So all lanes of the warp meet in the (expensive) shading code once per pass instead
+    // of alternating shade / shadow-resolve in two populations that never line up.
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      if (phase != PH_LOGIC) continue;
+      bool start = false;
+      if (what == (half == 0 ? ST_SHADOW : ST_EXTEND)) {
+        GHit g = trav_result(tv);
+        c_rays += 1; c_visits += g.visits; c_prims += g.prims;
+        bool finish = false;
+        if (half == 0) {   // Scene::shadow_ray, scene.rs:114-132
+          bool occluded = g.id >= 0 && g.t < sh_len && g.id != sh_light;
+          if (!occluded) ps.color = ps.color + contrib;
+          if (alive_after_shadow) { ray = make_ray(ext_o, ext_d); what = ST_EXTEND; start = true; }
+          else finish = true;
+        } else {
+          ShadeOut so;
+          shade_hit<SIMPLE>(P.rp, ray, g.id, g.t, ps, so);
+          if (so.finished) finish = true;
+          else if (so.shadow) {
+            ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
+            alive_after_shadow = so.survive;
+            ray = make_ray(so.sh_o, so.sh_d); what = ST_SHADOW; start = true;
+          } else if (so.survive) { ray = make_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
+          else finish = true;
+        }
+        if (finish) { acc_rgb = acc_rgb + ps.color; c_paths += 1; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
       }
-      if (finish) { acc_rgb = acc_rgb + ps.color; c_paths += 1; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
-    }
-    if (what == ST_GEN) {
-      if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream
-        ps.rng.s = stream_seed(pix, s, STREAM_PATH, P.rp.base_seed);
-        float j1 = ps.rng.f32();
-        float j2 = ps.rng.f32();
-        uint32_t py = pix / P.rp.W, px = pix - py * P.rp.W;
-        ray = camera_ray(P.rp.cam, px, py, j1, j2);
-        ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
-        what = ST_EXTEND; start = true;
-      } else {
-        P.accum[pix] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, __uint_as_float(s));
-        phase = PH_NEED;
+      if (what == ST_GEN) {
+        if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream
+          ps.rng.s = stream_seed(pix, s, STREAM_PATH, P.rp.base_seed);
+          float j1 = ps.rng.f32();
+          float j2 = ps.rng.f32();
+          uint32_t py = pix / P.rp.W, px = pix - py * P.rp.W;
+          ray = camera_ray(P.rp.cam, px, py, j1, j2);
+          ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
+          what = ST_EXTEND; start = true;
+        } else {
+          P.accum[pix] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, __uint_as_float(s));
+          phase = PH_NEED;
+        }
       }
+      if (start && trav_begin<BVH, SIMPLE>(sc, ray, tv)) phase = PH_TRAV;
     }
-    if (start && trav_begin<BVH, SIMPLE>(sc, ray, tv)) phase = PH_TRAV;
   }
   // ---- counters
   unsigned long long r = warp_sum_u64(c_rays), v = warp_sum_u64(c_visits), pr = warp_sum_u64(c_prims), pa = warp_sum_u64(c_paths);
@@ -620,6 +623,426 @@ void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
     else if (blocks_per_sm == 8) k_mega<2, true, 8><<<grid, MEGA_THREADS, 0, s>>>(P);
     else k_mega<2, true, 4><<<grid, MEGA_THREADS, 0, s>>>(P);
   } else { if (b4) k_mega<4, false, 4><<<grid, MEGA_THREADS, 0, s>>>(P); else k_mega<2, false, 4><<<grid, MEGA_THREADS, 0, s>>>(P); }
+}
+
+// ------------------------------------------------------------------ block-pool path kernel
+// k_pool: k_mega's two stages decoupled from the lanes. A block owns S path slots whose state is
+// parked in shared memory (SoA, 33 words per slot); a slot is always in exactly one place: the
+// logic queue qL, the traversal queue qT, the registers of a lane in logic mode, or (its ray only)
+// the registers of a lane in traversal mode. Warps are symmetric and change mode only when they
+// hold nothing:
+//   logic mode     — empty lanes pop slots from qL; the two-half logic pass of k_mega runs on
+//                    all 32 lanes; lanes whose new ray has to enter the BVH park their state and
+//                    push the slot to qT (their ray ended at the root guard otherwise — 85 % of
+//                    the bunny scene's rays — and they just carry on).
+//   traversal mode — Aila & Laine's persistent while-while loop with refill: when few lanes are
+//                    still traversing, the idle ones pop new rays from qT; a finished lane writes
+//                    (t, id) into its slot and pushes it to qL.
+// So the shading code and the traversal loop each run with (almost) full warps instead of the
+// ~11 of 32 lanes k_mega reaches with one path pinned per lane. Pixels are handed out from a
+// block-level chunk of the global slot queue (slots are in 8x4 tile order). A pixel's samples are
+// still run one after the other by its slot, so the accumulation order — and every bit of the
+// result — is unchanged.
+#define POOL_THREADS 256
+#define POOL_NF 33
+#define POOL_EMPTY 0xFFFFFFFFu
+enum : int { PQ_HEAD = 0, PQ_TAIL = 1, PQ_COUNT = 2 };
+enum : int { PC_L = 0, PC_T = 4, PC_RETIRED = 8, PC_LOCK = 9, PC_EXH = 10, PC_CHUNK = 12 /* 64-bit, 8-byte aligned */, PC_WORDS = 16 };
+// state words
+enum : int { PF_O = 0, PF_D = 3, PF_T = 6, PF_COL = 9, PF_RNG = 12, PF_PIX = 13, PF_S = 14, PF_SEND = 15, PF_ACC = 16, PF_FLAGS = 19,
+             PF_RT = 20, PF_RID = 21, PF_EXO = 22, PF_EXD = 25, PF_CON = 28, PF_SHLEN = 31, PF_SHLIGHT = 32 };
+
+// one lane reads the control word, every lane gets the same value (keeps the branches around the ballots uniform)
+WPT_DEV uint32_t pool_peek(volatile uint32_t* p, unsigned lane) {
+  uint32_t v = 0;
+  if (lane == 0) v = *p;
+  return __shfl_sync(0xFFFFFFFFu, v, 0);
+}
+// pop up to `want` entries for the lanes with `wants` (rank = index among them). Returns the number taken.
+WPT_DEV uint32_t pool_pop(volatile uint32_t* q, volatile uint32_t* ring, uint32_t mask, uint32_t want, unsigned lane, bool wants, uint32_t rank, uint32_t* item) {
+  uint32_t take = 0, pos = 0;
+  if (lane == 0) {
+    uint32_t c = q[PQ_COUNT];
+    while (c != 0) {
+      uint32_t t = min(c, want);
+      uint32_t old = atomicCAS(const_cast<uint32_t*>(q + PQ_COUNT), c, c - t);
+      if (old == c) { take = t; break; }
+      c = old;
+    }
+    if (take) pos = atomicAdd(const_cast<uint32_t*>(q + PQ_HEAD), take);
+  }
+  take = __shfl_sync(0xFFFFFFFFu, take, 0);
+  pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+  if (wants && rank < take) {
+    uint32_t idx = (pos + rank) & mask, v;
+    while ((v = ring[idx]) == POOL_EMPTY) {}   // the producer reserved this entry and is about to write it
+    ring[idx] = POOL_EMPTY;
+    *item = v;
+  }
+  __threadfence_block();
+  return take;
+}
+// push `item` of every lane with `has`
+WPT_DEV void pool_push(volatile uint32_t* q, volatile uint32_t* ring, uint32_t mask, unsigned lane, bool has, uint32_t item) {
+  unsigned m = __ballot_sync(0xFFFFFFFFu, has);
+  if (!m) return;
+  uint32_t n = (uint32_t)__popc(m), pos = 0;
+  if (lane == 0) pos = atomicAdd(const_cast<uint32_t*>(q + PQ_TAIL), n);
+  pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+  __threadfence_block();   // the slot's state is written before the entry becomes visible
+  if (has) ring[(pos + (uint32_t)__popc(m & ((1u << lane) - 1u))) & mask] = item;
+  __syncwarp();
+  if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<uint32_t*>(q + PQ_COUNT), n); }
+}
+// lane 0 only: take up to n consecutive global slots from the block's chunk (refilled from the global queue)
+__device__ __noinline__ void pool_pixels(volatile uint32_t* ctrl, uint32_t* work_counter, uint32_t chunk, uint32_t nslots, uint32_t n, uint32_t* base, uint32_t* k) {
+  volatile unsigned long long* pc = reinterpret_cast<volatile unsigned long long*>(ctrl + PC_CHUNK);
+  *k = 0; *base = 0;
+  for (;;) {
+    unsigned long long cur = *pc;
+    uint32_t nx = (uint32_t)cur, en = (uint32_t)(cur >> 32);
+    if (nx < en) {
+      uint32_t t = min(n, en - nx);
+      if (atomicCAS(const_cast<unsigned long long*>(pc), cur, ((unsigned long long)en << 32) | (nx + t)) == cur) { *base = nx; *k = t; return; }
+      continue;
+    }
+    if (ctrl[PC_EXH]) return;
+    if (atomicCAS(const_cast<uint32_t*>(ctrl + PC_LOCK), 0u, 1u) == 0u) {
+      cur = *pc; nx = (uint32_t)cur; en = (uint32_t)(cur >> 32);
+      if (nx >= en && !ctrl[PC_EXH]) {
+        uint32_t b = atomicAdd(work_counter, chunk);
+        if (b >= nslots) ctrl[PC_EXH] = 1u;
+        else *pc = ((unsigned long long)min(b + chunk, nslots) << 32) | b;
+      }
+      __threadfence_block();
+      atomicExch(const_cast<uint32_t*>(ctrl + PC_LOCK), 0u);
+    } else __nanosleep(40);
+  }
+}
+
+// park a path: write its state into its slot. The shadow-ray fields are only live while a
+// shadow ray is pending.
+template <bool FLUSH>
+WPT_DEV void pool_store(uint32_t* stw, float* stf, uint32_t S, uint32_t home, F3 ro, F3 rd, const PathRegs& ps, uint32_t pix, uint32_t s, uint32_t s_end, F3 acc_rgb,
+                        int what, bool alive_after_shadow, bool haspix, float res_t, int res_id, F3 ext_o, F3 ext_d, F3 contrib, float sh_len, int sh_light) {
+  uint32_t* w = stw + home; float* f = stf + home;
+  f[(PF_O + 0) * S] = ro.x; f[(PF_O + 1) * S] = ro.y; f[(PF_O + 2) * S] = ro.z;
+  f[(PF_D + 0) * S] = rd.x; f[(PF_D + 1) * S] = rd.y; f[(PF_D + 2) * S] = rd.z;
+  f[(PF_T + 0) * S] = ps.T.x; f[(PF_T + 1) * S] = ps.T.y; f[(PF_T + 2) * S] = ps.T.z;
+  f[(PF_COL + 0) * S] = ps.color.x; f[(PF_COL + 1) * S] = ps.color.y; f[(PF_COL + 2) * S] = ps.color.z;
+  w[PF_RNG * S] = ps.rng.s; w[PF_PIX * S] = pix; w[PF_S * S] = s; w[PF_SEND * S] = s_end;
+  f[(PF_ACC + 0) * S] = acc_rgb.x; f[(PF_ACC + 1) * S] = acc_rgb.y; f[(PF_ACC + 2) * S] = acc_rgb.z;
+  w[PF_FLAGS * S] = (uint32_t)what | (ps.bounced ? 4u : 0u) | (alive_after_shadow ? 8u : 0u) | (haspix ? 16u : 0u);
+  f[PF_RT * S] = res_t; w[PF_RID * S] = (uint32_t)res_id;
+  if (what == ST_SHADOW) {
+    f[(PF_EXO + 0) * S] = ext_o.x; f[(PF_EXO + 1) * S] = ext_o.y; f[(PF_EXO + 2) * S] = ext_o.z;
+    f[(PF_EXD + 0) * S] = ext_d.x; f[(PF_EXD + 1) * S] = ext_d.y; f[(PF_EXD + 2) * S] = ext_d.z;
+    f[(PF_CON + 0) * S] = contrib.x; f[(PF_CON + 1) * S] = contrib.y; f[(PF_CON + 2) * S] = contrib.z;
+    f[PF_SHLEN * S] = sh_len; w[PF_SHLIGHT * S] = (uint32_t)sh_light;
+  }
+}
+
+template <int BVH, bool SIMPLE, int MINB>
+__global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint32_t S, uint32_t cap) {
+  extern __shared__ __align__(16) uint32_t pool_smem[];
+  volatile uint32_t* ctrl = pool_smem;
+  volatile uint32_t* ringL = pool_smem + PC_WORDS;
+  volatile uint32_t* ringT = ringL + cap;
+  uint32_t* stw = pool_smem + PC_WORDS + 2 * cap;          // state word f of slot i: stw[f * S + i]
+  float* stf = reinterpret_cast<float*>(stw);
+  const uint32_t mask = cap - 1u;
+  const DScene& sc = P.rp.scene;
+  const unsigned FULL = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
+  uint32_t c_rays = 0, c_visits = 0, c_prims = 0, c_paths = 0;
+#ifdef POOL_INSTR
+  unsigned long long i_lp = 0, i_lh = 0, i_ls = 0, i_tp = 0, i_ta = 0, i_idle = 0, i_flush = 0, i_ts = 0, i_tl = 0, i_sw = 0;
+#endif
+
+  // ---- block setup: every slot starts in qL without a pixel
+  for (uint32_t i = threadIdx.x; i < PC_WORDS; i += POOL_THREADS) pool_smem[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < cap; i += POOL_THREADS) { ringL[i] = i < S ? i : POOL_EMPTY; ringT[i] = POOL_EMPTY; }
+  for (uint32_t i = threadIdx.x; i < S * POOL_NF; i += POOL_THREADS) stw[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) { ctrl[PC_L + PQ_TAIL] = S; ctrl[PC_L + PQ_COUNT] = S; }
+  __syncthreads();
+
+  bool in_logic = true;
+  for (;;) {
+    if (in_logic) {
+      // =============================================================== logic mode
+      bool have = false, pend = false, haspix = false, alive_after_shadow = false;
+      int what = ST_GEN;
+      uint32_t home = 0, pix = 0, s = 0, s_end = 0;
+      PathRegs ps; ps.color = f3(0, 0, 0); ps.T = f3(1, 1, 1); ps.rng.s = 1u; ps.bounced = false;
+      F3 ro = f3(0, 0, 0), rd = f3(1, 1, 1), acc_rgb = f3(0, 0, 0);
+      F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
+      float sh_len = 0.0f, res_t = 0.0f; int sh_light = -1, res_id = -1;
+      bool leave = false, finished = false;
+      while (!leave) {
+        // ---- refill policy. A warp that holds few paths and cannot top up from qL does not keep
+        // running thin passes: it hands its paths back to qL (another logic warp consolidates
+        // them) and goes traversing. An empty warp goes where the work is.
+        unsigned hv = __ballot_sync(FULL, have);
+        uint32_t n_have = (uint32_t)__popc(hv);
+        if (n_have < 32u) {
+          uint32_t availL = pool_peek(ctrl + PC_L + PQ_COUNT, lane);
+          bool refill = availL != 0u;
+          if (n_have + availL < P.t_hi) {   // would stay under-filled
+            uint32_t availT = pool_peek(ctrl + PC_T + PQ_COUNT, lane);
+            if (availT >= P.t_switch || (n_have == 0u && availL == 0u && availT != 0u)) {
+              if (n_have) {   // flush: these paths are logic-ready (their result is in res_t / res_id)
+                if (have) pool_store<true>(stw, stf, S, home, ro, rd, ps, pix, s, s_end, acc_rgb, what, alive_after_shadow, haspix, res_t, res_id, ext_o, ext_d, contrib, sh_len, sh_light);
+                pool_push(ctrl + PC_L, ringL, mask, lane, have, home);
+                have = false;
+              }
+              in_logic = false; leave = true;
+#ifdef POOL_INSTR
+              i_flush += n_have; i_sw += 1;
+#endif
+              continue;
+            }
+          }
+          if (refill) {
+            unsigned em = ~hv;
+            uint32_t item = 0, rank = (uint32_t)__popc(em & lt);
+            uint32_t got = pool_pop(ctrl + PC_L, ringL, mask, 32u - n_have, lane, !have, rank, &item);
+            if (!have && rank < got) {
+              home = item; have = true; pend = false;
+              const uint32_t* w = stw + home; const float* f = stf + home;
+              ro = f3(f[(PF_O + 0) * S], f[(PF_O + 1) * S], f[(PF_O + 2) * S]);
+              rd = f3(f[(PF_D + 0) * S], f[(PF_D + 1) * S], f[(PF_D + 2) * S]);
+              ps.T = f3(f[(PF_T + 0) * S], f[(PF_T + 1) * S], f[(PF_T + 2) * S]);
+              ps.color = f3(f[(PF_COL + 0) * S], f[(PF_COL + 1) * S], f[(PF_COL + 2) * S]);
+              ps.rng.s = w[PF_RNG * S]; pix = w[PF_PIX * S]; s = w[PF_S * S]; s_end = w[PF_SEND * S];
+              acc_rgb = f3(f[(PF_ACC + 0) * S], f[(PF_ACC + 1) * S], f[(PF_ACC + 2) * S]);
+              uint32_t fl = w[PF_FLAGS * S];
+              what = (int)(fl & 3u); ps.bounced = (fl & 4u) != 0; alive_after_shadow = (fl & 8u) != 0; haspix = (fl & 16u) != 0;
+              res_t = f[PF_RT * S]; res_id = (int)w[PF_RID * S];
+              if (what == ST_SHADOW) {
+                ext_o = f3(f[(PF_EXO + 0) * S], f[(PF_EXO + 1) * S], f[(PF_EXO + 2) * S]);
+                ext_d = f3(f[(PF_EXD + 0) * S], f[(PF_EXD + 1) * S], f[(PF_EXD + 2) * S]);
+                contrib = f3(f[(PF_CON + 0) * S], f[(PF_CON + 1) * S], f[(PF_CON + 2) * S]);
+                sh_len = f[PF_SHLEN * S]; sh_light = (int)w[PF_SHLIGHT * S];
+              }
+            }
+            hv = __ballot_sync(FULL, have);
+          }
+        }
+        if (!hv) {   // this warp holds nothing and found nothing
+          if (pool_peek(ctrl + PC_T + PQ_COUNT, lane) != 0u) { in_logic = false; leave = true; }
+          else if (pool_peek(ctrl + PC_RETIRED, lane) >= S) { finished = true; leave = true; }
+          else {
+            __nanosleep(200);
+#ifdef POOL_INSTR
+            i_idle += 1;
+#endif
+          }
+          continue;
+        }
+#ifdef POOL_INSTR
+        i_lp += 1; i_lh += __popc(hv);
+#endif
+        // ---- pixels for the lanes whose slot has none
+        bool needpix = have && what == ST_GEN && !haspix;
+        unsigned nm = __ballot_sync(FULL, needpix);
+        if (nm) {
+          uint32_t base = 0, k = 0;
+          if (lane == 0) pool_pixels(ctrl, P.work_counter, P.chunk, P.nslots, (uint32_t)__popc(nm), &base, &k);
+          base = __shfl_sync(FULL, base, 0); k = __shfl_sync(FULL, k, 0);
+          bool retire = false;
+          if (needpix) {
+            uint32_t rank = (uint32_t)__popc(nm & lt);
+            if (rank < k) {
+              uint32_t idx = base + rank;
+              pix = P.pixel[idx];
+              uint32_t spp = P.spp_per_slot ? P.spp_per_slot[idx] : P.uniform_spp;
+              float4 a0 = P.accum[pix];
+              acc_rgb = xyz(a0);
+              s = __float_as_uint(a0.w);   // samples accumulated so far = next sample index
+              s_end = s + spp;
+              haspix = true;
+            } else if (k == 0) { retire = true; have = false; }   // the global queue is exhausted: the slot retires
+          }
+          unsigned rm = __ballot_sync(FULL, retire);
+          if (rm && lane == 0) atomicAdd(const_cast<uint32_t*>(ctrl + PC_RETIRED), (uint32_t)__popc(rm));
+        }
+        // ---- logic pass, two halves (see k_mega)
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+#ifdef POOL_INSTR
+          if (half == 1) i_ls += __popc(__ballot_sync(FULL, have && !pend && haspix && what == ST_EXTEND));
+#endif
+          if (!have || pend || !haspix) continue;
+          bool start = false;
+          if (what == (half == 0 ? ST_SHADOW : ST_EXTEND)) {
+            bool finish = false;
+            if (half == 0) {   // Scene::shadow_ray, scene.rs:114-132
+              bool occluded = res_id >= 0 && res_t < sh_len && res_id != sh_light;
+              if (!occluded) ps.color = ps.color + contrib;
+              if (alive_after_shadow) { ro = ext_o; rd = ext_d; what = ST_EXTEND; start = true; }
+              else finish = true;
+            } else {
+              ShadeOut so;
+              Ray ray; ray.o = ro; ray.d = rd; ray.inv = f3(0, 0, 0);   // triangles / planes: shading reads origin and direction only
+              if (!SIMPLE) ray = make_ray(ro, rd);
+              shade_hit<SIMPLE>(P.rp, ray, res_id, res_t, ps, so);
+              if (so.finished) finish = true;
+              else if (so.shadow) {
+                ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
+                alive_after_shadow = so.survive;
+                ro = so.sh_o; rd = so.sh_d; what = ST_SHADOW; start = true;
+              } else if (so.survive) { ro = so.next_o; rd = so.next_d; what = ST_EXTEND; start = true; }
+              else finish = true;
+            }
+            if (finish) { acc_rgb = acc_rgb + ps.color; c_paths += 1; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
+          }
+          if (what == ST_GEN) {
+            if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream
+              ps.rng.s = stream_seed(pix, s, STREAM_PATH, P.rp.base_seed);
+              float j1 = ps.rng.f32();
+              float j2 = ps.rng.f32();
+              uint32_t py = pix / P.rp.W, px = pix - py * P.rp.W;
+              Ray cr = camera_ray(P.rp.cam, px, py, j1, j2);
+              ro = cr.o; rd = cr.d;
+              ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
+              what = ST_EXTEND; start = true;
+            } else {
+              P.accum[pix] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, __uint_as_float(s));
+              haspix = false;
+            }
+          }
+          if (start) {
+            Ray ray = make_ray(ro, rd);
+            Trav tv;
+            bool enter = trav_begin<BVH, SIMPLE>(sc, ray, tv);
+            res_t = tv.inf_t; res_id = tv.inf_id;   // the result if the BVH is not entered; the request otherwise
+            if (enter) pend = true;
+            else { c_rays += 1; c_visits += tv.visits; }
+          }
+        }
+        // ---- park the lanes whose ray has to traverse the BVH
+        bool park = have && pend;
+        if (__ballot_sync(FULL, park)) {
+          if (park) pool_store<false>(stw, stf, S, home, ro, rd, ps, pix, s, s_end, acc_rgb, what, alive_after_shadow, haspix, res_t, res_id, ext_o, ext_d, contrib, sh_len, sh_light);
+          pool_push(ctrl + PC_T, ringT, mask, lane, park, home);
+          if (park) { have = false; pend = false; }
+        }
+      }
+      if (finished) break;
+    } else {
+      // =============================================================== traversal mode
+      bool act = false; uint32_t home = 0;
+      Ray ray = make_ray(f3(0, 0, 0), f3(1, 1, 1));
+      Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0;
+      bool leave = false, finished = false;
+      while (!leave) {
+        unsigned am = __ballot_sync(FULL, act);
+        if ((uint32_t)__popc(am) <= P.t_lo && pool_peek(ctrl + PC_T + PQ_COUNT, lane) != 0u) {   // refill the idle lanes from qT
+          uint32_t item = 0, rank = (uint32_t)__popc(~am & lt);
+          uint32_t got = pool_pop(ctrl + PC_T, ringT, mask, 32u - (uint32_t)__popc(am), lane, !act, rank, &item);
+          if (!act && rank < got) {
+            home = item; act = true;
+            const float* f = stf + home;
+            F3 o = f3(f[(PF_O + 0) * S], f[(PF_O + 1) * S], f[(PF_O + 2) * S]);
+            F3 d = f3(f[(PF_D + 0) * S], f[(PF_D + 1) * S], f[(PF_D + 2) * S]);
+            ray = make_ray(o, d);
+            tv.inf_t = f[PF_RT * S]; tv.inf_id = (int)stw[PF_RID * S + home];
+            tv.bound = tv.inf_id >= 0 ? tv.inf_t : WPT_INF;   // as trav_begin left it
+            tv.best_id = -1; tv.sp = 0; tv.prims = 0;
+            if (BVH == 4) { tv.lf = 0u; tv.cnt = 0u; tv.visits = 0; }
+            else {
+              float4 rb = __ldg(reinterpret_cast<const float4*>(sc.nodes2) + 1);
+              tv.lf = __float_as_uint(rb.z); tv.cnt = __float_as_uint(rb.w); tv.visits = 1;   // the root guard was counted (scene.rs:207)
+            }
+          }
+          am = __ballot_sync(FULL, act);
+        }
+        if (!am) {
+          if (pool_peek(ctrl + PC_L + PQ_COUNT, lane) != 0u) { in_logic = true; leave = true; }
+          else if (pool_peek(ctrl + PC_RETIRED, lane) >= S) { finished = true; leave = true; }
+          else __nanosleep(200);
+          continue;
+        }
+#ifdef POOL_INSTR
+        i_tp += 1; i_ta += __popc(am);
+#endif
+        // ---- while-while burst: inner steps until (almost) every traversing lane waits at a leaf,
+        // then one leaf step; lanes that finish drop out. Leave when a refill is worthwhile.
+        bool fin = false;
+        unsigned trav = am;
+        do {
+          const bool tr = act && !fin;
+          const bool leaf = tr && trav_at_leaf<BVH>(tv);
+          const int n_inner = __popc(__ballot_sync(FULL, tr && !leaf));
+          bool need_pop = false;
+          if (n_inner == __popc(trav) || n_inner * (int)P.t_inner > __popc(trav)) {
+#ifdef POOL_INSTR
+            i_ts += 1; i_tl += n_inner;
+#endif
+            if (tr && !leaf) need_pop = trav_inner<BVH>(sc, ray, tv, stack_n, stack_d);
+          } else if (leaf) { trav_leaf<BVH, SIMPLE>(sc, ray, tv); need_pop = true; }
+          if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) fin = true;
+          trav = __ballot_sync(FULL, act && !fin);
+        } while ((uint32_t)__popc(trav) > P.t_lo);
+        // ---- finished lanes hand their slot back to the logic queue
+        if (fin) {
+          GHit g = trav_result(tv);
+          stf[PF_RT * S + home] = g.t; stw[PF_RID * S + home] = (uint32_t)g.id;
+          c_rays += 1; c_visits += g.visits; c_prims += g.prims;
+        }
+        pool_push(ctrl + PC_L, ringL, mask, lane, fin, home);
+        if (fin) act = false;
+      }
+      if (finished) break;
+    }
+  }
+  // ---- counters
+  unsigned long long r = warp_sum_u64(c_rays), v = warp_sum_u64(c_visits), pr = warp_sum_u64(c_prims), pa = warp_sum_u64(c_paths);
+  if (lane == 0 && (r | pa)) {
+    atomicAdd(&P.counters[0], r); atomicAdd(&P.counters[1], v); atomicAdd(&P.counters[2], pa); atomicAdd(&P.counters[3], pr);
+  }
+#ifdef POOL_INSTR
+  if (lane == 0) {
+    atomicAdd(&P.counters[4], i_lp); atomicAdd(&P.counters[5], i_lh); atomicAdd(&P.counters[6], i_ls); atomicAdd(&P.counters[7], i_tp);
+    atomicAdd(&P.counters[8], i_ta); atomicAdd(&P.counters[9], i_idle); atomicAdd(&P.counters[10], i_flush); atomicAdd(&P.counters[11], i_ts);
+    atomicAdd(&P.counters[12], i_tl); atomicAdd(&P.counters[13], i_sw);
+  }
+#endif
+}
+
+size_t pool_smem_bytes(uint32_t S, uint32_t cap) { return (size_t)(PC_WORDS + 2 * cap + S * POOL_NF) * sizeof(uint32_t); }
+
+template <int BVH, bool SIMPLE, int MINB>
+static void launch_pool_t(const MegaParams& P, uint32_t S, uint32_t cap, int grid, cudaStream_t s) {
+  size_t bytes = pool_smem_bytes(S, cap);
+  static size_t configured = 0;
+  if (configured != bytes) {
+    cudaFuncSetAttribute(k_pool<BVH, SIMPLE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaFuncSetAttribute(k_pool<BVH, SIMPLE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = bytes;
+  }
+  k_pool<BVH, SIMPLE, MINB><<<grid, POOL_THREADS, bytes, s>>>(P, S, cap);
+}
+void launch_pool(const MegaParams& P, int blocks_per_sm, uint32_t slots_per_block, cudaStream_t s) {
+  if (!P.nslots) return;
+  uint32_t S = slots_per_block < POOL_THREADS ? POOL_THREADS : slots_per_block;
+  uint32_t cap = 1; while (cap < S) cap <<= 1;
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  if (blocks_per_sm > 4) blocks_per_sm = 4;
+  const bool b4 = P.rp.scene.bvh_kind == 4;
+  if (!(P.simple_scene && !b4) && blocks_per_sm > 2) blocks_per_sm = 2;   // the other variants need > 64 registers
+  int grid = device_sm_count() * blocks_per_sm;
+  int need = (int)((P.nslots + S - 1) / S);
+  if (grid > need) grid = need;
+  if (P.simple_scene) {
+    if (b4) launch_pool_t<4, true, 2>(P, S, cap, grid, s);
+    else if (blocks_per_sm == 4) launch_pool_t<2, true, 4>(P, S, cap, grid, s);
+    else if (blocks_per_sm == 3) launch_pool_t<2, true, 3>(P, S, cap, grid, s);
+    else launch_pool_t<2, true, 2>(P, S, cap, grid, s);
+  } else { if (b4) launch_pool_t<4, false, 2>(P, S, cap, grid, s); else launch_pool_t<2, false, 2>(P, S, cap, grid, s); }
 }
 
 // ------------------------------------------------------------------ resolve (render_target.rs:59-64)

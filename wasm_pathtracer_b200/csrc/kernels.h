@@ -54,12 +54,15 @@ struct MegaParams {
   uint32_t uniform_spp, nslots;
   uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
   uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
+  uint32_t t_switch;              // k_pool: an under-filled logic warp flushes and goes traversing when qT holds at least this many rays
   uint32_t chunk;                 // slots a warp fetches at a time (multiple of 32)
   uint32_t simple_scene;          // shapes are triangles and planes only: kernel variant without torus / box code
   uint32_t* work_counter;         // zeroed before the launch
   unsigned long long* counters;
 };
 void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s);
+// Block-pool path kernel (k_pool): path states parked in shared memory, warps alternate between logic and traversal mode.
+void launch_pool(const MegaParams& P, int blocks_per_sm, uint32_t slots_per_block, cudaStream_t s);
 
 void launch_setup_slots(const PathState& st, const uint32_t* spp_per_slot, uint32_t uniform_spp, const float4* accum, cudaStream_t s);
 void launch_trace(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);

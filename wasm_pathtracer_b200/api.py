@@ -29,7 +29,8 @@ class WptConfig(C.Structure):
 
 
 def library_path():
-    return os.path.join(PKG_DIR, "libwpt.so")
+    # WPT_LIBRARY: A/B builds of the same library during kernel tuning (scripts/); never a different backend
+    return os.environ.get("WPT_LIBRARY") or os.path.join(PKG_DIR, "libwpt.so")
 
 
 _lib = None

@@ -659,7 +659,7 @@ WPT_DEV uint32_t pool_peek(volatile uint32_t* p, unsigned lane) {
   return __shfl_sync(0xFFFFFFFFu, v, 0);
 }
 // pop up to `want` entries for the lanes with `wants` (rank = index among them). Returns the number taken.
-WPT_DEV uint32_t pool_pop(volatile uint32_t* q, volatile uint32_t* ring, uint32_t mask, uint32_t want, unsigned lane, bool wants, uint32_t rank, uint32_t* item) {
+__device__ __noinline__ uint32_t pool_pop(volatile uint32_t* q, volatile uint32_t* ring, uint32_t mask, uint32_t want, unsigned lane, bool wants, uint32_t rank, uint32_t* item) {
   uint32_t take = 0, pos = 0;
   if (lane == 0) {
     uint32_t c = q[PQ_COUNT];
@@ -683,7 +683,7 @@ WPT_DEV uint32_t pool_pop(volatile uint32_t* q, volatile uint32_t* ring, uint32_
   return take;
 }
 // push `item` of every lane with `has`
-WPT_DEV void pool_push(volatile uint32_t* q, volatile uint32_t* ring, uint32_t mask, unsigned lane, bool has, uint32_t item) {
+__device__ __noinline__ void pool_push(volatile uint32_t* q, volatile uint32_t* ring, uint32_t mask, unsigned lane, bool has, uint32_t item) {
   unsigned m = __ballot_sync(0xFFFFFFFFu, has);
   if (!m) return;
   uint32_t n = (uint32_t)__popc(m), pos = 0;

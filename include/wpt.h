@@ -130,6 +130,13 @@ int wpt_ctx_render_random(wpt_ctx* ctx, uint64_t ticks);
 /* Multi-GPU: called between adaptive rounds so that the caller can exchange the accumulator
  * rows of the other ranks (the next error map reads the whole region). NULL removes it. */
 int wpt_ctx_set_exchange_callback(wpt_ctx* ctx, void (*callback)(void* user), void* user);
+/* Multi-GPU photon warm-up (tracer.rs:126-152 split over ranks): with this callback set and
+ * config.world > 1, rank r emits the shots r, r + world, ... of every batch into per-shot slots
+ * and calls back to have `n_words` 32-bit words at device pointer `dev_words` summed in place
+ * over all ranks (integer sum: every slot is written by one rank, so the merge is bit-exact),
+ * on the session's stream (e.g. ncclAllReduce(ncclUint32, ncclSum)). NULL removes it: every
+ * rank then emits all shots itself. */
+int wpt_ctx_set_reduce_callback(wpt_ctx* ctx, void (*callback)(void* user, void* dev_words, uint64_t n_words), void* user);
 /* Photon warm-up (tracer.rs:103-152) + octree light-CDF build (photon_tree.rs). */
 int wpt_ctx_build_photons(wpt_ctx* ctx);
 /* Block until queued GPU work is finished. */

@@ -54,3 +54,33 @@ def test_rows_of_rank_cover_the_region():
         for world in (1, 2, 3, 8):
             rows = sorted(sum((rows_of_rank(H, r, world, 10) for r in range(world)), []))
             assert rows == list(range(10, 10 + H))
+
+
+def _reduce_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wasm_pathtracer_b200.dist import allreduce_words
+    # the photon-batch merge: slot i is written by rank i % world only (raw float bits viewed as int32), zeros elsewhere
+    n = 1000
+    rng = np.random.default_rng(7)
+    full = rng.standard_normal(n).astype(np.float32).view(np.int32)
+    mine = np.where(np.arange(n) % world == rank, full, 0).astype(np.int32)
+    t = torch.from_numpy(mine.copy())
+    allreduce_words(t)
+    q.put((rank, t.numpy().copy(), full))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_photon_slot_merge_is_an_exact_integer_allreduce():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_reduce_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs: p.join(60)
+    for rank, got, full in res:
+        assert np.array_equal(got, full)      # bit-exact merge: x + 0 == x in integer arithmetic

@@ -146,3 +146,80 @@ def test_wavefront_engine_matches_persistent_engine(gpu_ok, meshes):
     rgb1, _ = a.accum(); st1 = a.stats()
     assert np.array_equal(bits(rgb0), bits(rgb1))
     assert (st0["rays"], st0["node_visits"], st0["paths"]) == (st1["rays"], st1["node_visits"], st1["paths"])
+
+
+def test_pool_engine_matches_persistent_engine(gpu_ok, meshes):
+    """k_pool (engine 2: path states parked in shared memory, warps alternating logic / traversal mode) renders
+    the same bits and counts as k_mega, for both BVH kinds, PNEE and a ragged viewport."""
+    for (w, h, bvh, rtype) in [(128, 72, 2, W.NORMAL_NEE), (333, 211, 2, W.PNEE), (97, 61, 4, W.NORMAL_NEE)]:
+        a = W.PathTracer(w, h, 2, *W.CAM_BUNNY, device=0); a.store_mesh(1, meshes[4])
+        a.set_config(bvh_kind=bvh, render_type=rtype, photon_target=20000, engine=0)
+        if rtype == W.PNEE:
+            a.build_photons()
+        a.reset(); a.render_exact(3); a.render_exact(1)
+        rgb0, c0 = a.accum(); st0 = a.stats()
+        a.reset(); a.set_config(engine=2); a.render_exact(3); a.render_exact(1)
+        rgb1, c1 = a.accum(); st1 = a.stats()
+        assert np.array_equal(bits(rgb0), bits(rgb1)) and np.array_equal(c0, c1)
+        assert (st0["rays"], st0["node_visits"], st0["paths"]) == (st1["rays"], st1["node_visits"], st1["paths"])
+        a.close()
+
+
+def test_photon_warmup_split_over_ranks_is_bit_exact(gpu_ok, meshes):
+    """Multi-GPU photon warm-up, emulated with two sessions on one GPU: rank r emits every 2nd shot of each
+    batch and the batch's per-shot slots are merged with an integer sum (the NCCL allreduce of dist.attach).
+    Both ranks must end up with exactly the single-session photon list and tree."""
+    import threading
+    import torch
+    from wasm_pathtracer_b200.dist import device_tensor
+
+    ref = W.PathTracer(64, 48, 0, *W.CAM_MUSEUM, device=0)
+    ref.set_config(render_type=W.PNEE, photon_target=30000)
+    ref.build_photons()
+    want = ref.photons(); want_tree = ref.photon_tree(); st_ref = ref.stats()
+
+    world = 2
+    barrier = threading.Barrier(world)
+    staged = [None] * world
+    results = [None] * world
+    errors = []
+
+    def rank_main(rank):
+        try:
+            pt = W.PathTracer(64, 48, 0, *W.CAM_MUSEUM, device=0)
+            pt.set_config(render_type=W.PNEE, photon_target=30000, rank=rank, world=world)
+
+            def reduce(ptr, n):   # what ncclAllReduce(uint32, sum) does, with the other session on the same GPU
+                pt.synchronize()
+                staged[rank] = device_tensor(ptr, (n,), torch.int32)
+                barrier.wait()
+                total = staged[0].clone()
+                for r in range(1, world):
+                    total += staged[r]
+                torch.cuda.synchronize()
+                barrier.wait()
+                staged[rank].copy_(total)
+                torch.cuda.synchronize()
+                barrier.wait()
+
+            pt.set_reduce_callback(reduce)
+            pt.build_photons()
+            results[rank] = (pt.photons(), pt.photon_tree(), pt.stats())
+            pt.close()
+        except Exception as e:   # pragma: no cover
+            errors.append(e)
+            barrier.abort()
+
+    ts = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in ts: t.start()
+    for t in ts: t.join(120)
+    assert not errors, errors
+    rays = 0
+    for (ph, tree, st) in results:
+        assert ph[3] == want[3]
+        for a, b in zip(ph[:3], want[:3]):
+            assert np.array_equal(bits(a) if a.dtype == np.float32 else a, bits(b) if b.dtype == np.float32 else b)
+        for a, b in zip(tree, want_tree):
+            assert np.array_equal(bits(a) if a.dtype == np.float32 else a, bits(b) if b.dtype == np.float32 else b)
+        rays += st["rays"]
+    assert rays == st_ref["rays"]      # each shot was traced by exactly one rank

@@ -85,6 +85,7 @@ def load_library():
         "wpt_ctx_build_photons": (i32, [vp]),
         "wpt_ctx_render_random": (i32, [vp, u64]),
         "wpt_ctx_set_exchange_callback": (i32, [vp, C.c_void_p, vp]),
+        "wpt_ctx_set_reduce_callback": (i32, [vp, C.c_void_p, vp]),
         "wpt_ctx_synchronize": (i32, [vp]),
         "wpt_ctx_stats": (i32, [vp, P(u64)]),
         "wpt_ctx_primary_probe": (i32, [vp, P(C.c_int32), P(u32), P(f32)]),
@@ -250,6 +251,16 @@ class PathTracer:
             return
         self._cb = C.CFUNCTYPE(None, C.c_void_p)(lambda _u: fn())
         self._chk(self.L.wpt_ctx_set_exchange_callback(self.h, C.cast(self._cb, C.c_void_p), None))
+
+    def set_reduce_callback(self, fn):
+        """fn(dev_ptr, n_words) must sum `n_words` uint32 at `dev_ptr` over all ranks in place, on the session's
+        stream (multi-GPU photon warm-up: each rank emits every world-th shot); None removes it."""
+        if fn is None:
+            self._rcb = None
+            self._chk(self.L.wpt_ctx_set_reduce_callback(self.h, None, None))
+            return
+        self._rcb = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)(lambda _u, p, n: fn(int(p), int(n)))
+        self._chk(self.L.wpt_ctx_set_reduce_callback(self.h, C.cast(self._rcb, C.c_void_p), None))
 
     def build_photons(self):
         self._chk(self.L.wpt_ctx_build_photons(self.h))

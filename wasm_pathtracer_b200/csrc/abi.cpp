@@ -156,6 +156,9 @@ int wpt_ctx_render_random(wpt_ctx* ctx, uint64_t ticks) {
 int wpt_ctx_set_exchange_callback(wpt_ctx* ctx, void (*cb)(void*), void* user) {
   return guard([&] { Context* c = C(ctx); if (cb) c->exchange_hook = [cb, user] { cb(user); }; else c->exchange_hook = nullptr; });
 }
+int wpt_ctx_set_reduce_callback(wpt_ctx* ctx, void (*cb)(void*, void*, uint64_t), void* user) {
+  return guard([&] { Context* c = C(ctx); if (cb) c->reduce_hook = [cb, user](uint32_t* p, uint64_t n) { cb(user, p, n); }; else c->reduce_hook = nullptr; });
+}
 int wpt_ctx_build_photons(wpt_ctx* ctx) { return guard([&] { C(ctx)->build_photons(); }); }
 int wpt_ctx_synchronize(wpt_ctx* ctx) { return guard([&] { Context* c = C(ctx); c->require_device(); WPT_CUDA(cudaStreamSynchronize(c->stream)); }); }
 int wpt_ctx_stats(wpt_ctx* ctx, uint64_t out[8]) { return guard([&] { C(ctx)->stats(out); }); }

@@ -128,6 +128,8 @@ struct Context {
   std::list<Strategy> strategies;
   DevBuf<unsigned long long> a_stats, a_block_tot, a_block_suffix;
   std::function<void()> exchange_hook;   // multi-GPU: gather all rows' accumulators between adaptive rounds
+  std::function<void(uint32_t*, uint64_t)> reduce_hook;   // multi-GPU: in-place sum-allreduce of 32-bit words on `stream` (photon batches)
+  DevBuf<uint32_t> ph_dense;   // one photon batch: [meta | light | loc_w x 4] per shot slot
   Strategy& strategy_for(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh);
   void clear_strategies();
   void region_error(Strategy& s, float stats3[3]);

@@ -20,55 +20,53 @@ void Context::build_photons() {
   const uint64_t target = cfg.photon_target;
   const uint32_t batch = 131072;
   const uint32_t cap = (uint32_t)std::min<uint64_t>(target + batch, 0x7FFFFFFFull);
-  ph_loc_w.alloc(cap); ph_light_shot.alloc(cap); ph_meta.alloc(batch); ph_count.alloc(1);
-  WPT_CUDA(cudaMemsetAsync(ph_count.p, 0, sizeof(uint32_t), stream));
+  // Multi-GPU: with a reduce hook rank r emits the shots r, r + world, ... of every
+  // batch into dense per-shot slots and the batch is merged with an integer sum-allreduce; every
+  // rank then holds the same records and builds the same tree. Without a hook every rank emits all shots.
+  const bool split = cfg.world > 1 && (bool)reduce_hook;
+  const uint32_t e_rank = split ? cfg.rank : 0u, e_world = split ? cfg.world : 1u;
+  ph_loc_w.alloc(cap); ph_light_shot.alloc(cap); ph_dense.alloc((size_t)batch * 6);
+  uint32_t* d_meta = ph_dense.p; uint32_t* d_light = ph_dense.p + batch; float4* d_lw = reinterpret_cast<float4*>(ph_dense.p + 2 * (size_t)batch);
   RenderParams rp = params(WPT_NORMAL_NEE);
-  std::vector<uint32_t> meta(batch);
-  std::vector<uint32_t> shot_of;   // global shot index per stored photon (host order = device order)
-  uint64_t shots = 0, stored = 0, visits = 0;
+  std::vector<uint32_t> dense((size_t)batch * 6);
+  uint64_t shots = 0, stored = 0, visits = 0, own_shots = 0;
   uint32_t guard = 0;
+  ph_light.clear(); ph_loc.clear(); ph_w.clear();
   while (stored < target) {
     if (++guard > 100000) throw std::runtime_error("photon warm-up does not converge (no diffuse surface reachable)");
-    uint32_t before = (uint32_t)stored;
-    launch_photon_emit(rp, shots, batch, ph_meta.p, ph_loc_w.p, ph_light_shot.p, ph_count.p, cap, stream);
+    const uint32_t before = (uint32_t)stored;
+    WPT_CUDA(cudaMemsetAsync(ph_dense.p, 0, (size_t)batch * 6 * sizeof(uint32_t), stream));
+    launch_photon_emit(rp, shots, batch, e_rank, e_world, d_meta, d_light, d_lw, stream);
     launches += 1;
-    WPT_CUDA(cudaMemcpyAsync(meta.data(), ph_meta.p, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    if (split) reduce_hook(ph_dense.p, (uint64_t)batch * 6);
+    WPT_CUDA(cudaMemcpyAsync(dense.data(), ph_dense.p, dense.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     WPT_CUDA(cudaStreamSynchronize(stream));
-    uint32_t hits = 0, cut = batch;
-    for (uint32_t i = 0; i < batch; i++)
-      if (meta[i] & 0x80000000u) { hits++; if (before + hits == target) { cut = i + 1; break; } }
-    for (uint32_t i = 0; i < cut; i++) visits += meta[i] & 0x7FFFFFFFu;
-    // bring this batch's records to the host: keep those of shots < cut, in shot order
-    uint32_t appended = 0;
-    for (uint32_t i = 0; i < batch; i++) appended += (meta[i] >> 31);
-    std::vector<float4> lw(appended); std::vector<uint2> ls(appended);
-    if (appended) {
-      WPT_CUDA(cudaMemcpyAsync(lw.data(), ph_loc_w.p + before, appended * sizeof(float4), cudaMemcpyDeviceToHost, stream));
-      WPT_CUDA(cudaMemcpyAsync(ls.data(), ph_light_shot.p + before, appended * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
-      WPT_CUDA(cudaStreamSynchronize(stream));
-    }
-    std::vector<uint32_t> order(appended);
-    std::iota(order.begin(), order.end(), 0u);
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ls[a].y < ls[b].y; });
+    const uint32_t* meta = dense.data(); const uint32_t* light = dense.data() + batch;
+    const float4* lw = reinterpret_cast<const float4*>(dense.data() + 2 * (size_t)batch);
+    // the photon set ends with the shot that stores photon number `target`: keep shots < cut, in shot order
     std::vector<float4> lw2; std::vector<uint2> ls2;
-    for (uint32_t k : order) if (ls[k].y < cut) { lw2.push_back(lw[k]); ls2.push_back(ls[k]); shot_of.push_back((uint32_t)(shots + ls[k].y)); }
+    uint32_t cut = batch;
+    for (uint32_t i = 0; i < batch; i++) {
+      if (i % e_world == e_rank) { visits += meta[i] & 0x7FFFFFFFu; own_shots += 1; }   // this rank's share of the rays
+      if (meta[i] & 0x80000000u) {
+        lw2.push_back(lw[i]); ls2.push_back(make_uint2(light[i], i));
+        if (before + lw2.size() == target) { cut = i + 1; break; }
+      }
+    }
     if (!lw2.empty()) {
       WPT_CUDA(cudaMemcpyAsync(ph_loc_w.p + before, lw2.data(), lw2.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
       WPT_CUDA(cudaMemcpyAsync(ph_light_shot.p + before, ls2.data(), ls2.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream));
+      WPT_CUDA(cudaStreamSynchronize(stream));
     }
     stored = before + lw2.size();
-    uint32_t st32 = (uint32_t)stored;
-    WPT_CUDA(cudaMemcpyAsync(ph_count.p, &st32, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-    WPT_CUDA(cudaStreamSynchronize(stream));
     // host copies for the read-back API
-    if (before == 0) { ph_light.clear(); ph_loc.clear(); ph_w.clear(); }
     for (size_t k = 0; k < lw2.size(); k++) { ph_light.push_back(ls2[k].x); ph_loc.push_back(lw2[k].x); ph_loc.push_back(lw2[k].y); ph_loc.push_back(lw2[k].z); ph_w.push_back(lw2[k].w); }
     shots += cut;
   }
   photon_shots = shots; photon_count = stored;
   photons_shot_total += shots; photons_stored_total += stored;
   // the photon rays are rays of this session: rays += shots, node visits += their visits
-  photon_rays += shots; photon_visits += visits;
+  photon_rays += own_shots; photon_visits += visits;
   // ---- octree topology, level by level (photon_tree.rs:165-196)
   const uint32_t N = (uint32_t)stored;
   std::vector<uint32_t> child_base(1, 0xFFFFFFFFu), count(1, N), depth(1, 0);

@@ -1072,7 +1072,9 @@ void launch_resolve_rgba(const float4* accum, uint8_t* rgba, uint32_t n, cudaStr
 // ------------------------------------------------------------------ photons (tracer.rs:126-152)
 // One thread per photon shot k (stream (k, 0, STREAM_PHOTON)): light pick, point on the light,
 // uniform hemisphere direction by rejection (rng.rs:50-68), one Scene::trace, store on a
-// diffuse hit. `meta[i]` = node visits | (stored ? 1<<31 : 0) for the host-side cut.
+// diffuse hit. `meta[i]` = node visits | (stored ? 1<<31 : 0) for the host-side cut. The batch buffers are
+// zeroed before the launch and every slot is written by exactly one rank, so a sum-allreduce of the raw
+// 32-bit words merges the ranks' shots bit for bit (x + 0 = x).
 WPT_DEV F3 next_hemisphere(Rng& rng, F3 normal) {
   float x, y, z;
   for (;;) {
@@ -1086,9 +1088,9 @@ WPT_DEV F3 next_hemisphere(Rng& rng, F3 normal) {
   if (dot(v, normal) < 0.0f) return -v;
   return v;
 }
-__global__ void __launch_bounds__(128) k_photon_emit(RenderParams rp, unsigned long long shot0, uint32_t n, uint32_t* meta, float4* rec_loc_w, uint2* rec_light_shot, uint32_t* rec_count, uint32_t rec_cap) {
+__global__ void __launch_bounds__(128) k_photon_emit(RenderParams rp, unsigned long long shot0, uint32_t n, uint32_t rank, uint32_t world, uint32_t* meta, uint32_t* rec_light, float4* rec_loc_w) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || i % world != rank) return;   // multi-GPU: rank r emits the shots r, r + world, ... of the batch
   unsigned long long k = shot0 + i;
   Rng rng; rng.s = stream_seed((uint32_t)k, 0u, STREAM_PHOTON, rp.base_seed);
   uint32_t light_id = rng.range(0, rp.scene.num_lights);
@@ -1105,17 +1107,16 @@ __global__ void __launch_bounds__(128) k_photon_emit(RenderParams rp, unsigned l
       if (mc.w == 0.0f) {   // hit.mat.is_diffuse(), tracer.rs:144
         F3 hp = (ray.o + t * ray.d) + n * WPT_EPSILON;
         float w = dot(ln, dir) * fmaxf(fmaxf(inten.x, inten.y), inten.z);
-        uint32_t slot = atomicAdd(rec_count, 1u);
-        if (slot < rec_cap) { rec_loc_w[slot] = make_float4(hp.x, hp.y, hp.z, w); rec_light_shot[slot] = make_uint2(light_id, (uint32_t)i); }
+        rec_loc_w[i] = make_float4(hp.x, hp.y, hp.z, w); rec_light[i] = light_id;   // dense: the record of shot i lives in slot i
         stored = true;
       }
     }
   }
   meta[i] = g.visits | (stored ? 0x80000000u : 0u);
 }
-void launch_photon_emit(const RenderParams& rp, unsigned long long shot0, uint32_t n, uint32_t* meta, float4* rec_loc_w, uint2* rec_light_shot, uint32_t* rec_count, uint32_t rec_cap, cudaStream_t s) {
+void launch_photon_emit(const RenderParams& rp, unsigned long long shot0, uint32_t n, uint32_t rank, uint32_t world, uint32_t* meta, uint32_t* rec_light, float4* rec_loc_w, cudaStream_t s) {
   if (!n) return;
-  k_photon_emit<<<(n + 127) / 128, 128, 0, s>>>(rp, shot0, n, meta, rec_loc_w, rec_light_shot, rec_count, rec_cap);
+  k_photon_emit<<<(n + 127) / 128, 128, 0, s>>>(rp, shot0, n, rank, world ? world : 1u, meta, rec_light, rec_loc_w);
 }
 
 // ---- octree (photon_tree.rs). Cells are split level by level; a cell is split iff it finally

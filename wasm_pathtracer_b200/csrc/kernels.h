@@ -73,7 +73,7 @@ void launch_trace_batch(const RenderParams& rp, const float* o, const float* d, 
 void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t rank, uint32_t world, cudaStream_t s);
 
 // photons
-void launch_photon_emit(const RenderParams& rp, unsigned long long shot0, uint32_t n, uint32_t* meta, float4* rec_loc_w, uint2* rec_light_shot, uint32_t* rec_count, uint32_t rec_cap, cudaStream_t s);
+void launch_photon_emit(const RenderParams& rp, unsigned long long shot0, uint32_t n, uint32_t rank, uint32_t world, uint32_t* meta, uint32_t* rec_light, float4* rec_loc_w, cudaStream_t s);
 void launch_octree_assign(const float4* loc_w, uint32_t n, uint32_t* node_of, const uint32_t* child_base, uint32_t* count, cudaStream_t s);
 void launch_octree_bins(const float4* loc_w, const uint2* light_shot, uint32_t n, const uint32_t* child_base, unsigned long long* fx, uint32_t num_lights, cudaStream_t s);
 void launch_octree_cdf(const unsigned long long* fx, float* bins, float* cum, uint32_t num_nodes, uint32_t num_lights, cudaStream_t s);

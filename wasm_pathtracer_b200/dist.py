@@ -64,3 +64,28 @@ def allgather_rows(pt, rank, world, group=None):
         exchange_rows(acc, rank, world, group)
     pt.mark_accum_dirty()
     return acc
+
+
+def allreduce_words(words, group=None):
+    """In-place integer sum of a 1-D int32 tensor over all ranks (NCCL on CUDA tensors, gloo on CPU)."""
+    dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group)
+    return words
+
+
+def attach(pt, rank, world, group=None):
+    """Wire a PathTracer session into the process group: row partition, accumulator all-gather between
+    adaptive rounds, and the photon warm-up split over ranks (each batch of per-shot photon slots is
+    merged with an integer sum-allreduce on the session's stream — every slot is written by exactly
+    one rank, so the result is bit-identical to a single-GPU warm-up)."""
+    pt.set_config(rank=rank, world=world)
+    if world == 1:
+        pt.set_exchange_callback(None); pt.set_reduce_callback(None)
+        return pt
+
+    def reduce(ptr, n):
+        with torch.cuda.stream(session_stream(pt)):
+            allreduce_words(device_tensor(ptr, (n,), torch.int32), group)
+
+    pt.set_exchange_callback(lambda: allgather_rows(pt, rank, world, group))
+    pt.set_reduce_callback(reduce)
+    return pt

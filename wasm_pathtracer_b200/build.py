@@ -27,3 +27,20 @@ def build_library(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("building libwpt.so failed")
     return LIB
+
+
+TOOLS_DIR = os.path.join(PKG_DIR, "..", "tools")
+RENDER = os.path.join(TOOLS_DIR, "wpt_render")
+
+
+def build_tools(force=False):
+    """Compile tools/wpt_render (the worker-style progressive driver, plain C++ over include/wpt.h)."""
+    src = os.path.join(TOOLS_DIR, "wpt_render.cpp")
+    if force or not os.path.exists(RENDER) or os.path.getmtime(RENDER) < max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", src, "-I" + os.path.join(PKG_DIR, "..", "include"), "-L" + PKG_DIR, "-lwpt",
+               "-Wl,-rpath,$ORIGIN/../wasm_pathtracer_b200", "-o", RENDER]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("building tools/wpt_render failed")
+    return RENDER

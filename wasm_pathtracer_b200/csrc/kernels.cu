@@ -608,21 +608,26 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   if (lane == 1) atomicAdd(&P.counters[8], i_sh);
 #endif
 }
-void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
-  if (!P.nslots) return;
-  if (!(P.simple_scene && P.rp.scene.bvh_kind == 2)) blocks_per_sm = 4;   // the other variants are built for 4 blocks / SM
+template <int BVH, bool SIMPLE>
+static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   int grid = device_sm_count() * blocks_per_sm;
   int need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS);
   if (grid > need) grid = need;
+  switch (blocks_per_sm) {
+    case 5: k_mega<BVH, SIMPLE, 5><<<grid, MEGA_THREADS, 0, s>>>(P); break;
+    case 6: k_mega<BVH, SIMPLE, 6><<<grid, MEGA_THREADS, 0, s>>>(P); break;
+    case 7: k_mega<BVH, SIMPLE, 7><<<grid, MEGA_THREADS, 0, s>>>(P); break;
+    case 8: k_mega<BVH, SIMPLE, 8><<<grid, MEGA_THREADS, 0, s>>>(P); break;
+    default: k_mega<BVH, SIMPLE, 4><<<grid, MEGA_THREADS, 0, s>>>(P); break;
+  }
+}
+// blocks_per_sm[variant]: 0 = triangles/planes BVH2, 1 = triangles/planes BVH4, 2 = generic BVH2, 3 = generic BVH4
+void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s) {
+  if (!P.nslots) return;
   const bool b4 = P.rp.scene.bvh_kind == 4;
-  if (P.simple_scene) {
-    if (b4) k_mega<4, true, 4><<<grid, MEGA_THREADS, 0, s>>>(P);
-    else if (blocks_per_sm == 5) k_mega<2, true, 5><<<grid, MEGA_THREADS, 0, s>>>(P);
-    else if (blocks_per_sm == 6) k_mega<2, true, 6><<<grid, MEGA_THREADS, 0, s>>>(P);
-    else if (blocks_per_sm == 7) k_mega<2, true, 7><<<grid, MEGA_THREADS, 0, s>>>(P);
-    else if (blocks_per_sm == 8) k_mega<2, true, 8><<<grid, MEGA_THREADS, 0, s>>>(P);
-    else k_mega<2, true, 4><<<grid, MEGA_THREADS, 0, s>>>(P);
-  } else { if (b4) k_mega<4, false, 4><<<grid, MEGA_THREADS, 0, s>>>(P); else k_mega<2, false, 4><<<grid, MEGA_THREADS, 0, s>>>(P); }
+  auto clampb = [](int b) { return b < 4 ? 4 : (b > 8 ? 8 : b); };
+  if (P.simple_scene) { if (b4) launch_mega_t<4, true>(P, clampb(blocks_per_sm[1]), s); else launch_mega_t<2, true>(P, clampb(blocks_per_sm[0]), s); }
+  else { if (b4) launch_mega_t<4, false>(P, clampb(blocks_per_sm[3]), s); else launch_mega_t<2, false>(P, clampb(blocks_per_sm[2]), s); }
 }
 
 // ------------------------------------------------------------------ block-pool path kernel

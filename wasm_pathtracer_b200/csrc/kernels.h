@@ -60,7 +60,7 @@ struct MegaParams {
   uint32_t* work_counter;         // zeroed before the launch
   unsigned long long* counters;
 };
-void launch_mega(const MegaParams& P, int blocks_per_sm, cudaStream_t s);
+void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s);   // per kernel variant, see kernels.cu
 // Block-pool path kernel (k_pool): path states parked in shared memory, warps alternate between logic and traversal mode.
 void launch_pool(const MegaParams& P, int blocks_per_sm, uint32_t slots_per_block, cudaStream_t s);
 

@@ -53,6 +53,17 @@ struct RenderTarget {   // render_target.rs:5-138
     result[i * 4 + 1] = to_u8(a.y / cnt);
     result[i * 4 + 2] = to_u8(a.z / cnt);
   }
+  // Mode B only (contract B10): `n` samples whose colours were summed from +0 are added at once.
+  void write_sum(size_t x, size_t y, Vec3 sum, uint32_t n) {
+    size_t i = viewport_width * y + x;
+    acc_buffer[i] = acc_buffer[i] + sum;
+    acc_count[i] += n;
+    Vec3 a = acc_buffer[i];
+    float cnt = (float)acc_count[i];
+    result[i * 4 + 0] = to_u8(a.x / cnt);
+    result[i * 4 + 1] = to_u8(a.y / cnt);
+    result[i * 4 + 2] = to_u8(a.z / cnt);
+  }
   Vec3 read_clamped(size_t x, size_t y) const {   // render_target.rs:74-77
     size_t i = viewport_width * y + x;
     return clamp01(acc_buffer[i] / (float)acc_count[i]);

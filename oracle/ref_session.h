@@ -189,14 +189,29 @@ struct Session {
   }
 
   // One sample `s` of pixel (x,y): stream (pixel index in the full viewport, s, STREAM_PATH).
-  void mb_sample(const Integrator& I, size_t x, size_t y, uint32_t s, Stats& st) {
+  Vec3 mb_sample(const Integrator& I, size_t x, size_t y, uint32_t s, Stats& st) {
     Rng r(stream_seed((uint32_t)(y * W + x), s, STREAM_PATH, mb.base_seed));
     float j1 = r.next();
     float j2 = r.next();
     Ray ray = camera_ray(camera, W, H, x, y, j1, j2);
     Vec3 res = I.trace_original_color(ray, r, st);
     st.paths++;
-    target->write(x, y, res);
+    return res;
+  }
+  // Mode-B accumulation contract: the `n` samples a pixel receives in one call are
+  // summed in segments of at most `seg` consecutive samples, each segment from +0 in sample order,
+  // and the segment sums are added to the accumulator in order. (A single call of <= seg samples
+  // on a cleared pixel gives the same bits as RenderTarget::write per sample, since 0 + c == c.)
+  // Segments are what lets the GPU run the samples of ONE pixel on several lanes at once.
+  static constexpr uint32_t MB_SEGMENT = 16;
+  void mb_samples(const Integrator& I, size_t x, size_t y, uint32_t n, uint32_t seg, Stats& st) {
+    uint32_t s0 = (uint32_t)target->acc_count[y * W + x];
+    for (uint32_t j = 0; j < n; j += seg) {
+      uint32_t m = n - j < seg ? n - j : seg;
+      Vec3 sum(0.0f, 0.0f, 0.0f);
+      for (uint32_t k = 0; k < m; k++) sum = sum + mb_sample(I, x, y, s0 + j + k, st);
+      target->write_sum(x, y, sum, m);
+    }
   }
 
   // `spp` more samples for every pixel of the region; pixel rows interleaved over threads.
@@ -209,8 +224,7 @@ struct Session {
       for (size_t yy = t; yy < mb.rh; yy += threads)
         for (size_t xx = 0; xx < mb.rw; xx++) {
           size_t x = mb.rx + xx, y = mb.ry + yy;
-          uint32_t s0 = (uint32_t)target->acc_count[y * W + x];
-          for (uint32_t s = 0; s < spp; s++) mb_sample(I, x, y, s0 + s, tst[t]);
+          mb_samples(I, x, y, spp, MB_SEGMENT, tst[t]);
         }
       tst[t].prim_tests = tl_prim_tests();
     };
@@ -283,8 +297,8 @@ struct Session {
         for (size_t yy = t; yy < mb.rh; yy += threads)
           for (size_t xx = 0; xx < mb.rw; xx++) {
             size_t x = mb.rx + xx, y = mb.ry + yy;
-            uint32_t s0 = (uint32_t)target->acc_count[y * W + x];
-            for (uint32_t s = 0; s < take[yy * mb.rw + xx]; s++) mb_sample(I, x, y, s0 + s, tst[t]);
+            uint32_t n = take[yy * mb.rw + xx];
+            if (n) mb_samples(I, x, y, n, n, tst[t]);   // a strategy round = one segment per pixel (round spp <= 33)
           }
         tst[t].prim_tests = tl_prim_tests();
       };
@@ -318,8 +332,8 @@ struct Session {
       for (size_t yy = t; yy < mb.rh; yy += threads)
         for (size_t xx = 0; xx < mb.rw; xx++) {
           size_t x = mb.rx + xx, y = mb.ry + yy;
-          uint32_t s0 = (uint32_t)target->acc_count[y * W + x];
-          for (uint32_t s = 0; s < take[yy * mb.rw + xx]; s++) mb_sample(I, x, y, s0 + s, tst[t]);
+          uint32_t n = take[yy * mb.rw + xx];
+          if (n) mb_samples(I, x, y, n, n, tst[t]);
         }
     };
     run_threads(threads, work);

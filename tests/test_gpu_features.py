@@ -223,3 +223,32 @@ def test_photon_warmup_split_over_ranks_is_bit_exact(gpu_ok, meshes):
             assert np.array_equal(bits(a) if a.dtype == np.float32 else a, bits(b) if b.dtype == np.float32 else b)
         rays += st["rays"]
     assert rays == st_ref["rays"]      # each shot was traced by exactly one rank
+
+
+def test_segmented_accumulation_contract_b10(gpu_ok, meshes):
+    """render_exact sums a pixel's samples in segments of 16 (each from +0, added in order), so that one pixel's
+    samples can run on several lanes: 37 + 5 samples = segments 16 | 16 | 5 then 5. The oracle follows the same
+    contract; the three engines and a two-rank partition give the same bits."""
+    w, h = 80, 45
+    pt, orc = pair(2, W.CAM_BUNNY, w, h, meshes[3], rtype=W.NORMAL_NEE)
+    pt.render_exact(37); pt.render_exact(5)
+    orc.mb_render_exact(37, threads=4); orc.mb_render_exact(5, threads=4)
+    rgb, cnt = pt.accum(); orgb, ocnt = orc.accum()
+    assert np.array_equal(cnt, ocnt) and int(cnt.min()) == 42
+    assert np.array_equal(bits(rgb), bits(orgb))
+    st, ost = pt.stats(), orc.stats(0)
+    assert (st["rays"], st["node_visits"], st["paths"]) == (ost["rays"], ost["node_visits"], ost["paths"])
+    for engine in (1, 2):
+        pt.reset(); pt.set_config(engine=engine); pt.render_exact(37); pt.render_exact(5)
+        r2, c2 = pt.accum()
+        assert np.array_equal(bits(rgb), bits(r2)) and np.array_equal(cnt, c2), engine
+    # two row-interleaved ranks, each rendering its rows: together the same frame
+    parts = []
+    for rank in range(2):
+        q = W.PathTracer(w, h, 2, *W.CAM_BUNNY, device=0); q.store_mesh(1, meshes[3])
+        q.set_config(render_type=W.NORMAL_NEE, rank=rank, world=2)
+        q.render_exact(37); q.render_exact(5)
+        parts.append(q.accum()[0]); q.close()
+    merged = parts[0].copy(); merged[1::2] = parts[1][1::2]
+    assert np.array_equal(bits(merged), bits(rgb))
+    pt.close()

@@ -2,6 +2,7 @@
 // driver loop. No CPU rendering path exists here: without a CUDA device every entry point
 // fails.
 #include "context.h"
+#include <algorithm>
 #include <cstring>
 #include <cmath>
 #include <cstdio>
@@ -237,6 +238,10 @@ void Context::run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot
   RenderParams rp = params(render_type);
   PathState st = path_state();
   WaveBuffers wb = wave_buffers();
+  // contract B10: this run is one segment — its samples are summed from +0 in d_seg_acc, then added
+  d_seg_acc.alloc((size_t)W * H);
+  launch_clear_pixels(d_seg_acc.p, s_pixel.p, slots, stream);
+  wb.accum = d_seg_acc.p;
   launch_setup_slots(st, d_spp_per_slot, uniform_spp, d_accum.p, stream);
   WPT_CUDA(cudaMemsetAsync(w_shadow_n.p, 0, 2 * sizeof(uint32_t), stream));
   WPT_CUDA(cudaMemsetAsync(w_ring.p, 0, 64 * sizeof(uint32_t), stream));
@@ -269,6 +274,8 @@ void Context::run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot
     if (profiling) ev_harvest();
     if (h_ring[iter & 63u] == 0) break;
   }
+  launch_add_segment(d_accum.p, s_pixel.p, slots, d_seg_acc.p, stream);
+  launches += 2;
   iterations += iter;
   rgba_stale = true;
 }
@@ -280,7 +287,14 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   if (render_type == WPT_PNEE && !photons_ready) throw std::runtime_error("photon tree not built");
   MegaParams P{};
   P.rp = params(render_type);
-  P.accum = d_accum.p; P.pixel = s_pixel.p; P.spp_per_slot = d_spp_per_slot; P.uniform_spp = uniform_spp; P.nslots = slots;
+  P.accum = d_accum.p; P.pixel = s_pixel.p; P.spp_per_slot = d_spp_per_slot; P.uniform_spp = uniform_spp;
+  // contract B10: render_exact cuts a pixel's samples into segments of WPT_SEGMENT_LEN, each summed from +0 by its
+  // own slot (so one pixel's samples can run on several lanes); a strategy round (per-slot counts) is one segment.
+  P.nseg = d_spp_per_slot ? 1u : std::max(1u, (uniform_spp + WPT_SEGMENT_LEN - 1u) / WPT_SEGMENT_LEN);
+  P.seg_len = d_spp_per_slot ? 0x7FFFFFFFu : WPT_SEGMENT_LEN;
+  if ((uint64_t)slots * P.nseg > 0x7FFFFFFFull) throw std::runtime_error("too many samples per pixel for one render_exact call at this viewport size");
+  P.nslots = slots * P.nseg;
+  if (P.nseg > 1) { d_seg_buf.alloc((size_t)P.nslots); P.seg_buf = d_seg_buf.p; }
   P.work_counter = w_work.p; P.counters = w_counters.p;
   WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
   cudaEvent_t a = nullptr, b = nullptr;
@@ -311,6 +325,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   } else launch_mega(P, env_minb, stream);
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());
+  if (P.nseg > 1) { launch_combine_segments(d_accum.p, s_pixel.p, slots, d_seg_buf.p, P.nseg, uniform_spp, stream); launches += 1; }
   launches += 1; iterations += 1;
   rgba_stale = true;
 }
@@ -326,7 +341,9 @@ void Context::render_exact(uint32_t spp) {
   uint32_t rx, ry, rw, rh;
   region(&rx, &ry, &rw, &rh);
   ensure_slots(rx, ry, rw, rh);
-  run_paths(cfg.render_type, nullptr, spp);
+  if (cfg.engine == 1) {   // the wavefront engine runs the segments of contract B10 one after the other
+    for (uint32_t rem = spp; rem > 0;) { uint32_t m = std::min(rem, WPT_SEGMENT_LEN); run_wavefront(cfg.render_type, nullptr, m); rem -= m; }
+  } else run_persistent(cfg.render_type, nullptr, spp);
 }
 
 const uint8_t* Context::results(uint32_t show_sampling) {   // wasm_interface.rs:120-134

@@ -478,7 +478,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
   uint32_t c_rays = 0, c_visits = 0, c_prims = 0, c_paths = 0;
   uint32_t chunk_next = 0, chunk_end = 0, spare_next = 0, spare_end = 0; bool queue_empty = false;   // warp-uniform
-  F3 acc_rgb = f3(0, 0, 0);   // this pixel's accumulator (render_target.rs:8): loaded at fetch, stored when the pixel is done
+  F3 acc_rgb = f3(0, 0, 0);   // sum of this segment's samples (contract B10), added to the pixel's accumulator (render_target.rs:8) when the segment is done
+  uint32_t slot_id = 0;
 #ifdef MEGA_INSTR
   unsigned long long i_lp = 0, i_ll = 0, i_ts = 0, i_tl = 0, i_sh = 0;   // logic passes, logic lanes, trav steps, trav lanes, shade lanes
 #endif
@@ -503,12 +504,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         uint32_t idx = r < avail ? chunk_next + r : spare_next + (r - avail);
         bool ok = r < avail ? true : (idx < spare_end);
         if (ok) {
-          pix = P.pixel[idx];
-          uint32_t spp = P.spp_per_slot ? P.spp_per_slot[idx] : P.uniform_spp;
-          float4 a0 = P.accum[pix];
-          acc_rgb = xyz(a0);
-          s = __float_as_uint(a0.w);   // samples accumulated so far = next sample index
-          s_end = s + spp;
+          // contract B10: the samples of this launch are summed per segment from +0; a slot is one segment
+          uint32_t pslot = idx, j = 0;
+          if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
+          slot_id = idx;
+          pix = P.pixel[pslot];
+          uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;
+          uint32_t s0 = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
+          uint32_t b = min(j * P.seg_len, spp);
+          s = s0 + b;
+          s_end = s0 + min(b + P.seg_len, spp);
+          acc_rgb = f3(0.0f, 0.0f, 0.0f);
           what = ST_GEN; phase = PH_LOGIC;
         } else if (queue_empty) phase = PH_DONE;
       }
@@ -591,7 +597,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
           what = ST_EXTEND; start = true;
         } else {
-          P.accum[pix] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, __uint_as_float(s));
+          if (P.nseg > 1) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
+          else {   // the only segment of its pixel: add it here
+            float4 a = P.accum[pix];
+            P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));
+          }
           phase = PH_NEED;
         }
       }
@@ -649,13 +659,13 @@ void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s
 // still run one after the other by its slot, so the accumulation order — and every bit of the
 // result — is unchanged.
 #define POOL_THREADS 256
-#define POOL_NF 33
+#define POOL_NF 34
 #define POOL_EMPTY 0xFFFFFFFFu
 enum : int { PQ_HEAD = 0, PQ_TAIL = 1, PQ_COUNT = 2 };
 enum : int { PC_L = 0, PC_T = 4, PC_RETIRED = 8, PC_LOCK = 9, PC_EXH = 10, PC_CHUNK = 12 /* 64-bit, 8-byte aligned */, PC_WORDS = 16 };
 // state words
 enum : int { PF_O = 0, PF_D = 3, PF_T = 6, PF_COL = 9, PF_RNG = 12, PF_PIX = 13, PF_S = 14, PF_SEND = 15, PF_ACC = 16, PF_FLAGS = 19,
-             PF_RT = 20, PF_RID = 21, PF_EXO = 22, PF_EXD = 25, PF_CON = 28, PF_SHLEN = 31, PF_SHLIGHT = 32 };
+             PF_RT = 20, PF_RID = 21, PF_EXO = 22, PF_EXD = 25, PF_CON = 28, PF_SHLEN = 31, PF_SHLIGHT = 32, PF_SLOT = 33 };
 
 // one lane reads the control word, every lane gets the same value (keeps the branches around the ballots uniform)
 WPT_DEV uint32_t pool_peek(volatile uint32_t* p, unsigned lane) {
@@ -728,14 +738,14 @@ __device__ __noinline__ void pool_pixels(volatile uint32_t* ctrl, uint32_t* work
 // park a path: write its state into its slot. The shadow-ray fields are only live while a
 // shadow ray is pending.
 template <bool FLUSH>
-WPT_DEV void pool_store(uint32_t* stw, float* stf, uint32_t S, uint32_t home, F3 ro, F3 rd, const PathRegs& ps, uint32_t pix, uint32_t s, uint32_t s_end, F3 acc_rgb,
+WPT_DEV void pool_store(uint32_t* stw, float* stf, uint32_t S, uint32_t home, F3 ro, F3 rd, const PathRegs& ps, uint32_t pix, uint32_t slot_id, uint32_t s, uint32_t s_end, F3 acc_rgb,
                         int what, bool alive_after_shadow, bool haspix, float res_t, int res_id, F3 ext_o, F3 ext_d, F3 contrib, float sh_len, int sh_light) {
   uint32_t* w = stw + home; float* f = stf + home;
   f[(PF_O + 0) * S] = ro.x; f[(PF_O + 1) * S] = ro.y; f[(PF_O + 2) * S] = ro.z;
   f[(PF_D + 0) * S] = rd.x; f[(PF_D + 1) * S] = rd.y; f[(PF_D + 2) * S] = rd.z;
   f[(PF_T + 0) * S] = ps.T.x; f[(PF_T + 1) * S] = ps.T.y; f[(PF_T + 2) * S] = ps.T.z;
   f[(PF_COL + 0) * S] = ps.color.x; f[(PF_COL + 1) * S] = ps.color.y; f[(PF_COL + 2) * S] = ps.color.z;
-  w[PF_RNG * S] = ps.rng.s; w[PF_PIX * S] = pix; w[PF_S * S] = s; w[PF_SEND * S] = s_end;
+  w[PF_RNG * S] = ps.rng.s; w[PF_PIX * S] = pix; w[PF_S * S] = s; w[PF_SEND * S] = s_end; w[PF_SLOT * S] = slot_id;
   f[(PF_ACC + 0) * S] = acc_rgb.x; f[(PF_ACC + 1) * S] = acc_rgb.y; f[(PF_ACC + 2) * S] = acc_rgb.z;
   w[PF_FLAGS * S] = (uint32_t)what | (ps.bounced ? 4u : 0u) | (alive_after_shadow ? 8u : 0u) | (haspix ? 16u : 0u);
   f[PF_RT * S] = res_t; w[PF_RID * S] = (uint32_t)res_id;
@@ -780,7 +790,7 @@ __global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint3
       // =============================================================== logic mode
       bool have = false, pend = false, haspix = false, alive_after_shadow = false;
       int what = ST_GEN;
-      uint32_t home = 0, pix = 0, s = 0, s_end = 0;
+      uint32_t home = 0, pix = 0, s = 0, s_end = 0, slot_id = 0;
       PathRegs ps; ps.color = f3(0, 0, 0); ps.T = f3(1, 1, 1); ps.rng.s = 1u; ps.bounced = false;
       F3 ro = f3(0, 0, 0), rd = f3(1, 1, 1), acc_rgb = f3(0, 0, 0);
       F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
@@ -799,7 +809,7 @@ __global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint3
             uint32_t availT = pool_peek(ctrl + PC_T + PQ_COUNT, lane);
             if (availT >= P.t_switch || (n_have == 0u && availL == 0u && availT != 0u)) {
               if (n_have) {   // flush: these paths are logic-ready (their result is in res_t / res_id)
-                if (have) pool_store<true>(stw, stf, S, home, ro, rd, ps, pix, s, s_end, acc_rgb, what, alive_after_shadow, haspix, res_t, res_id, ext_o, ext_d, contrib, sh_len, sh_light);
+                if (have) pool_store<true>(stw, stf, S, home, ro, rd, ps, pix, slot_id, s, s_end, acc_rgb, what, alive_after_shadow, haspix, res_t, res_id, ext_o, ext_d, contrib, sh_len, sh_light);
                 pool_push(ctrl + PC_L, ringL, mask, lane, have, home);
                 have = false;
               }
@@ -821,7 +831,7 @@ __global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint3
               rd = f3(f[(PF_D + 0) * S], f[(PF_D + 1) * S], f[(PF_D + 2) * S]);
               ps.T = f3(f[(PF_T + 0) * S], f[(PF_T + 1) * S], f[(PF_T + 2) * S]);
               ps.color = f3(f[(PF_COL + 0) * S], f[(PF_COL + 1) * S], f[(PF_COL + 2) * S]);
-              ps.rng.s = w[PF_RNG * S]; pix = w[PF_PIX * S]; s = w[PF_S * S]; s_end = w[PF_SEND * S];
+              ps.rng.s = w[PF_RNG * S]; pix = w[PF_PIX * S]; s = w[PF_S * S]; s_end = w[PF_SEND * S]; slot_id = w[PF_SLOT * S];
               acc_rgb = f3(f[(PF_ACC + 0) * S], f[(PF_ACC + 1) * S], f[(PF_ACC + 2) * S]);
               uint32_t fl = w[PF_FLAGS * S];
               what = (int)(fl & 3u); ps.bounced = (fl & 4u) != 0; alive_after_shadow = (fl & 8u) != 0; haspix = (fl & 16u) != 0;
@@ -861,13 +871,16 @@ __global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint3
           if (needpix) {
             uint32_t rank = (uint32_t)__popc(nm & lt);
             if (rank < k) {
-              uint32_t idx = base + rank;
-              pix = P.pixel[idx];
-              uint32_t spp = P.spp_per_slot ? P.spp_per_slot[idx] : P.uniform_spp;
-              float4 a0 = P.accum[pix];
-              acc_rgb = xyz(a0);
-              s = __float_as_uint(a0.w);   // samples accumulated so far = next sample index
-              s_end = s + spp;
+              uint32_t idx = base + rank, pslot = idx, j = 0;
+              if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
+              slot_id = idx;
+              pix = P.pixel[pslot];
+              uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;
+              uint32_t s0 = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
+              uint32_t b = min(j * P.seg_len, spp);
+              s = s0 + b;
+              s_end = s0 + min(b + P.seg_len, spp);
+              acc_rgb = f3(0.0f, 0.0f, 0.0f);   // contract B10: segment sum from +0
               haspix = true;
             } else if (k == 0) { retire = true; have = false; }   // the global queue is exhausted: the slot retires
           }
@@ -915,7 +928,11 @@ __global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint3
               ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
               what = ST_EXTEND; start = true;
             } else {
-              P.accum[pix] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, __uint_as_float(s));
+              if (P.nseg > 1) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
+              else {
+                float4 a = P.accum[pix];
+                P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));
+              }
               haspix = false;
             }
           }
@@ -931,7 +948,7 @@ __global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint3
         // ---- park the lanes whose ray has to traverse the BVH
         bool park = have && pend;
         if (__ballot_sync(FULL, park)) {
-          if (park) pool_store<false>(stw, stf, S, home, ro, rd, ps, pix, s, s_end, acc_rgb, what, alive_after_shadow, haspix, res_t, res_id, ext_o, ext_d, contrib, sh_len, sh_light);
+          if (park) pool_store<false>(stw, stf, S, home, ro, rd, ps, pix, slot_id, s, s_end, acc_rgb, what, alive_after_shadow, haspix, res_t, res_id, ext_o, ext_d, contrib, sh_len, sh_light);
           pool_push(ctrl + PC_T, ringT, mask, lane, park, home);
           if (park) { have = false; pend = false; }
         }
@@ -1048,6 +1065,44 @@ void launch_pool(const MegaParams& P, int blocks_per_sm, uint32_t slots_per_bloc
     else if (blocks_per_sm == 3) launch_pool_t<2, true, 3>(P, S, cap, grid, s);
     else launch_pool_t<2, true, 2>(P, S, cap, grid, s);
   } else { if (b4) launch_pool_t<4, false, 2>(P, S, cap, grid, s); else launch_pool_t<2, false, 2>(P, S, cap, grid, s); }
+}
+
+// ------------------------------------------------------------------ segments (contract B10)
+// accum[pix] += seg_0; += seg_1; ... in segment order, one thread per pixel; the sample count grows by spp.
+__global__ void k_combine_segments(float4* accum, const uint32_t* __restrict__ pixel, uint32_t npix, const float4* __restrict__ seg_buf, uint32_t nseg, uint32_t spp) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  uint32_t pix = pixel[i];
+  float4 a = accum[pix];
+  for (uint32_t j = 0; j < nseg; j++) { float4 g = seg_buf[(size_t)i * nseg + j]; a.x += g.x; a.y += g.y; a.z += g.z; }
+  a.w = __uint_as_float(__float_as_uint(a.w) + spp);
+  accum[pix] = a;
+}
+void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, uint32_t nseg, uint32_t spp, cudaStream_t s) {
+  if (!npix) return;
+  k_combine_segments<<<(npix + 255) / 256, 256, 0, s>>>(accum, pixel, npix, seg_buf, nseg, spp);
+}
+// wavefront engine: one segment was accumulated sample by sample into seg_acc (rgb sum from +0, count): add it
+__global__ void k_add_segment(float4* accum, const uint32_t* __restrict__ pixel, uint32_t npix, const float4* __restrict__ seg_acc) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  uint32_t pix = pixel[i];
+  float4 a = accum[pix], g = seg_acc[pix];
+  a.x += g.x; a.y += g.y; a.z += g.z;
+  a.w = __uint_as_float(__float_as_uint(a.w) + __float_as_uint(g.w));
+  accum[pix] = a;
+}
+void launch_add_segment(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_acc, cudaStream_t s) {
+  if (!npix) return;
+  k_add_segment<<<(npix + 255) / 256, 256, 0, s>>>(accum, pixel, npix, seg_acc);
+}
+__global__ void k_clear_pixels(float4* buf, const uint32_t* __restrict__ pixel, uint32_t npix) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npix) buf[pixel[i]] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+void launch_clear_pixels(float4* buf, const uint32_t* pixel, uint32_t npix, cudaStream_t s) {
+  if (!npix) return;
+  k_clear_pixels<<<(npix + 255) / 256, 256, 0, s>>>(buf, pixel, npix);
 }
 
 // ------------------------------------------------------------------ resolve (render_target.rs:59-64)

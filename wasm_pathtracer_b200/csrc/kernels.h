@@ -51,7 +51,9 @@ struct MegaParams {
   float4* accum;
   const uint32_t* pixel;          // slot -> viewport pixel index
   const uint32_t* spp_per_slot;   // may be null: `uniform_spp` for every slot
-  uint32_t uniform_spp, nslots;
+  uint32_t uniform_spp, nslots;       // nslots = pixel slots x nseg
+  uint32_t nseg, seg_len;             // contract B10: a pixel's samples of this launch are cut into nseg segments of seg_len
+  float4* seg_buf;                    // nseg > 1: segment sums [pixel slot * nseg + j], combined in order by launch_combine_segments
   uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
   uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
   uint32_t t_switch;              // k_pool: an under-filled logic warp flushes and goes traversing when qT holds at least this many rays
@@ -67,6 +69,9 @@ void launch_pool(const MegaParams& P, int blocks_per_sm, uint32_t slots_per_bloc
 void launch_setup_slots(const PathState& st, const uint32_t* spp_per_slot, uint32_t uniform_spp, const float4* accum, cudaStream_t s);
 void launch_trace(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
 void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
+void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, uint32_t nseg, uint32_t spp, cudaStream_t s);
+void launch_add_segment(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_acc, cudaStream_t s);
+void launch_clear_pixels(float4* buf, const uint32_t* pixel, uint32_t npix, cudaStream_t s);
 void launch_resolve_rgba(const float4* accum, uint8_t* rgba, uint32_t n, cudaStream_t s);
 void launch_primary_probe(const RenderParams& rp, int32_t* ids, uint32_t* visits, float* dist, cudaStream_t s);
 void launch_trace_batch(const RenderParams& rp, const float* o, const float* d, uint64_t n, int32_t* ids, float* dist, uint32_t* visits, float* normals, cudaStream_t s);

@@ -2,6 +2,9 @@
 // reference-style compute() tick driver. All rendering goes through Context::run_paths.
 #include "context.h"
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -250,6 +253,11 @@ void Context::render_take(Strategy& s, uint32_t render_type) {
 // Every rank evaluates the (cheap) error map of the whole region from the gathered
 // accumulators, so no reduction is needed; each rank renders only its own rows.
 uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange) {
+  // WPT_TRACE_ROUNDS=1: wall-clock split of the rounds (error map / render / exchange), printed once per call
+  static const bool trace = std::getenv("WPT_TRACE_ROUNDS") != nullptr;
+  double t_err = 0, t_render = 0, t_xchg = 0; uint32_t rounds = 0;
+  auto now = [&] { if (trace) cudaStreamSynchronize(stream); return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   const uint32_t N = s.rw * s.rh;
   if (!N) return 0;
   if (s.round_left.n < N) { s.round_left.alloc(N); s.take.alloc(N); s.round_spp.alloc(N); launch_fill_u32(s.round_left.p, N, 0, stream); s.left_total = 0; s.started = false; }
@@ -264,6 +272,7 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
         s.started = true;
       } else {
         float st3[3];
+        auto t0 = now();
         region_error(s, st3);
         launch_adaptive_spp(s.mse.p, N, st3[0], st3[1], st3[2], s.round_left.p, d_sampling.p, W, s.rx, s.ry, s.rw, stream);
         a_stats.alloc(4);
@@ -274,6 +283,7 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
         WPT_CUDA(cudaMemcpyAsync(&tot, a_stats.p, sizeof tot, cudaMemcpyDeviceToHost, stream));
         WPT_CUDA(cudaStreamSynchronize(stream));
         s.left_total = tot;
+        if (trace) t_err += secs(t0, now());
       }
       WPT_CUDA(cudaMemcpyAsync(s.round_spp.p, s.round_left.p, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
     }
@@ -295,13 +305,17 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
       launches += 2;
       taken = room;
     }
+    auto t1 = now();
     render_take(s, render_type);
     launch_sub_u32(s.round_left.p, s.take.p, N, stream);
     launches += 1;
     s.left_total -= taken;
     used += taken;
+    auto t2 = now();
     if (exchange) exchange();   // multi-GPU: gather the other ranks' rows before the next error map
+    if (trace) { auto t3 = now(); t_render += secs(t1, t2); t_xchg += secs(t2, t3); rounds++; }
   }
+  if (trace) std::fprintf(stderr, "wpt adaptive (rank %u): %u rounds, error map %.3f s, render %.3f s, exchange %.3f s\n", cfg.rank, rounds, t_err, t_render, t_xchg);
   return used;
 }
 

@@ -28,23 +28,33 @@ def device_tensor(ptr, shape, dtype=torch.float32):
     return torch.as_tensor(_DevArray(ptr, shape, typestr), device="cuda")
 
 
+_staging = {}
+
+
 def exchange_rows(frame, rank, world, group=None):
     """All-gather interleaved rows of `frame` ((H, ...) tensor, CPU or CUDA) in place.
 
     On entry rank r holds valid data in rows r, r + world, ...; on exit every rank holds all rows.
+    Three device operations: pack own rows, one all_gather_into_tensor, one permuted unpack.
     """
     if world == 1:
         return frame
     H = frame.shape[0]
+    rest = tuple(frame.shape[1:])
     per = (H + world - 1) // world
+    key = (H, rest, frame.dtype, str(frame.device), world)
+    if key not in _staging:
+        _staging[key] = (torch.zeros((per,) + rest, dtype=frame.dtype, device=frame.device),
+                         torch.empty((world, per) + rest, dtype=frame.dtype, device=frame.device))
+    send, recv = _staging[key]
     mine = frame[rank::world]
-    send = torch.zeros((per,) + tuple(frame.shape[1:]), dtype=frame.dtype, device=frame.device)
-    send[: mine.shape[0]] = mine
-    recv = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(recv, send, group=group)
-    for r in range(world):
-        n = frame[r::world].shape[0]
-        frame[r::world] = recv[r][:n]
+    send[: mine.shape[0]].copy_(mine)
+    dist.all_gather_into_tensor(recv.view((world * per,) + rest), send, group=group)   # concatenated along dim 0 (nccl and gloo)
+    full = H // world                       # rows every rank owns
+    if full:
+        frame[: full * world].view((full, world) + rest).copy_(recv[:, :full].transpose(0, 1))
+    for r in range(H - full * world):       # ragged tail: ranks r < H mod world own one more row
+        frame[full * world + r].copy_(recv[r, full])
     return frame
 
 

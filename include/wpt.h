@@ -30,6 +30,9 @@ typedef struct wpt_ctx wpt_ctx;
 enum { WPT_NO_NEE = 0, WPT_NORMAL_NEE = 1, WPT_PNEE = 2 };
 /* Scene ids, wasm_interface.rs:389-398 / PanelScenes.elm:39-43 */
 enum { WPT_SCENE_MUSEUM = 0, WPT_SCENE_BUNNY = 2 };
+/* Extension, not a reference scene id (the reference panics on it): the commented-out Whitted scene of
+ * scenes.rs:113-130 — textured Square floor (if texture 0 is loaded), refracting + reflecting Sphere. DESIGN.md 9. */
+enum { WPT_SCENE_EXT_WHITTED = 256 };
 
 /* ------------------------------------------------------------------ 1. global instance
  * (reference: `static mut CONFIG`, wasm_interface.rs:37-62) */

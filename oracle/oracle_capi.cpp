@@ -24,6 +24,10 @@ int orc_update_scene(void* s, uint32_t id) { ORC_TRY ((Session*)s)->update_scene
 int orc_update_settings(void* s, uint32_t lt, uint32_t rt, uint32_t la, uint32_t ra, uint32_t dbg) { ORC_TRY ((Session*)s)->update_settings(lt, rt, la, ra, dbg); return 0; ORC_CATCH(-1) }
 int orc_update_viewport(void* s, uint32_t w, uint32_t h) { ORC_TRY ((Session*)s)->update_viewport(w, h); return 0; ORC_CATCH(-1) }
 int orc_update_camera(void* s, float x, float y, float z, float rx, float ry) { ORC_TRY ((Session*)s)->update_camera(x, y, z, rx, ry); return 0; ORC_CATCH(-1) }
+// allocate_texture + the client's copy in one call (wasm_interface.rs:335-352, worker.ts:182-190): packed RGB8, row-major
+int orc_store_texture(void* s, uint32_t id, uint32_t w, uint32_t h, const uint8_t* rgb) {
+  ORC_TRY Session* S = (Session*)s; S->textures[id].assign(rgb, rgb + (size_t)w * h * 3); S->tex_size[id] = std::make_pair(w, h); return 0; ORC_CATCH(-1)
+}
 int orc_allocate_mesh(void* s, uint32_t id, uint32_t nv) { ORC_TRY ((Session*)s)->allocate_mesh(id, nv); return 0; ORC_CATCH(-1) }
 float* orc_mesh_vertices(void* s, uint32_t id) { ORC_TRY return ((Session*)s)->mesh_vertices(id); ORC_CATCH(nullptr) }
 int orc_notify_mesh_loaded(void* s, uint32_t id) { ORC_TRY return ((Session*)s)->notify_mesh_loaded(id) ? 1 : 0; ORC_CATCH(-1) }
@@ -207,6 +211,7 @@ uint32_t orc_rng_range(uint32_t seed, uint32_t n, uint32_t lo, uint32_t hi, uint
 uint32_t orc_stream_seed(uint32_t index, uint32_t sample, uint32_t stream, uint32_t base) { return stream_seed(index, sample, stream, base); }
 uint32_t orc_museum_colors(int32_t* order27) { std::vector<int> o; uint32_t st; museum_shapes(&o, &st); for (size_t i = 0; i < o.size() && i < 27; i++) order27[i] = o[i]; return st; }
 void orc_shared_sincos(const float* a, uint32_t n, float* s, float* c) { for (uint32_t i = 0; i < n; i++) shared_sincos(a[i], &s[i], &c[i]); }
+void orc_shared_exp_neg(const float* x, uint32_t n, float* out) { for (uint32_t i = 0; i < n; i++) out[i] = shared_exp_neg(x[i]); }
 void orc_hemisphere(uint32_t seed, uint32_t n, const float* normal, float* out) {
   Rng r(seed); Vec3 nn(normal[0], normal[1], normal[2]);
   for (uint32_t i = 0; i < n; i++) { Vec3 v = r.next_hemisphere(nn); out[i * 3] = v.x; out[i * 3 + 1] = v.y; out[i * 3 + 2] = v.z; }

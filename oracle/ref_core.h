@@ -181,6 +181,18 @@ static inline void shared_sincos(float a, float* s_out, float* c_out) {
   }
 }
 
+// EXTENSION: e^-x for x >= 0 from f32 + - * and exponent bits only, identical on CPU and GPU
+// (the reference keeps Vec3::exp, vec3.rs:88-92, for Beer's law but no material uses it any more).
+static inline float shared_exp_neg(float x) {
+  if (!(x < 87.0f)) return 0.0f;
+  float kf = (float)(int)(x * 1.44269504f + 0.5f);            // round(x / ln 2)
+  float r = (kf * 0.693145751953125f - x) + kf * 1.42860682030941723212e-6f;   // -(x - k ln2), Cody-Waite split
+  float p = 1.0f + r * (1.0f + r * (0.5f + r * (0.16666667f + r * (0.041666668f + r * (0.008333334f + r * 0.0013888889f)))));
+  uint32_t bits = (uint32_t)(127 - (int)kf) << 23;             // 2^-k
+  float scale; std::memcpy(&scale, &bits, 4);
+  return p * scale;
+}
+
 // ---------------------------------------------------------------- Ray
 // src/graphics/ray.rs:22-39
 struct Ray {

@@ -234,6 +234,37 @@ struct Integrator {
         else if (!has_nee || !has_diffuse_bounced) color = color + throughput * hit.mat.intensity;
         return color;
       }
+      // ---- EXTENSION (parity unpinned): specular materials. Not reachable from the reference's scenes.
+      if (hit.mat.kind == MAT_REFRACT || (hit.mat.kind == MAT_REFLECT && rng.next() < hit.mat.param)) {
+        Vec3 d = ray.dir, n = hit.normal, wi;
+        float cos_in = dot(-d, n);
+        if (hit.mat.kind == MAT_REFLECT) {
+          wi = 2.0f * cos_in * n - (-d);                        // Vec3::reflect, vec3.rs:85-87
+          throughput = throughput * hit.mat.color.to_vec3();
+        } else {
+          float n1 = hit.is_entering ? 1.0f : hit.mat.param, n2 = hit.is_entering ? hit.mat.param : 1.0f;
+          if (!hit.is_entering) {                                // Beer's law over the distance travelled inside
+            Vec3 a = hit.mat.intensity;
+            throughput = throughput * Vec3(shared_exp_neg(a.x * hit.distance), shared_exp_neg(a.y * hit.distance), shared_exp_neg(a.z * hit.distance));
+          }
+          float r0 = (n1 - n2) / (n1 + n2); r0 = r0 * r0;        // Schlick with total internal reflection
+          float cosx = cos_in; bool tir = false;
+          if (n1 > n2) { float nr = n1 / n2; float sin2 = nr * nr * (1.0f - cosx * cosx); if (sin2 > 1.0f) tir = true; else cosx = std::sqrt(1.0f - sin2); }
+          float x = 1.0f - cosx;
+          float fres = tir ? 1.0f : r0 + (1.0f - r0) * x * x * x * x * x;
+          if (rng.next() < fres) wi = 2.0f * cos_in * n - (-d);
+          else {
+            float eta = n1 / n2;
+            float k = 1.0f - eta * eta * (1.0f - cos_in * cos_in);
+            wi = normalize(eta * d + (eta * cos_in - std::sqrt(fmax_(k, 0.0f))) * n);
+          }
+        }
+        ray = Ray(hit_point + wi * EPSILON, wi);
+        has_diffuse_bounced = false;                            // a light seen through a specular bounce is not covered by NEE
+        float keep = fmax_(fmin_(fmax_(fmax_(throughput.x, throughput.y), throughput.z), 0.9f), 0.1f);
+        if (rng.next() < keep) { throughput = throughput * (1.0f / keep); continue; }
+        return color;
+      }
       Vec3 wi; float pdf;
       sample_hemisphere(rng, hit.normal, trig, &wi, &pdf);
       Color3 brdf = hit.mat.color / PI_F;                       // material.rs:120-126
@@ -287,7 +318,7 @@ struct Integrator {
     st.photons_shot++;
     if (some) {
       Vec3 hp = ray.at(hit.distance) + hit.normal * EPSILON;
-      if (!hit.mat.emissive) {
+      if (hit.mat.is_diffuse()) {
         *light_out = light_id; *loc = hp;
         *w = dot(ln, light_normal) * fmax_(fmax_(intensity.x, intensity.y), intensity.z);
         st.photons_stored++;

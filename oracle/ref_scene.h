@@ -266,6 +266,20 @@ static inline std::vector<Shape> bunny_shapes(const std::vector<Shape>* mesh_tri
   return shapes;
 }
 // wasm_interface.rs:297-313 — Preload vertices (9 floats per triangle) -> Triangled
+// EXTENSION scene (id 256): the commented-out "Turner Whitted" scene of scenes.rs:113-130 — textured
+// Square floor (only if texture 0 is loaded, like `if let Some(t) = textures.get(&0)`), a refracting and a reflecting
+// sphere on a sky-blue background — lit by an emissive quad instead of the removed point light.
+static inline std::vector<Shape> whitted_shapes(const Texture* tex0) {
+  std::vector<Shape> shapes;
+  if (tex0) shapes.push_back(Shape::square(Vec3(0.0f, -1.0f, 4.0f), 8.0f, Material::diffuse_texture(tex0)));
+  shapes.push_back(Shape::sphere(Vec3(-1.3f, 1.0f, -0.2f), 0.7f, Material::refract(Vec3(0.5f, 1.0f, 0.5f), 1.02f)));
+  shapes.push_back(Shape::sphere(Vec3(-0.4f, 0.0f, 1.0f), 0.6f, Material::reflect(Color3(1.0f, 1.0f, 1.0f), 0.3f)));
+  Vec3 lc1(-1.0f, 6.0f, -3.0f), lc2(1.0f, 6.0f, -3.0f), lc3(1.0f, 6.0f, -1.0f), lc4(-1.0f, 6.0f, -1.0f);
+  shapes.push_back(Shape::triangle(lc3, lc2, lc1, Material::emit(Vec3(16.0f, 16.0f, 16.0f))));
+  shapes.push_back(Shape::triangle(lc4, lc3, lc1, Material::emit(Vec3(16.0f, 16.0f, 16.0f))));
+  return shapes;
+}
+
 static inline std::vector<Shape> mesh_to_triangles(const float* verts, size_t num_vertices) {
   std::vector<Shape> tris;
   size_t nt = num_vertices / 3;

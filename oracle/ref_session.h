@@ -22,7 +22,9 @@ struct Session {
   // ## global state (wasm_interface.rs:38-42)
   std::map<uint32_t, std::vector<float>> mesh_preload;   // Mesh::Preload
   std::map<uint32_t, std::vector<Shape>> mesh_tris;      // Mesh::Triangled
-  std::map<uint32_t, std::vector<uint8_t>> textures;     // stored, never sampled (F5)
+  std::map<uint32_t, std::vector<uint8_t>> textures;     // stored, never sampled (F5) — except by the extension scene 256
+  std::map<uint32_t, std::pair<uint32_t, uint32_t>> tex_size;
+  std::unique_ptr<Texture> ext_tex0;
   Rng rng;
   // ## session state
   size_t W, H;
@@ -50,6 +52,11 @@ struct Session {
     else if (id == 2) {
       auto it = mesh_tris.find(1);   // MESH_BUNNY_HIGH, scenes.rs:12
       s->build(Color3(0, 0, 0), bunny_shapes(it == mesh_tris.end() ? nullptr : &it->second), use_bvh4);
+    } else if (id == 256) {   // EXTENSION scene
+      auto it = textures.find(0);
+      ext_tex0.reset();
+      if (it != textures.end()) { ext_tex0.reset(new Texture()); ext_tex0->width = tex_size[0].first; ext_tex0->height = tex_size[0].second; ext_tex0->data.assign(it->second.begin(), it->second.begin() + (size_t)ext_tex0->width * ext_tex0->height * 3); }
+      s->build(Color3(135.0f / 255.0f, 206.0f / 255.0f, 250.0f / 255.0f), whitted_shapes(ext_tex0.get()), use_bvh4);
     } else throw std::runtime_error("Invalid scene");
     return s;
   }

@@ -10,12 +10,37 @@ namespace ref {
 
 // ---------------------------------------------------------------- Material
 // material.rs:16-20 — only Diffuse and Emissive exist at this commit (finding F5)
+// EXTENSION (parity unpinned): Reflect / Refract / textured diffuse are named by the
+// task but were removed from the reference (only the commented-out Whitted scene, scenes.rs:113-130,
+// and the helpers Vec3::reflect / Vec3::exp / Hit::is_entering are left). Their semantics here are ours.
+struct Texture {   // texture.rs:9-31
+  std::vector<uint8_t> data; uint32_t width = 0, height = 0;
+  static uint32_t as_u32(float v) { if (!(v > 0.0f)) return 0u; if (v >= 4294967296.0f) return 0xFFFFFFFFu; return (uint32_t)v; }   // Rust `as u32` saturates
+  Color3 at(float u, float v) const {
+    uint32_t ix = ((as_u32(std::floor(u * (float)width)) % width) + width) % width;
+    uint32_t iy = ((as_u32(std::floor(v * (float)height)) % height) + height) % height;
+    const uint8_t* t = &data[(size_t)(iy * width + ix) * 3];
+    return Color3((float)t[0] / 255.0f, (float)t[1] / 255.0f, (float)t[2] / 255.0f);
+  }
+};
+enum MatKind : int { MAT_DIFFUSE = 0, MAT_EMISSIVE = 1, MAT_REFLECT = 2, MAT_REFRACT = 3, MAT_DIFFUSE_TEX = 4 };
 struct Material {
   bool emissive;
-  Color3 color;      // Diffuse
-  Vec3 intensity;    // Emissive
-  static Material diffuse(Color3 c) { Material m; m.emissive = false; m.color = c; return m; }
-  static Material emit(Vec3 i) { Material m; m.emissive = true; m.intensity = i; return m; }
+  Color3 color;      // Diffuse / Reflect
+  Vec3 intensity;    // Emissive; Refract: absorption
+  int kind = MAT_DIFFUSE;
+  float param = 0.0f;               // Reflect: reflection share; Refract: index of refraction
+  const Texture* tex = nullptr;     // textured diffuse
+  static Material diffuse(Color3 c) { Material m; m.emissive = false; m.color = c; m.kind = MAT_DIFFUSE; return m; }
+  static Material emit(Vec3 i) { Material m; m.emissive = true; m.intensity = i; m.kind = MAT_EMISSIVE; return m; }
+  static Material reflect(Color3 c, float reflection) { Material m = diffuse(c); m.kind = MAT_REFLECT; m.param = reflection; return m; }
+  static Material refract(Vec3 absorption, float ior) { Material m = diffuse(Color3(1, 1, 1)); m.kind = MAT_REFRACT; m.intensity = absorption; m.param = ior; return m; }
+  static Material diffuse_texture(const Texture* t) { Material m = diffuse(Color3(1, 1, 1)); m.kind = MAT_DIFFUSE_TEX; m.tex = t; return m; }
+  bool is_diffuse() const { return kind == MAT_DIFFUSE || kind == MAT_DIFFUSE_TEX; }
+  Material evaluate_at(float u, float v) const {   // material.rs:63-70 with the removed texture variant restored
+    if (kind != MAT_DIFFUSE_TEX) return *this;
+    Material m = diffuse(tex->at(u, v)); return m;
+  }
 };
 
 // ray.rs:46-63 — Hit::new normalises the normal (again)
@@ -170,14 +195,14 @@ static inline Roots roots_quartic(double a4, double a3, double a2, double a1, do
 
 // ---------------------------------------------------------------- Shape
 // The reference uses Rc<dyn Tracable>; a tagged struct is the same thing flattened.
-enum ShapeType : int { SH_TRIANGLE = 0, SH_PLANE = 1, SH_TORUS = 2, SH_AARECT = 3 };
+enum ShapeType : int { SH_TRIANGLE = 0, SH_PLANE = 1, SH_TORUS = 2, SH_AARECT = 3, SH_SPHERE = 4, SH_SQUARE = 5 };
 
 struct Shape {
   ShapeType type;
   Material mat;
   Vec3 v0, v1, v2;          // triangle
   Vec3 location, normal;    // plane (location, normal) / torus (location)
-  float big_r, small_r;     // torus
+  float big_r, small_r;     // torus; sphere: big_r = radius; square: big_r = size
   float x_min, x_max, y_min, y_max, z_min, z_max;   // aa_rect (note: min/max interleaved, aa_rect.rs:8-16)
   int source_index = -1;    // position in the scene's original shape list (debug / tests)
 
@@ -192,6 +217,13 @@ struct Shape {
   }
   static Shape aarect(float x0, float x1, float y0, float y1, float z0, float z1, Material m) {
     Shape s{}; s.type = SH_AARECT; s.x_min = x0; s.x_max = x1; s.y_min = y0; s.y_max = y1; s.z_min = z0; s.z_max = z1; s.mat = m; return s;
+  }
+
+  static Shape sphere(Vec3 loc, float radius, Material m) {   // sphere.rs:17-22
+    Shape s{}; s.type = SH_SPHERE; s.location = loc; s.big_r = radius; s.mat = m; return s;
+  }
+  static Shape square(Vec3 loc, float size, Material m) {     // square.rs:17-22
+    Shape s{}; s.type = SH_SQUARE; s.location = loc; s.big_r = size; s.mat = m; return s;
   }
 
   bool is_emissive() const { return mat.emissive; }
@@ -214,6 +246,16 @@ struct Shape {
       case SH_AARECT:       // aa_rect.rs:57-67
         *out = AABB(x_min, y_min, z_min, x_max, y_max, z_max);
         return true;
+      case SH_SPHERE: {     // sphere.rs:31-36
+        float r = big_r;
+        *out = AABB(location.x - r, location.y - r, location.z - r, location.x + r, location.y + r, location.z + r);
+        return true;
+      }
+      case SH_SQUARE: {     // square.rs:31-44 (flat box)
+        float hs = big_r * 0.5f;
+        *out = AABB(location.x - hs, location.y, location.z - hs, location.x + hs, location.y, location.z + hs);
+        return true;
+      }
       default: return false;
     }
   }
@@ -221,7 +263,7 @@ struct Shape {
   bool centroid(Vec3* out) const {
     switch (type) {
       case SH_TRIANGLE: { AABB b; aabb(&b); *out = b.center(); return true; }
-      case SH_TORUS: *out = location; return true;
+      case SH_TORUS: case SH_SPHERE: case SH_SQUARE: *out = location; return true;   // torus.rs:28-30, sphere.rs:26-28, square.rs:26-28
       case SH_AARECT: *out = Vec3(0.5f * (x_min + x_max), 0.5f * (y_min + y_max), 0.5f * (z_min + z_max)); return true;
       default: return false;
     }
@@ -289,14 +331,41 @@ struct Shape {
         if (tmax > 0.0f) { *t_out = tmax; return true; }
         return false;
       }
-      case SH_TORUS: {      // ray.rs:110-116 default: trace().distance
+      case SH_TORUS: case SH_SQUARE: {   // ray.rs:110-116 default: trace().distance
         Hit h;
         if (!trace(ray, &h)) return false;
         *t_out = h.distance;
         return true;
       }
+      case SH_SPHERE: {     // sphere.rs:104-131
+        float t;
+        if (!sphere_t(ray, &t, nullptr)) return false;
+        *t_out = t;
+        return true;
+      }
     }
     return false;
+  }
+  // sphere.rs:55-82 / 106-128: algebraic solution with a = 1
+  bool sphere_t(const Ray& ray, float* t_out, bool* entering) const {
+    float a = 1.0f;
+    float b = 2.0f * dot(ray.dir, ray.origin - location);
+    float c = dot(ray.origin - location, ray.origin - location) - big_r * big_r;
+    float d = b * b - 4.0f * a * c;
+    if (d < 0.0f) return false;
+    float d_sqrt = std::sqrt(d);
+    float t0 = (-b + d_sqrt) / (2.0f * a);
+    float t1 = (-b - d_sqrt) / (2.0f * a);
+    float t = fmin_(t0, t1);
+    bool ent = true;
+    if (t <= 0.0f) {
+      t = fmax_(t0, t1);
+      if (t <= 0.0f) return false;
+      ent = false;
+    }
+    *t_out = t;
+    if (entering) *entering = ent;
+    return true;
   }
 
   // Tracable::trace
@@ -385,6 +454,27 @@ struct Shape {
         Vec3 n = unit((float)(alpha * px), (float)py, (float)(alpha * pz));
         if (np % 2 == 1) *out = Hit((float)closest, -n, mat, false);
         else *out = Hit((float)closest, n, mat, true);
+        return true;
+      }
+      case SH_SPHERE: {     // sphere.rs:49-101 (textured spheres are not supported: atan2 / asin are libm-dependent)
+        float t; bool ent;
+        if (!sphere_t(ray, &t, &ent)) return false;
+        Vec3 nrm = (ray.at(t) - location) / big_r;
+        if (mat.kind == MAT_DIFFUSE_TEX) throw std::runtime_error("textured sphere not supported");
+        *out = Hit(t, ent ? nrm : -nrm, mat, ent);
+        return true;
+      }
+      case SH_SQUARE: {     // square.rs:56-99
+        float n_dot_dir = ray.dir.y;
+        if (n_dot_dir == 0.0f) return false;
+        float t = (location.y - ray.origin.y) / n_dot_dir;
+        if (t <= 0.0f) return false;
+        Vec3 hit = ray.at(t);
+        float dx = std::fabs(hit.x - location.x), dz = std::fabs(hit.z - location.z);
+        if (2.0f * dx >= big_r || 2.0f * dz >= big_r) return false;
+        Vec3 nrm = n_dot_dir > 0.0f ? Vec3(0.0f, -1.0f, 0.0f) : Vec3(0.0f, 1.0f, 0.0f);
+        float u = (hit.x - location.x) / big_r + 0.5f, v = (hit.z - location.z) / big_r + 0.5f;
+        *out = Hit(t, nrm, mat.evaluate_at(u, v), true);
         return true;
       }
     }

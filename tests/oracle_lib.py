@@ -16,6 +16,8 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
 
 SCENE_MUSEUM, SCENE_BUNNY = 0, 2
+SCENE_EXT_WHITTED = 256                         # extension scene
+CAM_WHITTED = (0.0, 2.5, -6.0, 0.35, 0.0)
 NO_NEE, NORMAL_NEE, PNEE = 0, 1, 2
 TRIG_LIBM, TRIG_SHARED = 0, 1
 CAM_MUSEUM = (0.0, 16.34, -23.76, 0.54, 0.0)    # src_ts/client/index.ts:156
@@ -98,6 +100,11 @@ class Oracle:
     def reset(self): self._chk(self.L.orc_reset(self.h))
     def rebuild_bvh(self, bvh4): self._chk(self.L.orc_rebuild_bvh(self.h, int(bvh4)))
     def set_trig_a(self, trig): self.L.orc_set_trig_a(self.h, trig)
+
+    def store_texture(self, tex_id, rgb):
+        """rgb: uint8 array (h, w, 3) (worker.ts:182-190)."""
+        t = np.ascontiguousarray(rgb, dtype=np.uint8)
+        self._chk(self.L.orc_store_texture(self.h, tex_id, t.shape[1], t.shape[0], t.ctypes.data_as(C.POINTER(C.c_uint8))))
 
     def load_mesh(self, mesh_id, verts):
         """verts: float32 array (num_vertices, 3), 3 vertices per triangle (worker.ts:171-179)."""
@@ -238,6 +245,11 @@ def museum_colors():
 def shared_sincos(a):
     a = np.ascontiguousarray(a, np.float32); s = np.empty_like(a); c = np.empty_like(a)
     lib().orc_shared_sincos(_p(a, C.c_float), a.size, _p(s, C.c_float), _p(c, C.c_float)); return s, c
+
+
+def shared_exp_neg(x):
+    x = np.ascontiguousarray(x, np.float32); out = np.empty_like(x)
+    lib().orc_shared_exp_neg(_p(x, C.c_float), x.size, _p(out, C.c_float)); return out
 
 
 def hemisphere(seed, n, normal):

@@ -1,0 +1,78 @@
+"""Extension of DESIGN.md 9: Sphere / Square primitives and Texture::at follow the reference's
+sources (sphere.rs, square.rs, texture.rs — present but unreachable there); Reflect / Refract (Fresnel, Beer's law)
+were removed from the reference, so their semantics are this repo's: parity UNPINNED, GPU vs oracle still bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import wasm_pathtracer_b200 as W
+
+
+def checker():   # CHECKER_RED_YELLOW, src_ts/shared/graphics/texture.ts:17-36
+    t = np.zeros((16, 16, 3), np.uint8)
+    for y in range(16):
+        for x in range(16):
+            t[y, x] = (255, 0, 0) if x % 2 == y % 2 else (255, 255, 0)
+    return t
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def test_extension_scene_host_logic(built):
+    """Scene contents and BVH order of the extension scene: host builder == oracle (no GPU needed)."""
+    pt = W.PathTracer(32, 32, W.SCENE_BUNNY, *W.CAM_WHITTED, device=W.DEVICE_NONE)
+    with pytest.raises(W.WptError):
+        pt.update_scene(1)                       # still not a scene: the reference panics on it
+    pt.update_scene(W.SCENE_EXT_WHITTED)         # no texture loaded: no floor (scenes.rs:118-120)
+    assert pt.scene_info()["num_shapes"] == 4 and pt.scene_info()["num_lights"] == 2
+    pt.store_texture(0, checker())
+    pt.update_scene(W.SCENE_EXT_WHITTED)
+    info = pt.scene_info()
+    assert info["num_shapes"] == 5 and info["num_inf"] == 0 and info["num_lights"] == 2
+    orc = O.Oracle(32, 32, O.SCENE_BUNNY, O.CAM_WHITTED)
+    orc.store_texture(0, checker()); orc.update_scene(O.SCENE_EXT_WHITTED)
+    src, typ = pt.shape_order()
+    osrc, otyp = orc.shape_order()
+    assert np.array_equal(src, osrc) and np.array_equal(typ, otyp)
+    b, lf, cnt = pt.bvh2()
+    ob, olf, ocnt = orc.bvh2()
+    assert np.array_equal(bits(b), bits(ob)) and np.array_equal(lf, olf) and np.array_equal(cnt, ocnt)
+
+
+def test_shared_exp_is_close_to_exp(built):
+    """Beer's law uses a shared e^-x built from f32 + - * (bit-identical on CPU and GPU); it must still be exp."""
+    xs = np.concatenate([np.linspace(0, 20, 2001), [0.0, 1e-7, 86.9, 87.0, 200.0]]).astype(np.float32)
+    got = O.shared_exp_neg(xs)
+    want = np.exp(-xs.astype(np.float64))
+    ok = xs < 87.0
+    assert np.allclose(got[ok], want[ok], rtol=3e-6, atol=1e-38) and (got[~ok] == 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rtype", [W.NO_NEE, W.NORMAL_NEE, W.PNEE])
+def test_extension_scene_gpu_matches_oracle(gpu_ok, rtype):
+    w, h = 96, 64
+    pt = W.PathTracer(w, h, W.SCENE_BUNNY, *W.CAM_WHITTED, device=0)
+    orc = O.Oracle(w, h, O.SCENE_BUNNY, O.CAM_WHITTED)
+    pt.store_texture(0, checker()); orc.store_texture(0, checker())
+    pt.update_scene(W.SCENE_EXT_WHITTED); orc.update_scene(O.SCENE_EXT_WHITTED)
+    pt.set_config(render_type=rtype, photon_target=20000); orc.mb_config(type=rtype, photon_target=20000)
+    ids, vis, dist = pt.primary_probe()
+    oids, ovis, odist = orc.mb_primary_probe()
+    assert np.array_equal(ids, oids) and np.array_equal(vis, ovis) and np.array_equal(bits(dist), bits(odist))
+    pt.render_exact(24); orc.mb_render_exact(24, threads=4)
+    rgb, cnt = pt.accum(); orgb, ocnt = orc.accum()
+    assert np.array_equal(cnt, ocnt)
+    assert np.array_equal(bits(rgb), bits(orgb))
+    st, ost = pt.stats(), orc.stats(0)
+    assert (st["rays"], st["node_visits"], st["paths"]) == (ost["rays"], ost["node_visits"], ost["paths"])
+    assert np.array_equal(pt.results(0), orc.results(0))
+    # the scene really exercises the new code: floor texels, sky, and both spheres are visible
+    img = pt.results(0).reshape(h, w, 4)
+    assert (ids >= 0).sum() > 500 and len(np.unique(img.reshape(-1, 4), axis=0)) > 50
+    for engine in (1, 2):
+        pt.reset(); pt.set_config(engine=engine); pt.render_exact(24)
+        assert np.array_equal(bits(pt.accum()[0]), bits(rgb)), engine
+    pt.close()

@@ -12,8 +12,8 @@ The product is `libwpt.so` (hand-written sm_100a CUDA + C++ host code, C ABI dec
 There is no CPU rendering path: `PathTracer` raises if the library or a CUDA device is missing.
 """
 from .api import (PathTracer, WptError, WptConfig, load_library, library_path, parse_obj,
-                  NO_NEE, NORMAL_NEE, PNEE, SCENE_MUSEUM, SCENE_BUNNY, CAM_MUSEUM, CAM_BUNNY, DEVICE_NONE)
+                  NO_NEE, NORMAL_NEE, PNEE, SCENE_MUSEUM, SCENE_BUNNY, SCENE_EXT_WHITTED, CAM_MUSEUM, CAM_BUNNY, CAM_WHITTED, DEVICE_NONE)
 from .build import build_library
 
 __all__ = ["PathTracer", "WptError", "WptConfig", "load_library", "library_path", "parse_obj", "build_library",
-           "NO_NEE", "NORMAL_NEE", "PNEE", "SCENE_MUSEUM", "SCENE_BUNNY", "CAM_MUSEUM", "CAM_BUNNY", "DEVICE_NONE"]
+           "NO_NEE", "NORMAL_NEE", "PNEE", "SCENE_MUSEUM", "SCENE_BUNNY", "SCENE_EXT_WHITTED", "CAM_MUSEUM", "CAM_BUNNY", "CAM_WHITTED", "DEVICE_NONE"]

@@ -12,6 +12,8 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 NO_NEE, NORMAL_NEE, PNEE = 0, 1, 2            # wasm_interface.rs:207-214
 SCENE_MUSEUM, SCENE_BUNNY = 0, 2              # wasm_interface.rs:389-398
+SCENE_EXT_WHITTED = 256                       # extension scene: not a reference id
+CAM_WHITTED = (0.0, 2.5, -6.0, 0.35, 0.0)
 CAM_MUSEUM = (0.0, 16.34, -23.76, 0.54, 0.0)  # src_ts/client/index.ts:156
 CAM_BUNNY = (-0.9, 5.4, 0.4, 0.58, 0.0)       # src_ts/client/index.ts:158
 DEVICE_NONE = -2
@@ -209,6 +211,12 @@ class PathTracer:
 
     def notify_texture_loaded(self, tex_id):
         return self._chk(self.L.wpt_ctx_notify_texture_loaded(self.h, tex_id)) == 1
+
+    def store_texture(self, tex_id, rgb):
+        """The worker's texture upload (src_ts/worker/worker.ts:182-190): rgb = uint8 array (height, width, 3)."""
+        t = np.ascontiguousarray(rgb, np.uint8)
+        self.allocate_texture(tex_id, t.shape[1], t.shape[0])[:] = t
+        return self.notify_texture_loaded(tex_id)
 
     def compute(self, num_samples):
         self._chk(self.L.wpt_ctx_compute(self.h, num_samples))

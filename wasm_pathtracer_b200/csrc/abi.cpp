@@ -114,7 +114,7 @@ int wpt_ctx_notify_mesh_loaded(wpt_ctx* ctx, uint32_t id) {   // wasm_interface.
 }
 uint8_t* wpt_ctx_allocate_texture(wpt_ctx* ctx, uint32_t id, uint32_t w, uint32_t h) {   // wasm_interface.rs:335-352
   uint8_t* p = nullptr;
-  guard([&] { Context* c = C(ctx); c->textures[id].assign((size_t)w * h * 3 + 1, 0); p = c->textures[id].data(); });
+  guard([&] { Context* c = C(ctx); c->textures[id].assign((size_t)w * h * 3 + 1, 0); c->tex_dims[id] = std::make_pair(w, h); p = c->textures[id].data(); });
   return p;
 }
 int wpt_ctx_notify_texture_loaded(wpt_ctx* ctx, uint32_t) {   // wasm_interface.rs:357-366: stub, always false

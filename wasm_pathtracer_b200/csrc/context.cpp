@@ -93,13 +93,18 @@ void Context::reset() {   // wasm_interface.rs:137-148
 
 void Context::select_scene(uint32_t id) {
   std::vector<HostShape> shapes; std::vector<HostMaterial> mats;
+  float bg[3] = {0.0f, 0.0f, 0.0f};   // Color3::BLACK for both reference scenes (scenes.rs:51,110)
   if (id == WPT_SCENE_MUSEUM) scene_museum(shapes, mats);
   else if (id == WPT_SCENE_BUNNY) {
     auto it = mesh_tris.find(1);   // MESH_BUNNY_HIGH, scenes.rs:12
     scene_bunny(it == mesh_tris.end() ? nullptr : &it->second, shapes, mats);
+  } else if (id == WPT_SCENE_EXT_WHITTED) {   // extension: not a reference scene id
+    auto it = textures.find(0);
+    scene_whitted(it != textures.end(), shapes, mats, bg);
   } else throw std::runtime_error("Invalid scene");
   HostScene ns;
   build_scene(ns, std::move(shapes), std::move(mats), cfg.bvh_kind);
+  ns.bg[0] = bg[0]; ns.bg[1] = bg[1]; ns.bg[2] = bg[2];
   if (ns.depth2 + 2 > 64 || ns.depth4 * 3 + 4 > 64) throw std::runtime_error("BVH too deep for the device traversal stack");
   scene = std::move(ns);
   scene_id = id;
@@ -122,6 +127,17 @@ void Context::upload_scene() {
   h_scene_bytes = total;
   for (int i = 0; i < 5; i++) if (len[i]) std::memcpy((char*)h_scene_blob + blob_off[i], src[i], len[i]);
   d_nodes2.alloc(n2.size()); d_nodes4.alloc(n4.size()); d_shapes.alloc(shp.size()); d_mats.alloc(mats.size()); d_lights.alloc(lights.size());
+  for (uint32_t t = 0; t < WPT_MAX_TEXTURES; t++) {   // textures referenced by textured-diffuse materials (extension scene only)
+    d_tex_w[t] = d_tex_h[t] = 0;
+    auto it = textures.find(t); auto dm = tex_dims.find(t);
+    if (it == textures.end() || dm == tex_dims.end() || !dm->second.first || !dm->second.second) continue;
+    size_t bytes = (size_t)dm->second.first * dm->second.second * 3;
+    d_tex[t].alloc(bytes);
+    WPT_CUDA(cudaMemcpyAsync(d_tex[t].p, it->second.data(), bytes, cudaMemcpyHostToDevice, stream));
+    d_tex_w[t] = dm->second.first; d_tex_h[t] = dm->second.second;
+  }
+  for (const HostMaterial& m : scene.mats)
+    if (m.kind == MAT_DIFFUSE_TEX && (m.tex >= WPT_MAX_TEXTURES || !d_tex_w[m.tex])) throw std::runtime_error("textured material without a loaded texture");
   reupload_scene();
   WPT_CUDA(cudaStreamSynchronize(stream));
 }
@@ -181,6 +197,7 @@ RenderParams Context::params(uint32_t render_type) const {
   rp.scene.num_inf = scene.num_inf; rp.scene.num_shapes = (uint32_t)scene.shapes.size(); rp.scene.num_lights = (uint32_t)scene.lights.size();
   rp.scene.bvh_kind = scene.bvh_kind;
   rp.scene.bg_r = scene.bg[0]; rp.scene.bg_g = scene.bg[1]; rp.scene.bg_b = scene.bg[2];
+  for (uint32_t t = 0; t < WPT_MAX_TEXTURES; t++) { rp.scene.tex[t].rgb = d_tex[t].p; rp.scene.tex[t].width = d_tex_w[t]; rp.scene.tex[t].height = d_tex_h[t]; }
   rp.cam.ox = cam[0]; rp.cam.oy = cam[1]; rp.cam.oz = cam[2];
   // sin/cos of the camera angles are evaluated once on the host (vec3.rs:103-104,116-117)
   rp.cam.cx = std::cos(cam[3]); rp.cam.sx = std::sin(cam[3]); rp.cam.cy = std::cos(cam[4]); rp.cam.sy = std::sin(cam[4]);
@@ -312,6 +329,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   P.chunk = (uint32_t)env_chunk;
   P.simple_scene = 1;
   for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { P.simple_scene = 0; break; }
+  for (const HostMaterial& m : scene.mats) if (m.kind != MAT_DIFFUSE && m.kind != MAT_EMISSIVE) { P.simple_scene = 0; break; }
   if (std::getenv("WPT_NO_SIMPLE")) P.simple_scene = 0;
   if (cfg.engine == 2) {   // block-pool kernel: refill threshold of the traversal warps, slots and blocks per SM
     static const int p_tlo = std::getenv("WPT_POOL_TLO") ? std::atoi(std::getenv("WPT_POOL_TLO")) : 20;

@@ -54,6 +54,8 @@ struct Context {
   std::map<uint32_t, std::vector<float>> mesh_preload;
   std::map<uint32_t, std::vector<HostShape>> mesh_tris;
   std::map<uint32_t, std::vector<uint8_t>> textures;
+  std::map<uint32_t, std::pair<uint32_t, uint32_t>> tex_dims;   // width, height per texture id
+  DevBuf<uint8_t> d_tex[WPT_MAX_TEXTURES]; uint32_t d_tex_w[WPT_MAX_TEXTURES] = {0, 0, 0, 0}, d_tex_h[WPT_MAX_TEXTURES] = {0, 0, 0, 0};   // extension scene
 
   HostScene scene;
   DevBuf<DNode2> d_nodes2;

@@ -74,6 +74,15 @@ WPT_DEV void shared_sincos(float a, float* s_out, float* c_out) {
   }
 }
 
+// EXTENSION: e^-x for x >= 0 from f32 + - * and exponent bits only (same code as the oracle's)
+WPT_DEV float shared_exp_neg(float x) {
+  if (!(x < 87.0f)) return 0.0f;
+  float kf = (float)(int)(x * 1.44269504f + 0.5f);
+  float r = (kf * 0.693145751953125f - x) + kf * 1.42860682030941723212e-6f;
+  float p = 1.0f + r * (1.0f + r * (0.5f + r * (0.16666667f + r * (0.041666668f + r * (0.008333334f + r * 0.0013888889f)))));
+  return p * __uint_as_float((uint32_t)(127 - (int)kf) << 23);
+}
+
 // ------------------------------------------------------------------ boxes (aabb.rs)
 // AABB::hit, aabb.rs:132-164. Box = (a.x,a.y,a.z)-(a.w,b.x,b.y).
 WPT_DEV bool box_hit(float x0, float y0, float z0, float x1, float y1, float z1, const Ray& r, float* t) {
@@ -229,7 +238,7 @@ __device__ __noinline__ void d_quartic(double a4, double a3, double a2, double a
 
 // ------------------------------------------------------------------ primitives
 // Torus::trace, torus.rs:61-126. Returns hit distance (f32) and outward-or-flipped normal.
-__device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray& ray, float* t_out, F3* n_out) {
+__device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray& ray, float* t_out, F3* n_out, bool* entering_out = nullptr) {
   double a = (double)q1.x, b = (double)q1.y;
   F3 d = ray.o - xyz(q0);
   F3 e = ray.d;
@@ -254,7 +263,43 @@ __device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray& ray, f
     double alpha = 1.0 - a / sqrt(px * px + pz * pz);
     F3 n = normalize(f3((float)(alpha * px), (float)py, (float)(alpha * pz)));
     *n_out = (np % 2 == 1) ? -n : n;   // odd number of positive roots: inside (torus.rs:120-124)
+    if (entering_out) *entering_out = (np % 2 == 0);
   }
+  return true;
+}
+
+// Sphere (sphere.rs:55-82, 106-128): algebraic solution with a = 1
+WPT_DEV bool sphere_t(float4 q0, float4 q1, const Ray& ray, float* t_out, bool* entering) {
+  F3 oc = ray.o - xyz(q0);
+  float a = 1.0f;
+  float b = 2.0f * dot(ray.d, oc);
+  float c = dot(oc, oc) - q1.x * q1.x;
+  float d = b * b - 4.0f * a * c;
+  if (d < 0.0f) return false;
+  float ds = sqrtf(d);
+  float t0 = (-b + ds) / (2.0f * a);
+  float t1 = (-b - ds) / (2.0f * a);
+  float t = fminf(t0, t1);
+  bool ent = true;
+  if (t <= 0.0f) {
+    t = fmaxf(t0, t1);
+    if (t <= 0.0f) return false;
+    ent = false;
+  }
+  *t_out = t; *entering = ent;
+  return true;
+}
+// Square (square.rs:56-99): finite upward-facing plane; uv as the reference computes it for a textured material
+WPT_DEV bool square_t(float4 q0, float4 q1, const Ray& ray, float* t_out, float* u, float* v) {
+  float n_dot_dir = ray.d.y;
+  if (n_dot_dir == 0.0f) return false;
+  float t = (q0.y - ray.o.y) / n_dot_dir;
+  if (t <= 0.0f) return false;
+  F3 hit = ray.o + t * ray.d;
+  float dx = fabsf(hit.x - q0.x), dz = fabsf(hit.z - q0.z);
+  if (2.0f * dx >= q1.x || 2.0f * dz >= q1.x) return false;
+  *t_out = t;
+  *u = (hit.x - q0.x) / q1.x + 0.5f; *v = (hit.z - q0.z) / q1.x + 0.5f;
   return true;
 }
 
@@ -302,6 +347,12 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
     if (tmin > 0.0f) t = tmin;
     else if (tmax > 0.0f) t = tmax;
     else return false;
+  } else if (type == SH_SPHERE) {
+    bool ent;
+    if (!sphere_t(q0, q1, ray, &t, &ent)) return false;
+  } else if (type == SH_SQUARE) {   // ray.rs:110-116 default = trace().distance
+    float u, v;
+    if (!square_t(q0, q1, ray, &t, &u, &v)) return false;
   } else {                     // torus: ray.rs:110-116 default = trace().distance
     if (!torus_trace(q0, q1, ray, &t, nullptr)) return false;
   }
@@ -313,13 +364,14 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
 // Tracable::trace for the winning shape (scene.rs:140): distance, Hit::new-normalised normal,
 // material index. Returns false if the full intersection reports no hit.
 template <bool SIMPLE>
-WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float* t_out, F3* n_out, uint32_t* mat_out) {
+WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float* t_out, F3* n_out, uint32_t* mat_out, bool* entering_out = nullptr, float2* uv_out = nullptr) {
   const float4* p = reinterpret_cast<const float4*>(shapes + idx);
   float4 q0 = __ldg(p), q1 = __ldg(p + 1);
   uint32_t meta = __float_as_uint(q0.w);
   uint32_t type = meta & 0xFFu;
   *mat_out = meta >> 8;
   F3 n; float t;
+  bool entering = true;   // Hit::is_entering (only the extension's refracting material reads it)
   if (type == SH_TRIANGLE) {   // triangle.rs:116-157
     float4 q2 = __ldg(p + 2), q3 = __ldg(p + 3);
     F3 v0 = xyz(q0), v1 = xyz(q1), v2 = xyz(q2);
@@ -335,6 +387,7 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
     if (!(dot(nn, cross(v2 - v1, pt - v1)) + slack >= 0.0f)) return false;
     if (!(dot(nn, cross(v0 - v2, pt - v2)) + slack >= 0.0f)) return false;
     n = (n_dot_d > 0.0f) ? -nn : nn;
+    entering = !(n_dot_d > 0.0f);
   } else if (SIMPLE || type == SH_PLANE) {   // plane.rs:45-77
     F3 nr = xyz(q1);
     float n_dot_dir = dot(nr, ray.d);
@@ -355,16 +408,28 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
       else if (tmin == ty1) n = f3(0, -1, 0); else if (tmin == ty2) n = f3(0, 1, 0);
       else if (tmin == tz1) n = f3(0, 0, -1); else n = f3(0, 0, 1);
     } else if (tmax > 0.0f) {
-      t = tmax;
+      t = tmax; entering = false;
       if (tmax == tx1) n = f3(1, 0, 0); else if (tmax == tx2) n = f3(-1, 0, 0);
       else if (tmax == ty1) n = f3(0, 1, 0); else if (tmax == ty2) n = f3(0, -1, 0);
       else if (tmax == tz1) n = f3(0, 0, 1); else n = f3(0, 0, -1);
     } else return false;
+  } else if (type == SH_SPHERE) {   // sphere.rs:49-101
+    bool ent;
+    if (!sphere_t(q0, q1, ray, &t, &ent)) return false;
+    n = ((ray.o + t * ray.d) - xyz(q0)) / q1.x;
+    if (!ent) n = -n;
+    entering = ent;
+  } else if (type == SH_SQUARE) {   // square.rs:56-99
+    float u, v;
+    if (!square_t(q0, q1, ray, &t, &u, &v)) return false;
+    n = ray.d.y > 0.0f ? f3(0, -1, 0) : f3(0, 1, 0);
+    if (uv_out) *uv_out = make_float2(u, v);
   } else {
-    if (!torus_trace(q0, q1, ray, &t, &n)) return false;
+    if (!torus_trace(q0, q1, ray, &t, &n, &entering)) return false;
   }
   *t_out = t;
   *n_out = normalize(n);   // Hit::new, ray.rs:59-62
+  if (entering_out) *entering_out = entering;
   return true;
 }
 

@@ -59,10 +59,29 @@ static HostShape aarect(float x0, float x1, float y0, float y1, float z0, float 
   std::memcpy(s.p, v, sizeof v);
   return s;
 }
+static HostShape sphere(V3 loc, float radius, uint32_t mat) {   // sphere.rs:17-22
+  HostShape s{}; s.type = SH_SPHERE; s.mat = mat;
+  float v[9] = {loc.x, loc.y, loc.z, radius, 0, 0, 0, 0, 0};
+  std::memcpy(s.p, v, sizeof v);
+  return s;
+}
+static HostShape square(V3 loc, float size, uint32_t mat) {     // square.rs:17-22
+  HostShape s{}; s.type = SH_SQUARE; s.mat = mat;
+  float v[9] = {loc.x, loc.y, loc.z, size, 0, 0, 0, 0, 0};
+  std::memcpy(s.p, v, sizeof v);
+  return s;
+}
 static inline float clamp01(float v) { return mn(1.0f, mx(0.0f, v)); }   // Color3::new, color3.rs:32-38
 static uint32_t add_mat(std::vector<HostMaterial>& mats, float r, float g, float b, bool emissive) {
   if (!emissive) { r = clamp01(r); g = clamp01(g); b = clamp01(b); }
-  mats.push_back(HostMaterial{r, g, b, emissive});
+  HostMaterial m{}; m.r = r; m.g = g; m.b = b; m.emissive = emissive; m.kind = emissive ? MAT_EMISSIVE : MAT_DIFFUSE;
+  mats.push_back(m);
+  return (uint32_t)mats.size() - 1;
+}
+static uint32_t add_mat_ext(std::vector<HostMaterial>& mats, uint32_t kind, float r, float g, float b, float param, uint32_t tex) {
+  HostMaterial m{}; m.r = r; m.g = g; m.b = b; m.emissive = false; m.kind = kind; m.param = param; m.tex = tex;
+  if (kind == MAT_REFLECT || kind == MAT_DIFFUSE_TEX) { m.r = clamp01(r); m.g = clamp01(g); m.b = clamp01(b); }
+  mats.push_back(m);
   return (uint32_t)mats.size() - 1;
 }
 
@@ -123,6 +142,19 @@ void scene_bunny(const std::vector<HostShape>* mesh, std::vector<HostShape>& sha
   shapes.push_back(tri(lc4, lc3, lc1, light_m));
 }
 
+// Extension scene 256 — scenes.rs:113-130 with an emissive quad instead of the removed point light
+void scene_whitted(bool with_floor, std::vector<HostShape>& shapes, std::vector<HostMaterial>& mats, float bg[3]) {
+  shapes.clear(); mats.clear();
+  bg[0] = 135.0f / 255.0f; bg[1] = 206.0f / 255.0f; bg[2] = 250.0f / 255.0f;
+  if (with_floor) shapes.push_back(square(V3{0.0f, -1.0f, 4.0f}, 8.0f, add_mat_ext(mats, MAT_DIFFUSE_TEX, 1.0f, 1.0f, 1.0f, 0.0f, 0)));
+  shapes.push_back(sphere(V3{-1.3f, 1.0f, -0.2f}, 0.7f, add_mat_ext(mats, MAT_REFRACT, 0.5f, 1.0f, 0.5f, 1.02f, 0)));
+  shapes.push_back(sphere(V3{-0.4f, 0.0f, 1.0f}, 0.6f, add_mat_ext(mats, MAT_REFLECT, 1.0f, 1.0f, 1.0f, 0.3f, 0)));
+  uint32_t light_m = add_mat(mats, 16.0f, 16.0f, 16.0f, true);
+  V3 lc1{-1.0f, 6.0f, -3.0f}, lc2{1.0f, 6.0f, -3.0f}, lc3{1.0f, 6.0f, -1.0f}, lc4{-1.0f, 6.0f, -1.0f};
+  shapes.push_back(tri(lc3, lc2, lc1, light_m));
+  shapes.push_back(tri(lc4, lc3, lc1, light_m));
+}
+
 // wasm_interface.rs:297-313: v * 0.5, then translate by (0,0,5)
 std::vector<HostShape> mesh_triangles(const float* verts, size_t num_vertices, uint32_t mat) {
   size_t nt = num_vertices / 3;
@@ -158,11 +190,21 @@ static bool shape_box(const HostShape& s, Box* b) {
     case SH_AARECT:       // aa_rect.rs:57-67
       for (int c = 0; c < 3; c++) { b->lo[c] = s.p[c]; b->hi[c] = s.p[3 + c]; }
       return true;
+    case SH_SPHERE:       // sphere.rs:31-36
+      for (int c = 0; c < 3; c++) { b->lo[c] = s.p[c] - s.p[3]; b->hi[c] = s.p[c] + s.p[3]; }
+      return true;
+    case SH_SQUARE: {     // square.rs:31-44
+      float hs = s.p[3] * 0.5f;
+      b->lo[0] = s.p[0] - hs; b->hi[0] = s.p[0] + hs;
+      b->lo[1] = s.p[1]; b->hi[1] = s.p[1];
+      b->lo[2] = s.p[2] - hs; b->hi[2] = s.p[2] + hs;
+      return true;
+    }
     default: return false;
   }
 }
 static V3 shape_centroid(const HostShape& s, const Box& b) {
-  if (s.type == SH_TORUS) return V3{s.p[0], s.p[1], s.p[2]};   // torus.rs:28-30
+  if (s.type == SH_TORUS || s.type == SH_SPHERE || s.type == SH_SQUARE) return V3{s.p[0], s.p[1], s.p[2]};   // torus.rs:28-30, sphere.rs:26-28, square.rs:26-28
   // triangle: AABB centre (ray.rs:77-83); aa_rect: aa_rect.rs:48-54 — the same expression
   return V3{0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2])};
 }
@@ -502,11 +544,18 @@ void flatten_scene(const HostScene& sc, std::vector<DNode2>& n2, std::vector<DNo
         d.q0 = make_float4(s.p[0], s.p[1], s.p[2], meta);
         d.q1 = make_float4(s.p[3], s.p[4], s.p[5], 0.0f);
         break;
+      case SH_SPHERE: case SH_SQUARE:
+        d.q0 = make_float4(s.p[0], s.p[1], s.p[2], meta);
+        d.q1 = make_float4(s.p[3], 0.0f, 0.0f, 0.0f);
+        break;
     }
     shp[i] = d;
   }
   mats.resize(sc.mats.size());
-  for (size_t i = 0; i < sc.mats.size(); i++) mats[i].c = make_float4(sc.mats[i].r, sc.mats[i].g, sc.mats[i].b, sc.mats[i].emissive ? 1.0f : 0.0f);
+  for (size_t i = 0; i < sc.mats.size(); i++) {
+    mats[i].c = make_float4(sc.mats[i].r, sc.mats[i].g, sc.mats[i].b, (float)sc.mats[i].kind);
+    mats[i].p = make_float4(sc.mats[i].param, bits_f(sc.mats[i].tex), 0.0f, 0.0f);
+  }
   lights.resize(sc.lights.size());
   for (size_t i = 0; i < sc.lights.size(); i++) {
     const HostShape& s = sc.shapes[sc.lights[i]];

@@ -18,10 +18,10 @@ struct Box { float lo[3], hi[3]; };
 struct HostShape {
   ShapeType type;
   uint32_t mat;       // index into HostScene::mats
-  float p[9];         // triangle: v0,v1,v2 | plane: location, normal | torus: location, R, r | aa_rect: lo, hi
+  float p[9];         // triangle: v0,v1,v2 | plane: location, normal | torus: location, R, r | aa_rect: lo, hi | sphere: location, radius | square: location, size
   int32_t source;     // index in the scene's original shape list
 };
-struct HostMaterial { float r, g, b; bool emissive; };
+struct HostMaterial { float r, g, b; bool emissive; uint32_t kind = MAT_DIFFUSE; float param = 0.0f; uint32_t tex = 0; };
 
 struct HostBVH2Node { Box box; uint32_t left_first, count; };
 struct HostBVH4Node { Box child[4]; int32_t children[4]; uint32_t num_children; };
@@ -41,6 +41,8 @@ struct HostScene {
 // scenes.rs:15-68 / :75-111
 void scene_museum(std::vector<HostShape>& shapes, std::vector<HostMaterial>& mats);
 void scene_bunny(const std::vector<HostShape>* mesh, std::vector<HostShape>& shapes, std::vector<HostMaterial>& mats);
+// extension scene 256: the commented-out Whitted scene of scenes.rs:113-130; `with_floor` = texture 0 is loaded
+void scene_whitted(bool with_floor, std::vector<HostShape>& shapes, std::vector<HostMaterial>& mats, float bg[3]);
 // wasm_interface.rs:297-313 — `verts` = 9 floats per triangle; material slot `mat`
 std::vector<HostShape> mesh_triangles(const float* verts, size_t num_vertices, uint32_t mat);
 // scene.rs:43-69 (+ bvh.rs, bvh4.rs)

@@ -188,9 +188,10 @@ WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_h
   const bool has_nee = rp.render_type != 0;
   out.finished = false; out.survive = false; out.shadow = false;
   bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
+  bool entering = true; float2 uv = make_float2(0.0f, 0.0f);
   if (id >= 0) {   // scene.rs:140
     if (SIMPLE) { shape_hit_normal_tri_plane(rp.scene.shapes, (uint32_t)id, ray, &n, &mat); t = t_hit; some = true; }
-    else some = shape_trace_full<false>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat);
+    else some = shape_trace_full<false>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat, &entering, &uv);
   }
   if (!some) {   // tracer.rs:325-328
     ps.color = ps.color + ps.T * f3(rp.scene.bg_r, rp.scene.bg_g, rp.scene.bg_b);
@@ -199,10 +200,49 @@ WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_h
   }
   float4 mc = __ldg(&rp.scene.mats[mat].c);
   F3 hit_point = ray.o + t * ray.d;
-  if (mc.w != 0.0f) {   // emissive, tracer.rs:245-254
+  if (mc.w == (float)MAT_EMISSIVE) {   // emissive, tracer.rs:245-254
     if (rp.light_debug ? !ps.bounced : (!has_nee || !ps.bounced)) ps.color = ps.color + ps.T * xyz(mc);
     out.finished = true;
     return;
+  }
+  if (!SIMPLE && mc.w != (float)MAT_DIFFUSE) {   // ---- extension materials (parity unpinned)
+    float4 mp = __ldg(&rp.scene.mats[mat].p);
+    if (mc.w == (float)MAT_DIFFUSE_TEX) {   // Texture::at, texture.rs:23-31 (`as u32` saturates)
+      const DTexture tx = rp.scene.tex[__float_as_uint(mp.y)];
+      float fu = floorf(uv.x * (float)tx.width), fv = floorf(uv.y * (float)tx.height);
+      uint32_t iu = !(fu > 0.0f) ? 0u : (fu >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fu);
+      uint32_t iv = !(fv > 0.0f) ? 0u : (fv >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fv);
+      const uint8_t* px = tx.rgb + (size_t)((iv % tx.height) * tx.width + (iu % tx.width)) * 3;
+      mc.x = (float)px[0] / 255.0f; mc.y = (float)px[1] / 255.0f; mc.z = (float)px[2] / 255.0f;
+    } else if (mc.w == (float)MAT_REFRACT || ps.rng.f32() < mp.x) {   // specular bounce (Reflect draws its share first)
+      F3 d = ray.d, wi;
+      float cos_in = dot(-d, n);
+      if (mc.w == (float)MAT_REFLECT) {
+        wi = (2.0f * cos_in) * n - (-d);   // Vec3::reflect, vec3.rs:85-87
+        ps.T = ps.T * xyz(mc);
+      } else {
+        float n1 = entering ? 1.0f : mp.x, n2 = entering ? mp.x : 1.0f;
+        if (!entering) ps.T = ps.T * f3(shared_exp_neg(mc.x * t), shared_exp_neg(mc.y * t), shared_exp_neg(mc.z * t));   // Beer's law
+        float r0 = (n1 - n2) / (n1 + n2); r0 = r0 * r0;   // Schlick with total internal reflection
+        float cosx = cos_in; bool tir = false;
+        if (n1 > n2) { float nr = n1 / n2; float sin2 = nr * nr * (1.0f - cosx * cosx); if (sin2 > 1.0f) tir = true; else cosx = sqrtf(1.0f - sin2); }
+        float x = 1.0f - cosx;
+        float fres = tir ? 1.0f : r0 + (1.0f - r0) * x * x * x * x * x;
+        if (ps.rng.f32() < fres) wi = (2.0f * cos_in) * n - (-d);
+        else {
+          float eta = n1 / n2;
+          float k = 1.0f - eta * eta * (1.0f - cos_in * cos_in);
+          wi = normalize(eta * d + (eta * cos_in - sqrtf(fmaxf(k, 0.0f))) * n);
+        }
+      }
+      out.next_o = hit_point + wi * WPT_EPSILON;
+      out.next_d = wi;
+      ps.bounced = false;   // a light seen through a specular bounce is not covered by NEE
+      float keep = fmaxf(fminf(fmaxf(fmaxf(ps.T.x, ps.T.y), ps.T.z), 0.9f), 0.1f);
+      out.survive = ps.rng.f32() < keep;
+      if (out.survive) ps.T = ps.T * (1.0f / keep);
+      return;
+    }
   }
   // material.rs:97-118 cosine-weighted bounce
   float r1 = ps.rng.f32();
@@ -390,7 +430,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(RenderParams rp, PathSt
         else {
           ro.x = so.next_o.x; ro.y = so.next_o.y; ro.z = so.next_o.z;
           rd.x = so.next_d.x; rd.y = so.next_d.y; rd.z = so.next_d.z;
-          flags |= SL_BOUNCED;
+          if (ps.bounced) flags |= SL_BOUNCED; else flags &= ~SL_BOUNCED;   // a specular bounce (extension materials) clears it
           if (so.shadow) {
             st.sh_o[i] = make_float4(so.sh_o.x, so.sh_o.y, so.sh_o.z, so.sh_len);
             st.sh_d[i] = make_float4(so.sh_d.x, so.sh_d.y, so.sh_d.z, __int_as_float(so.sh_light));
@@ -1164,7 +1204,7 @@ __global__ void __launch_bounds__(128) k_photon_emit(RenderParams rp, unsigned l
     float t; F3 n; uint32_t mat;
     if (shape_trace_full<false>(rp.scene.shapes, (uint32_t)g.id, ray, &t, &n, &mat)) {
       float4 mc = __ldg(&rp.scene.mats[mat].c);
-      if (mc.w == 0.0f) {   // hit.mat.is_diffuse(), tracer.rs:144
+      if (mc.w == (float)MAT_DIFFUSE || mc.w == (float)MAT_DIFFUSE_TEX) {   // hit.mat.is_diffuse(), tracer.rs:144
         F3 hp = (ray.o + t * ray.d) + n * WPT_EPSILON;
         float w = dot(ln, dir) * fmaxf(fmaxf(inten.x, inten.y), inten.z);
         rec_loc_w[i] = make_float4(hp.x, hp.y, hp.z, w); rec_light[i] = light_id;   // dense: the record of shot i lives in slot i

@@ -10,7 +10,10 @@ namespace wpt {
 #define WPT_EPSILON 0.0002f
 #define WPT_PI 3.14159265358979323846f
 
-enum ShapeType : uint32_t { SH_TRIANGLE = 0, SH_PLANE = 1, SH_TORUS = 2, SH_AARECT = 3 };
+enum ShapeType : uint32_t { SH_TRIANGLE = 0, SH_PLANE = 1, SH_TORUS = 2, SH_AARECT = 3, SH_SPHERE = 4, SH_SQUARE = 5 };
+// Material kinds (DMaterial::c.w). Only DIFFUSE and EMISSIVE exist in the reference (material.rs:16-20); the others are the
+// extension of DESIGN.md 9 (named by the task, removed from the reference: parity unpinned).
+enum MatKind : uint32_t { MAT_DIFFUSE = 0, MAT_EMISSIVE = 1, MAT_REFLECT = 2, MAT_REFRACT = 3, MAT_DIFFUSE_TEX = 4 };
 
 // BVH2 node, 32 B like the reference's BVHNode (bvh.rs:14-20); siblings are adjacent so the
 // two child boxes tested at scene.rs:242-243 are one 64 B fetch.
@@ -30,10 +33,17 @@ struct DNode4 {
 //   plane   : q0=(location, meta) q1=(normal, normal.location)        (plane.rs:80-99)
 //   torus   : q0=(location, meta) q1=(big_r, small_r, 0, 0)           (torus.rs:11-16)
 //   aa_rect : q0=(x_min,y_min,z_min, meta) q1=(x_max,y_max,z_max,0)   (aa_rect.rs:8-16)
+//   sphere  : q0=(location, meta) q1=(radius, 0, 0, 0)                (sphere.rs:10-15)
+//   square  : q0=(location, meta) q1=(size, 0, 0, 0)                  (square.rs:11-16)
 struct DShape { float4 q0, q1, q2, q3; };
 
-// Material (material.rs:16-20): c = (r,g,b, emissive ? 1 : 0); r,g,b = colour or intensity
-struct DMaterial { float4 c; };
+// Material (material.rs:16-20): c = (r,g,b, kind); r,g,b = colour, intensity (emissive) or absorption (refract);
+// p.x = reflection share (reflect) / index of refraction (refract), p.y = bits(texture slot) (textured diffuse)
+struct DMaterial { float4 c; float4 p; };
+
+// Texture (texture.rs:9-13): packed RGB8, row-major
+struct DTexture { const uint8_t* rgb; uint32_t width, height; };
+#define WPT_MAX_TEXTURES 4
 
 // Area light = emissive triangle (scene.rs:62-66): shape index, Heron area (triangle.rs:70-78),
 // unit normal (triangle.rs:104) and intensity.
@@ -66,6 +76,7 @@ struct DScene {
   const DLight* lights;
   uint32_t num_inf, num_shapes, num_lights, bvh_kind;
   float bg_r, bg_g, bg_b, pad;
+  DTexture tex[WPT_MAX_TEXTURES];   // extension: textured diffuse
 };
 
 // Mode-B accumulation contract B10: render_exact sums a pixel's samples in segments of this length

@@ -277,7 +277,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (procedural stand-in mesh, 81920 triangles; reference bunny2.obj is a stripped blob)",
                 "config": {"workload": "bunny scene, stand-in mesh 81920 tris, BVH%d 16 bins, 1920x1080, %d spp per GPU (%d total), NormalNEE, diffuse+emissive, mode-B per-path streams" % (args.bvh, args.spp, spp_total),
-                           "partition": "rows interleaved over %d rank(s), NCCL all_gather of accumulators; a pixel's samples run as segments of 16 on separate lanes (contract B10)" % world,
+                           "partition": "rows interleaved over %d rank(s), NCCL all_gather of accumulators; a pixel's samples run as segments of 8 on separate lanes (contract B10)" % world,
                            "engine": "persistent path kernel (k_mega)" if args.engine == 0 else "multi-kernel wavefront (k_trace + k_shade)",
                            "l2": "flushed before every timed step: a 256 MiB buffer is overwritten on the kernel's stream (inside the timed region)"},
                 "mpaths_per_s": mpaths, "rays_per_step": rays_all, "paths_per_step": paths_all,

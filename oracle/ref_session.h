@@ -210,7 +210,7 @@ struct Session {
   // and the segment sums are added to the accumulator in order. (A single call of <= seg samples
   // on a cleared pixel gives the same bits as RenderTarget::write per sample, since 0 + c == c.)
   // Segments are what lets the GPU run the samples of ONE pixel on several lanes at once.
-  static constexpr uint32_t MB_SEGMENT = 16;
+  static constexpr uint32_t MB_SEGMENT = 8;   // measured: 8 beats 16 by 6 % on the 16-spp bench frame (gpurun_out/sweep9.log)
   void mb_samples(const Integrator& I, size_t x, size_t y, uint32_t n, uint32_t seg, Stats& st) {
     uint32_t s0 = (uint32_t)target->acc_count[y * W + x];
     for (uint32_t j = 0; j < n; j += seg) {

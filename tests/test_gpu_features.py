@@ -226,8 +226,8 @@ def test_photon_warmup_split_over_ranks_is_bit_exact(gpu_ok, meshes):
 
 
 def test_segmented_accumulation_contract_b10(gpu_ok, meshes):
-    """render_exact sums a pixel's samples in segments of 16 (each from +0, added in order), so that one pixel's
-    samples can run on several lanes: 37 + 5 samples = segments 16 | 16 | 5 then 5. The oracle follows the same
+    """render_exact sums a pixel's samples in segments of 8 (each from +0, added in order), so that one pixel's
+    samples can run on several lanes: 37 + 5 samples = segments 8 | 8 | 8 | 8 | 5 then 5. The oracle follows the same
     contract; the three engines and a two-rank partition give the same bits."""
     w, h = 80, 45
     pt, orc = pair(2, W.CAM_BUNNY, w, h, meshes[3], rtype=W.NORMAL_NEE)

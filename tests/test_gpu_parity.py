@@ -123,7 +123,7 @@ def test_full_size_properties_1080p(gpu_ok, built):
     st_a = a.stats()
     assert (cnt_a == 4).all() and st_a["paths"] == 1920 * 1080 * 4
     # (1) sample streams continue where the last call stopped. Contract B10 sums each call's samples in
-    # segments of 16 from +0: 2 + 2 samples are the same samples grouped (c0+c1)+(c2+c3) instead of ((c0+c1)+c2)+c3 —
+    # segments of 8 from +0: 2 + 2 samples are the same samples grouped (c0+c1)+(c2+c3) instead of ((c0+c1)+c2)+c3 —
     # equal up to f32 associativity — while 16 + 16 samples are bit-identical to 32 in one call (same segments).
     a.reset(); a.render_exact(2); a.render_exact(2)
     rgb_b, cnt_b = a.accum()

@@ -307,8 +307,9 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   P.accum = d_accum.p; P.pixel = s_pixel.p; P.spp_per_slot = d_spp_per_slot; P.uniform_spp = uniform_spp;
   // contract B10: render_exact cuts a pixel's samples into segments of WPT_SEGMENT_LEN, each summed from +0 by its
   // own slot (so one pixel's samples can run on several lanes); a strategy round (per-slot counts) is one segment.
-  P.nseg = d_spp_per_slot ? 1u : std::max(1u, (uniform_spp + WPT_SEGMENT_LEN - 1u) / WPT_SEGMENT_LEN);
-  P.seg_len = d_spp_per_slot ? 0x7FFFFFFFu : WPT_SEGMENT_LEN;
+  static const uint32_t seg_len = std::getenv("WPT_SEGMENT_LEN_EXPERIMENT") ? (uint32_t)std::atoi(std::getenv("WPT_SEGMENT_LEN_EXPERIMENT")) : WPT_SEGMENT_LEN;   // tuning only: changes the bits
+  P.nseg = d_spp_per_slot ? 1u : std::max(1u, (uniform_spp + seg_len - 1u) / seg_len);
+  P.seg_len = d_spp_per_slot ? 0x7FFFFFFFu : seg_len;
   if ((uint64_t)slots * P.nseg > 0x7FFFFFFFull) throw std::runtime_error("too many samples per pixel for one render_exact call at this viewport size");
   P.nslots = slots * P.nseg;
   if (P.nseg > 1) { d_seg_buf.alloc((size_t)P.nslots); P.seg_buf = d_seg_buf.p; }

@@ -80,7 +80,7 @@ struct DScene {
 };
 
 // Mode-B accumulation contract B10: render_exact sums a pixel's samples in segments of this length
-#define WPT_SEGMENT_LEN 16u
+#define WPT_SEGMENT_LEN 8u
 
 // xorshift32 stream contract (DESIGN.md "RNG contract")
 enum : uint32_t { STREAM_PATH = 1, STREAM_PHOTON = 2, STREAM_PIXEL = 3 };

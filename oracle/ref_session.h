@@ -305,7 +305,7 @@ struct Session {
           for (size_t xx = 0; xx < mb.rw; xx++) {
             size_t x = mb.rx + xx, y = mb.ry + yy;
             uint32_t n = take[yy * mb.rw + xx];
-            if (n) mb_samples(I, x, y, n, n, tst[t]);   // a strategy round = one segment per pixel (round spp <= 33)
+            if (n) mb_samples(I, x, y, n, MB_SEGMENT, tst[t]);
           }
         tst[t].prim_tests = tl_prim_tests();
       };
@@ -340,7 +340,7 @@ struct Session {
         for (size_t xx = 0; xx < mb.rw; xx++) {
           size_t x = mb.rx + xx, y = mb.ry + yy;
           uint32_t n = take[yy * mb.rw + xx];
-          if (n) mb_samples(I, x, y, n, n, tst[t]);
+          if (n) mb_samples(I, x, y, n, MB_SEGMENT, tst[t]);
         }
     };
     run_threads(threads, work);

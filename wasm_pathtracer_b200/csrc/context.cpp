@@ -308,11 +308,26 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   // contract B10: render_exact cuts a pixel's samples into segments of WPT_SEGMENT_LEN, each summed from +0 by its
   // own slot (so one pixel's samples can run on several lanes); a strategy round (per-slot counts) is one segment.
   static const uint32_t seg_len = std::getenv("WPT_SEGMENT_LEN_EXPERIMENT") ? (uint32_t)std::atoi(std::getenv("WPT_SEGMENT_LEN_EXPERIMENT")) : WPT_SEGMENT_LEN;   // tuning only: changes the bits
-  P.nseg = d_spp_per_slot ? 1u : std::max(1u, (uniform_spp + seg_len - 1u) / seg_len);
-  P.seg_len = d_spp_per_slot ? 0x7FFFFFFFu : seg_len;
-  if ((uint64_t)slots * P.nseg > 0x7FFFFFFFull) throw std::runtime_error("too many samples per pixel for one render_exact call at this viewport size");
-  P.nslots = slots * P.nseg;
-  if (P.nseg > 1) { d_seg_buf.alloc((size_t)P.nslots); P.seg_buf = d_seg_buf.p; }
+  P.seg_len = seg_len;
+  if (d_spp_per_slot) {
+    // strategy round: per-slot counts (0..33 adaptive, anything for random). The segments of all pixels are listed
+    // pixel by pixel on the device; pixels without samples get no slot. At most 8 segments per pixel fit the list
+    // encoding (pixel slot << 3 | segment); the strategies cap a round at 33 samples, random rounds are checked.
+    if (slots >= (1u << 29)) throw std::runtime_error("viewport too large for the segment list encoding");
+    const uint32_t max_seg = 8;
+    d_seg_cnt.alloc((size_t)slots + 1); d_seg_off.alloc((size_t)slots + 1); d_seg_list.alloc((size_t)slots * max_seg);
+    size_t sb = seg_scan_bytes(slots);
+    d_scan_tmp.alloc(sb ? sb : 1);
+    launch_build_segment_list(d_spp_per_slot, slots, seg_len, d_seg_cnt.p, d_seg_off.p, d_scan_tmp.p, sb, d_seg_list.p, stream);
+    d_seg_buf.alloc((size_t)slots * max_seg);
+    P.nseg = 1; P.seg_list = d_seg_list.p; P.nslots_dev = d_seg_off.p + slots; P.nslots = slots; P.seg_buf = d_seg_buf.p;
+    launches += 3;
+  } else {
+    P.nseg = std::max(1u, (uniform_spp + seg_len - 1u) / seg_len);
+    if ((uint64_t)slots * P.nseg > 0x7FFFFFFFull) throw std::runtime_error("too many samples per pixel for one render_exact call at this viewport size");
+    P.nslots = slots * P.nseg;
+    if (P.nseg > 1) { d_seg_buf.alloc((size_t)P.nslots); P.seg_buf = d_seg_buf.p; }
+  }
   P.work_counter = w_work.p; P.counters = w_counters.p;
   WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
   cudaEvent_t a = nullptr, b = nullptr;
@@ -344,7 +359,8 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   } else launch_mega(P, env_minb, stream);
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());
-  if (P.nseg > 1) { launch_combine_segments(d_accum.p, s_pixel.p, slots, d_seg_buf.p, P.nseg, uniform_spp, stream); launches += 1; }
+  if (P.seg_list) { launch_combine_segment_list(d_accum.p, s_pixel.p, slots, d_seg_buf.p, d_seg_off.p, d_spp_per_slot, stream); launches += 1; }
+  else if (P.nseg > 1) { launch_combine_segments(d_accum.p, s_pixel.p, slots, d_seg_buf.p, P.nseg, uniform_spp, stream); launches += 1; }
   launches += 1; iterations += 1;
   rgba_stale = true;
 }

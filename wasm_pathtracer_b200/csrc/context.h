@@ -132,12 +132,13 @@ struct Context {
   std::function<void()> exchange_hook;   // multi-GPU: gather all rows' accumulators between adaptive rounds
   std::function<void(uint32_t*, uint64_t)> reduce_hook;   // multi-GPU: in-place sum-allreduce of 32-bit words on `stream` (photon batches)
   DevBuf<float4> d_seg_buf;    // k_mega / k_pool: segment sums of a multi-segment launch (contract B10)
+  DevBuf<uint32_t> d_seg_cnt, d_seg_off, d_seg_list, d_pass_spp; DevBuf<uint8_t> d_scan_tmp;   // strategy rounds: segment list (contract B10)
   DevBuf<float4> d_seg_acc;    // wavefront engine: the running segment, per pixel
   DevBuf<uint32_t> ph_dense;   // one photon batch: [meta | light | loc_w x 4] per shot slot
   Strategy& strategy_for(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh);
   void clear_strategies();
   void region_error(Strategy& s, float stats3[3]);
-  void render_take(Strategy& s, uint32_t render_type);
+  void render_take(Strategy& s, uint32_t render_type, bool bounded);
   uint64_t run_adaptive(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange);
   void run_random(Strategy& s, uint32_t render_type, uint64_t ticks);
   void render_random(uint64_t ticks);

@@ -241,12 +241,28 @@ void Context::round_spp(uint32_t* spp) {
   WPT_CUDA(cudaStreamSynchronize(stream));
 }
 
-// Render `take[]` (region-indexed samples per pixel) on this session's rows.
-void Context::render_take(Strategy& s, uint32_t render_type) {
+// Render `take[]` (region-indexed samples per pixel) on this session's rows. Contract B10: a pixel's samples of the
+// call are summed in segments of WPT_SEGMENT_LEN. `bounded` = no pixel has more than 64 samples (adaptive rounds: <= 33),
+// so one launch with the device-built segment list does it; otherwise (random strategy) the call is cut into passes of at
+// most 64 samples per pixel — the same segments in the same order. The wavefront engine runs one segment per pass.
+void Context::render_take(Strategy& s, uint32_t render_type, bool bounded) {
   ensure_slots(s.rx, s.ry, s.rw, s.rh);
   launch_gather_slot_spp(s.take.p, s_pixel.p, slots, W, s.rx, s.ry, s.rw, s_spp.p, stream);
   launches += 1;
-  run_paths(render_type, s_spp.p, 0);
+  if (cfg.engine != 1 && bounded) { run_persistent(render_type, s_spp.p, 0); return; }
+  const uint32_t per_pass = cfg.engine == 1 ? WPT_SEGMENT_LEN : 64u;
+  d_pass_spp.alloc(slots);
+  for (uint32_t pass = 0;; pass++) {
+    uint32_t any = 0;
+    WPT_CUDA(cudaMemsetAsync(w_work.p + 1, 0, sizeof(uint32_t), stream));
+    launch_segment_pass_spp(s_spp.p, slots, per_pass, pass, d_pass_spp.p, w_work.p + 1, stream);
+    WPT_CUDA(cudaMemcpyAsync(&any, w_work.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+    launches += 1;
+    if (!any) break;
+    if (cfg.engine == 1) run_wavefront(render_type, d_pass_spp.p, 0);
+    else run_persistent(render_type, d_pass_spp.p, 0);
+  }
 }
 
 // AdaptiveSamplingStrategy in mode B (see the oracle's mb_render_adaptive for the contract).
@@ -306,7 +322,7 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
       taken = room;
     }
     auto t1 = now();
-    render_take(s, render_type);
+    render_take(s, render_type, true);   // an adaptive round holds at most 33 samples per pixel
     launch_sub_u32(s.round_left.p, s.take.p, N, stream);
     launches += 1;
     s.left_total -= taken;
@@ -330,7 +346,7 @@ void Context::run_random(Strategy& s, uint32_t render_type, uint64_t ticks) {
   launches += 2;
   s.random_ticks += ticks;
   WPT_CUDA(cudaMemcpyAsync(s.round_spp.p, s.take.p, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-  render_take(s, render_type);
+  render_take(s, render_type, ticks <= 64);
 }
 
 uint64_t Context::render_adaptive(uint64_t budget) {

@@ -8,6 +8,7 @@
 //              Scene::trace_g / Scene::shadow_ray (scene.rs:104-184).
 #include "kernels.h"
 #include "device_core.cuh"
+#include <cub/device/device_scan.cuh>
 
 namespace wpt {
 
@@ -524,6 +525,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   unsigned long long i_lp = 0, i_ll = 0, i_ts = 0, i_tl = 0, i_sh = 0;   // logic passes, logic lanes, trav steps, trav lanes, shade lanes
 #endif
 
+  const uint32_t nslots = P.nslots_dev ? *P.nslots_dev : P.nslots;
   for (;;) {
     // ---- pixel fetch: the warp owns a chunk of consecutive slots (= neighbouring tiles) and
     // hands them to its lanes; one atomic per chunk
@@ -535,8 +537,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(P.work_counter, P.chunk);
         base = __shfl_sync(FULL, base, 0);
-        if (chunk_next >= chunk_end) { chunk_next = base; chunk_end = min(base + P.chunk, P.nslots); if (base >= P.nslots) { chunk_end = chunk_next = P.nslots; queue_empty = true; } }
-        else { spare_next = base; spare_end = min(base + P.chunk, P.nslots); if (base >= P.nslots) { spare_next = spare_end = P.nslots; queue_empty = true; } }
+        if (chunk_next >= chunk_end) { chunk_next = base; chunk_end = min(base + P.chunk, nslots); if (base >= nslots) { chunk_end = chunk_next = nslots; queue_empty = true; } }
+        else { spare_next = base; spare_end = min(base + P.chunk, nslots); if (base >= nslots) { spare_next = spare_end = nslots; queue_empty = true; } }
       }
       if (phase == PH_NEED) {
         uint32_t r = (uint32_t)__popc(need & ((1u << lane) - 1u));
@@ -546,7 +548,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         if (ok) {
           // contract B10: the samples of this launch are summed per segment from +0; a slot is one segment
           uint32_t pslot = idx, j = 0;
-          if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
+          if (P.seg_list) { uint32_t e = P.seg_list[idx]; pslot = e >> 3; j = e & 7u; }   // strategy round: (pixel slot, segment) from the list
+          else if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
           slot_id = idx;
           pix = P.pixel[pslot];
           uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
           what = ST_EXTEND; start = true;
         } else {
-          if (P.nseg > 1) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
+          if (P.nseg > 1 || P.seg_list) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
           else {   // the only segment of its pixel: add it here
             float4 a = P.accum[pix];
             P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));
@@ -662,7 +665,7 @@ template <int BVH, bool SIMPLE>
 static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   int grid = device_sm_count() * blocks_per_sm;
   int need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS);
-  if (grid > need) grid = need;
+  if (grid > need && !P.nslots_dev) grid = need;
   switch (blocks_per_sm) {
     case 5: k_mega<BVH, SIMPLE, 5><<<grid, MEGA_THREADS, 0, s>>>(P); break;
     case 6: k_mega<BVH, SIMPLE, 6><<<grid, MEGA_THREADS, 0, s>>>(P); break;
@@ -905,14 +908,15 @@ __global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint3
         unsigned nm = __ballot_sync(FULL, needpix);
         if (nm) {
           uint32_t base = 0, k = 0;
-          if (lane == 0) pool_pixels(ctrl, P.work_counter, P.chunk, P.nslots, (uint32_t)__popc(nm), &base, &k);
+          if (lane == 0) pool_pixels(ctrl, P.work_counter, P.chunk, P.nslots_dev ? *P.nslots_dev : P.nslots, (uint32_t)__popc(nm), &base, &k);
           base = __shfl_sync(FULL, base, 0); k = __shfl_sync(FULL, k, 0);
           bool retire = false;
           if (needpix) {
             uint32_t rank = (uint32_t)__popc(nm & lt);
             if (rank < k) {
               uint32_t idx = base + rank, pslot = idx, j = 0;
-              if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
+              if (P.seg_list) { uint32_t e = P.seg_list[idx]; pslot = e >> 3; j = e & 7u; }
+              else if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
               slot_id = idx;
               pix = P.pixel[pslot];
               uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;
@@ -968,7 +972,7 @@ __global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint3
               ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
               what = ST_EXTEND; start = true;
             } else {
-              if (P.nseg > 1) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
+              if (P.nseg > 1 || P.seg_list) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
               else {
                 float4 a = P.accum[pix];
                 P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));
@@ -1098,7 +1102,7 @@ void launch_pool(const MegaParams& P, int blocks_per_sm, uint32_t slots_per_bloc
   if (!(P.simple_scene && !b4) && blocks_per_sm > 2) blocks_per_sm = 2;   // the other variants need > 64 registers
   int grid = device_sm_count() * blocks_per_sm;
   int need = (int)((P.nslots + S - 1) / S);
-  if (grid > need) grid = need;
+  if (grid > need && !P.nslots_dev) grid = need;
   if (P.simple_scene) {
     if (b4) launch_pool_t<4, true, 2>(P, S, cap, grid, s);
     else if (blocks_per_sm == 4) launch_pool_t<2, true, 4>(P, S, cap, grid, s);
@@ -1121,6 +1125,57 @@ __global__ void k_combine_segments(float4* accum, const uint32_t* __restrict__ p
 void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, uint32_t nseg, uint32_t spp, cudaStream_t s) {
   if (!npix) return;
   k_combine_segments<<<(npix + 255) / 256, 256, 0, s>>>(accum, pixel, npix, seg_buf, nseg, spp);
+}
+// ---- strategy rounds: every pixel slot has its own sample count (0..33 for an adaptive round). The segments of all
+// pixels are listed pixel by pixel (exclusive scan of ceil(spp / seg_len)); pixels without samples get no slot at all.
+__global__ void k_seg_count(const uint32_t* __restrict__ slot_spp, uint32_t npix, uint32_t seg_len, uint32_t* __restrict__ cnt) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > npix) return;
+  cnt[i] = i < npix ? (slot_spp[i] + seg_len - 1u) / seg_len : 0u;   // cnt[npix] = 0: the scan's last entry is the total
+}
+__global__ void k_seg_fill(const uint32_t* __restrict__ off, uint32_t npix, uint32_t* __restrict__ list) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  uint32_t a = off[i], b = off[i + 1];
+  for (uint32_t j = 0; a + j < b; j++) list[a + j] = (i << 3) | j;
+}
+size_t seg_scan_bytes(uint32_t npix) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(npix + 1));
+  return bytes;
+}
+void launch_build_segment_list(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t* seg_cnt, uint32_t* seg_off, void* scan_tmp, size_t scan_bytes, uint32_t* seg_list, cudaStream_t s) {
+  if (!npix) return;
+  k_seg_count<<<(npix + 1 + 255) / 256, 256, 0, s>>>(slot_spp, npix, seg_len, seg_cnt);
+  cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, seg_cnt, seg_off, (int)(npix + 1), s);
+  k_seg_fill<<<(npix + 255) / 256, 256, 0, s>>>(seg_off, npix, seg_list);
+}
+__global__ void k_combine_segment_list(float4* accum, const uint32_t* __restrict__ pixel, uint32_t npix, const float4* __restrict__ seg_buf, const uint32_t* __restrict__ off, const uint32_t* __restrict__ slot_spp) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  uint32_t a = off[i], b = off[i + 1];
+  if (a == b) return;
+  uint32_t pix = pixel[i];
+  float4 acc = accum[pix];
+  for (uint32_t k = a; k < b; k++) { float4 g = seg_buf[k]; acc.x += g.x; acc.y += g.y; acc.z += g.z; }
+  acc.w = __uint_as_float(__float_as_uint(acc.w) + slot_spp[i]);
+  accum[pix] = acc;
+}
+void launch_combine_segment_list(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, const uint32_t* seg_off, const uint32_t* slot_spp, cudaStream_t s) {
+  if (!npix) return;
+  k_combine_segment_list<<<(npix + 255) / 256, 256, 0, s>>>(accum, pixel, npix, seg_buf, seg_off, slot_spp);
+}
+// wavefront engine: the samples of pass `pass` (= segment index) of every slot; any_left counts slots that still have samples
+__global__ void k_segment_pass_spp(const uint32_t* __restrict__ slot_spp, uint32_t npix, uint32_t seg_len, uint32_t pass, uint32_t* __restrict__ pass_spp, uint32_t* any_left) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  uint32_t spp = slot_spp[i], b = min(pass * seg_len, spp), m = min(seg_len, spp - b);
+  pass_spp[i] = m;
+  if (m && any_left) atomicAdd(any_left, 1u);
+}
+void launch_segment_pass_spp(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t pass, uint32_t* pass_spp, uint32_t* any_left, cudaStream_t s) {
+  if (!npix) return;
+  k_segment_pass_spp<<<(npix + 255) / 256, 256, 0, s>>>(slot_spp, npix, seg_len, pass, pass_spp, any_left);
 }
 // wavefront engine: one segment was accumulated sample by sample into seg_acc (rgb sum from +0, count): add it
 __global__ void k_add_segment(float4* accum, const uint32_t* __restrict__ pixel, uint32_t npix, const float4* __restrict__ seg_acc) {

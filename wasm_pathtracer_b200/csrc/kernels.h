@@ -54,6 +54,8 @@ struct MegaParams {
   uint32_t uniform_spp, nslots;       // nslots = pixel slots x nseg
   uint32_t nseg, seg_len;             // contract B10: a pixel's samples of this launch are cut into nseg segments of seg_len
   float4* seg_buf;                    // nseg > 1: segment sums [pixel slot * nseg + j], combined in order by launch_combine_segments
+  const uint32_t* seg_list;           // strategy rounds: slot -> (pixel slot << 3 | segment); then nslots comes from nslots_dev and seg_buf is indexed by slot
+  const uint32_t* nslots_dev;
   uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
   uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
   uint32_t t_switch;              // k_pool: an under-filled logic warp flushes and goes traversing when qT holds at least this many rays
@@ -70,6 +72,12 @@ void launch_setup_slots(const PathState& st, const uint32_t* spp_per_slot, uint3
 void launch_trace(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
 void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
 void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, uint32_t nseg, uint32_t spp, cudaStream_t s);
+// Strategy rounds (per-slot sample counts): cut every pixel's samples into segments of seg_len, listed pixel by pixel.
+// seg_off needs npix + 1 entries (seg_off[npix] = number of segments); scan_tmp is scratch of at least seg_scan_bytes(npix) bytes.
+size_t seg_scan_bytes(uint32_t npix);
+void launch_build_segment_list(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t* seg_cnt, uint32_t* seg_off, void* scan_tmp, size_t scan_bytes, uint32_t* seg_list, cudaStream_t s);
+void launch_combine_segment_list(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, const uint32_t* seg_off, const uint32_t* slot_spp, cudaStream_t s);
+void launch_segment_pass_spp(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t pass, uint32_t* pass_spp, uint32_t* any_left, cudaStream_t s);
 void launch_add_segment(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_acc, cudaStream_t s);
 void launch_clear_pixels(float4* buf, const uint32_t* pixel, uint32_t npix, cudaStream_t s);
 void launch_resolve_rgba(const float4* accum, uint8_t* rgba, uint32_t n, cudaStream_t s);

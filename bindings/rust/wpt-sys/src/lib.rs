@@ -2,7 +2,7 @@
 //! environment); kept in sync with the header by hand. Each function replaces the export of
 //! `src/wasm_interface.rs` named in `wpt.h`.
 #![allow(non_camel_case_types)]
-use std::os::raw::{c_char, c_int};
+use std::os::raw::{c_char, c_int, c_void};
 
 #[repr(C)]
 pub struct wpt_ctx { _private: [u8; 0] }
@@ -30,6 +30,8 @@ pub const WPT_NORMAL_NEE: u32 = 1;
 pub const WPT_PNEE: u32 = 2;
 pub const WPT_SCENE_MUSEUM: u32 = 0;
 pub const WPT_SCENE_BUNNY: u32 = 2;
+/// Extension scene: not a reference id.
+pub const WPT_SCENE_EXT_WHITTED: u32 = 256;
 pub const WPT_DEVICE_NONE: c_int = -2;
 
 extern "C" {
@@ -71,6 +73,14 @@ extern "C" {
     pub fn wpt_ctx_render_exact(ctx: *mut wpt_ctx, spp: u32) -> c_int;
     pub fn wpt_ctx_render_adaptive(ctx: *mut wpt_ctx, budget_ticks: u64) -> i64;
     pub fn wpt_ctx_render_random(ctx: *mut wpt_ctx, ticks: u64) -> c_int;
+    pub fn wpt_ctx_allocate_texture(ctx: *mut wpt_ctx, id: u32, width: u32, height: u32) -> *mut u8;
+    pub fn wpt_ctx_notify_texture_loaded(ctx: *mut wpt_ctx, id: u32) -> c_int;
+    /// Multi-GPU: called between adaptive rounds to exchange the accumulator rows (NCCL all-gather in the caller).
+    pub fn wpt_ctx_set_exchange_callback(ctx: *mut wpt_ctx, callback: Option<unsafe extern "C" fn(user: *mut c_void)>, user: *mut c_void) -> c_int;
+    /// Multi-GPU photon warm-up: in-place integer sum of `n_words` u32 at `dev_words` over all ranks (ncclAllReduce, ncclUint32, ncclSum).
+    pub fn wpt_ctx_set_reduce_callback(ctx: *mut wpt_ctx, callback: Option<unsafe extern "C" fn(user: *mut c_void, dev_words: *mut c_void, n_words: u64)>, user: *mut c_void) -> c_int;
+    pub fn wpt_ctx_device_buffers(ctx: *mut wpt_ctx, ptrs: *mut u64, sizes: *mut u64) -> c_int;
+    pub fn wpt_ctx_mark_accum_dirty(ctx: *mut wpt_ctx) -> c_int;
     pub fn wpt_ctx_build_photons(ctx: *mut wpt_ctx) -> c_int;
     pub fn wpt_ctx_synchronize(ctx: *mut wpt_ctx) -> c_int;
     pub fn wpt_ctx_stats(ctx: *mut wpt_ctx, out: *mut u64) -> c_int;

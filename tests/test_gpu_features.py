@@ -110,6 +110,22 @@ def test_random_strategy_bit_exact(gpu_ok, meshes):
     assert pt.accum()[1].sum() == 1000 + 64 * 48 * 3 + 1
 
 
+def test_random_strategy_many_samples_per_pixel(gpu_ok, meshes):
+    """A random-strategy call that gives pixels far more than 64 samples runs in passes of <= 64 per pixel (8 segments of
+    8, contract B10) — the same segments in the same order as the oracle's single loop; all engines agree."""
+    w, h = 24, 16
+    pt, orc = pair(2, W.CAM_BUNNY, w, h, meshes[3], rtype=W.NORMAL_NEE)
+    ticks = w * h * 150
+    pt.render_random(ticks); orc.mb_render_random(ticks, threads=4)
+    rgb, cnt = pt.accum(); orgb, ocnt = orc.accum()
+    assert cnt.max() > 128 and np.array_equal(cnt, ocnt)
+    assert np.array_equal(bits(rgb), bits(orgb))
+    for engine in (1, 2):
+        pt.reset(); pt.set_config(engine=engine); pt.render_random(ticks)
+        assert np.array_equal(bits(pt.accum()[0]), bits(rgb)), engine
+    pt.close()
+
+
 def test_compute_reference_defaults(gpu_ok, meshes):
     """compute(n) with the reference's default halves: left NormalNEE + random, right PNEE + adaptive
     (wasm_interface.rs:90-97,374-384), replayed on the oracle's mode-B drivers."""

@@ -589,9 +589,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 #ifdef MEGA_INSTR
           i_ts += 1; i_tl += n_inner;
 #endif
-          if (tr && !leaf) need_pop = trav_inner<BVH>(sc, ray, tv, stack_n, stack_d);
-        } else if (leaf) { trav_leaf<BVH, SIMPLE>(sc, ray, tv); need_pop = true; }
-        if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
+          // a vote costs about as much as a third of an inner step: descend P.inner_reps nodes per vote (lanes that
+          // reach a leaf or finish sit the rest out)
+#pragma unroll 1
+          for (uint32_t rep = 0; rep < P.inner_reps; rep++) {
+            bool np = false;
+            if (phase == PH_TRAV && !trav_at_leaf<BVH>(tv)) np = trav_inner<BVH>(sc, ray, tv, stack_n, stack_d);
+            if (np && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
+          }
+        } else {
+          if (leaf) { trav_leaf<BVH, SIMPLE>(sc, ray, tv); need_pop = true; }
+          if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
+        }
         trav = __ballot_sync(FULL, phase == PH_TRAV);
       } while (__popc(trav) >= (int)P.t_lo);
       continue;

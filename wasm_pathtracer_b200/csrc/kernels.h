@@ -58,6 +58,7 @@ struct MegaParams {
   const uint32_t* nslots_dev;
   uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
   uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
+  uint32_t inner_reps;            // k_mega: inner-node steps per vote inside a burst
   uint32_t t_switch;              // k_pool: an under-filled logic warp flushes and goes traversing when qT holds at least this many rays
   uint32_t chunk;                 // slots a warp fetches at a time (multiple of 32)
   uint32_t simple_scene;          // shapes are triangles and planes only: kernel variant without torus / box code

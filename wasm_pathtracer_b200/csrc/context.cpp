@@ -87,7 +87,7 @@ void Context::reset() {   // wasm_interface.rs:137-148
   for (int i = 0; i < 4; i++) life[i] += now[i];
   WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 16 * sizeof(unsigned long long), stream));
   photon_rays = photon_visits = 0;
-  iterations = launches = 0;
+  iterations = 0; launches = 1;   // the sampling-view fill of clear_targets() above
   photons_shot_total = photons_stored_total = 0;
 }
 

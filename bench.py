@@ -267,11 +267,18 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if args.engine == 0 and world == 1 and args.spp == SPP and args.bvh == 2 and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")   # dram read + write of one launch, ncu --set full
+        extra = {}
+        ppath = os.path.join(ROOT, "profiles", "r1c_peaks.json")   # L2 / L1 / FP32 roofs measured with tools/wpt_peaks on a B200 of this pool
+        if os.path.exists(ppath) and achieved:
+            pk = json.load(open(ppath))
+            extra = {"l2_peak_gbs": pk["l2_read_gbs"], "frac_of_l2": achieved / pk["l2_read_gbs"], "l1_peak_gbs": pk["l1_read_gbs"], "frac_of_l1": achieved / pk["l1_read_gbs"],
+                     "fp32_peak_tflops": pk["fp32_fma_tflops"]}
         roofline = {"bound": "hbm", "kernel": "k_trace" if args.engine == 1 else "k_mega", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                     "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": alg_bytes / max(1, prof["trace_launches"]), "avg_launch_ms": prof["trace_ms"] / max(1, prof["trace_launches"]),
                     "kernel_share_of_step": prof["trace_ms"] / ms if ms else None, "shade_kernel_share_of_step": prof["shade_ms"] / ms if ms else None,
                     "visits_per_ray": prof["node_visits"] / max(1, prof["rays"]), "prims_per_ray": prof["prim_tests"] / max(1, prof["rays"]),
+                    **extra,
                     "note": "achieved = algorithmic bytes (SURVEY 8d) / kernel time; the scene (~10 MB) is cache resident (measured DRAM traffic is ~3% of the algorithmic bytes, mostly local-memory evictions): the real bounds are instruction issue under divergence and load latency (DESIGN.md 5, profiles/r1c_k_mega_bench_full.md)"}
         line = {"metric": "Mrays/s (bunny 1080p, 16 spp, NormalNEE, BVH%d)" % args.bvh, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

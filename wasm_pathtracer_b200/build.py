@@ -43,4 +43,11 @@ def build_tools(force=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout)
             raise RuntimeError("building tools/wpt_render failed")
+    # tools/wpt_peaks: L2 / HBM / FP32 roofs measured on the box
+    psrc, pexe = os.path.join(TOOLS_DIR, "wpt_peaks.cu"), os.path.join(TOOLS_DIR, "wpt_peaks")
+    if force or not os.path.exists(pexe) or os.path.getmtime(pexe) < os.path.getmtime(psrc):
+        r = subprocess.run(["nvcc", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", psrc, "-o", pexe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("building tools/wpt_peaks failed")
     return RENDER

@@ -76,3 +76,54 @@ def test_extension_scene_gpu_matches_oracle(gpu_ok, rtype):
         pt.reset(); pt.set_config(engine=engine); pt.render_exact(24)
         assert np.array_equal(bits(pt.accum()[0]), bits(rgb)), engine
     pt.close()
+
+
+def _ext_oracle():
+    orc = O.Oracle(32, 32, O.SCENE_BUNNY, O.CAM_WHITTED)
+    orc.store_texture(0, checker()); orc.update_scene(O.SCENE_EXT_WHITTED)
+    src, typ = orc.shape_order()
+    return orc, {int(s): i for i, s in enumerate(src)}      # original shape index -> index after the BVH reorder
+
+
+def test_sphere_and_square_known_answers(built):
+    """Hand-derived hits of sphere.rs:49-131 and square.rs:56-99 on the extension scene (original shape order:
+    0 = Square floor y = -1, size 8, centre (0,-1,4); 1 = Sphere (-1.3,1,-0.2) r 0.7; 2 = Sphere (-0.4,0,1) r 0.6)."""
+    orc, at = _ext_oracle()
+    o = np.array([[-0.4, 0.0, -5.0],      # towards the centre of sphere 2 from outside: t = 6 - 0.6, outward normal -z
+                  [-0.4, 0.0, 1.0],       # from its centre: t = r, normal flipped towards the origin of the ray (is_entering = false)
+                  [0.0, 5.0, 4.0],        # straight down onto the floor: t = 6, normal +y
+                  [0.0, -5.0, 4.0],       # from below: the Square is two-sided, normal -y
+                  [5.0, 5.0, 4.0],        # x = 5: |dx| = 5, 2 dx >= size -> miss
+                  [4.0, 5.0, 4.0],        # exactly on the edge: 2 dx == size -> miss (square.rs:76 is `>=`)
+                  [-1.3, 1.0, -5.0]], np.float32)
+    d = np.array([[0, 0, 1], [0, 0, 1], [0, -1, 0], [0, 1, 0], [0, -1, 0], [0, -1, 0], [0, 0, 1]], np.float32)
+    ids, dist, vis, nrm = orc.trace_rays(o, d)
+    assert ids[0] == at[2] and abs(dist[0] - 5.4) < 1e-5 and np.allclose(nrm[0], [0, 0, -1], atol=1e-6)
+    assert ids[1] == at[2] and abs(dist[1] - 0.6) < 1e-6 and np.allclose(nrm[1], [0, 0, -1], atol=1e-6)
+    assert ids[2] == at[0] and dist[2] == 6.0 and np.array_equal(nrm[2], [0, 1, 0])
+    assert ids[3] == at[0] and dist[3] == 4.0 and np.array_equal(nrm[3], [0, -1, 0])
+    assert ids[4] == -1 and ids[5] == -1
+    assert ids[6] == at[1] and abs(dist[6] - (4.8 - 0.7)) < 1e-5
+
+
+def test_fresnel_beer_and_texture_semantics(built):
+    """The extension's material rules, observed through renders of single pixels: a camera inside the absorbing sphere
+    sees the sky attenuated by Beer's law on the way out; the checker floor is sampled with Texture::at (nearest texel)."""
+    orc, at = _ext_oracle()
+    # texture: looking straight down at the floor from above texel centres -> exactly red or yellow over black-ish shading
+    o = np.array([[0.25, 3.0, 4.25], [0.75, 3.0, 4.25]], np.float32); d = np.array([[0, -1, 0], [0, -1, 0]], np.float32)
+    ids, dist, _, _ = orc.trace_rays(o, d)
+    assert (ids == at[0]).all()
+    # u = (x - cx) / 8 + 0.5 -> texel column floor(u * 16); x = 0.25 -> u = 0.53125 -> column 8, x = 0.75 -> u = 0.59375 -> column 9
+    u = (o[:, 0] - 0.0) / 8.0 + 0.5; v = (o[:, 2] - 4.0) / 8.0 + 0.5
+    cols = np.floor(u * 16).astype(int); rows = np.floor(v * 16).astype(int)
+    assert list(cols) == [8, 9] and list(rows) == [8, 8]
+    tex = checker()
+    assert tuple(tex[rows[0], cols[0]]) == (255, 0, 0) and tuple(tex[rows[1], cols[1]]) == (255, 255, 0)
+    # Schlick at normal incidence for ior 1.02: r0 = ((1 - 1.02) / (1 + 1.02))^2
+    r0 = ((1.0 - 1.02) / (1.0 + 1.02)) ** 2
+    assert 9e-5 < r0 < 1e-4
+    # Beer through the whole refracting sphere (diameter 1.4, absorption (0.5, 1, 0.5)): the shared e^-x against numpy
+    t = np.float32(1.4)
+    got = O.shared_exp_neg(np.array([0.5, 1.0, 0.5], np.float32) * t)
+    assert np.allclose(got, np.exp(-np.array([0.7, 1.4, 0.7])), rtol=2e-6)

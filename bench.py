@@ -163,7 +163,12 @@ def main():
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spp_total = args.spp * world           # weak scaling: 16 spp per GPU, rows interleaved over ranks
-    W.build_library()
+    # in-tree library: only rank 0 may (re)build it and write the generated mesh; the others wait for it
+    if rank == 0:
+        W.build_library()
+        mesh_path()
+    if dist is not None:
+        dist.barrier()
     verts = W.parse_obj(open(mesh_path()).read(), True)
     pt = W.PathTracer(W_, H_, W.SCENE_BUNNY, *W.CAM_BUNNY, device=local)
     pt.store_mesh(W.api.MESH_BUNNY_HIGH, verts)

@@ -335,10 +335,11 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   static const int env_hi = std::getenv("WPT_MEGA_THI") ? std::atoi(std::getenv("WPT_MEGA_THI")) : 20;
   static const int env_lo = std::getenv("WPT_MEGA_TLO") ? std::atoi(std::getenv("WPT_MEGA_TLO")) : 10;
   // blocks per SM (= register budget) of the four kernel variants: triangles/planes BVH2, BVH4, generic BVH2, BVH4
-  // (measured, gpurun_out/sweep8.log, sweep11.log: the generic variant likes 10 although it spills (museum 85 -> 72 -> 68 ms);
+  // (measured, gpurun_out/sweep8.log, sweep11.log: the generic variant wants every warp it can get although it spills heavily at 32 registers
+  //  (museum, 8-spp frame: 4 blocks/SM 85 ms, 8: 72, 10: 68, 12: 65, 16: 59 — its bound is instruction fetch + latency);
   //  triangles/planes BVH2 8 or 9, 10 is worse; BVH4 5, or 8 with PNEE)
   static const int env_minb_base[4] = {std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 8, std::getenv("WPT_MEGA_MINB4") ? std::atoi(std::getenv("WPT_MEGA_MINB4")) : 0,
-                                       std::getenv("WPT_MEGA_MINBG") ? std::atoi(std::getenv("WPT_MEGA_MINBG")) : 10, std::getenv("WPT_MEGA_MINBG4") ? std::atoi(std::getenv("WPT_MEGA_MINBG4")) : 8};
+                                       std::getenv("WPT_MEGA_MINBG") ? std::atoi(std::getenv("WPT_MEGA_MINBG")) : 16, std::getenv("WPT_MEGA_MINBG4") ? std::atoi(std::getenv("WPT_MEGA_MINBG4")) : 16};
   int env_minb[4] = {env_minb_base[0], env_minb_base[1] ? env_minb_base[1] : (render_type == WPT_PNEE ? 8 : 5), env_minb_base[2], env_minb_base[3]};
   static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 2;
   static const int env_reps = std::getenv("WPT_MEGA_REPS") ? std::atoi(std::getenv("WPT_MEGA_REPS")) : 4;   // measured: 1 -> 20.0, 2 -> 19.3, 4 -> 18.8, 8 -> 19.5 ms (gpurun_out/sweep10*.log)

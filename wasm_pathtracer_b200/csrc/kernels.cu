@@ -682,6 +682,8 @@ static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s
     case 8: k_mega<BVH, SIMPLE, 8><<<grid, MEGA_THREADS, 0, s>>>(P); break;
     case 9: k_mega<BVH, SIMPLE, 9><<<grid, MEGA_THREADS, 0, s>>>(P); break;
     case 10: k_mega<BVH, SIMPLE, 10><<<grid, MEGA_THREADS, 0, s>>>(P); break;
+    case 12: k_mega<BVH, SIMPLE, 12><<<grid, MEGA_THREADS, 0, s>>>(P); break;
+    case 16: k_mega<BVH, SIMPLE, 16><<<grid, MEGA_THREADS, 0, s>>>(P); break;
     default: k_mega<BVH, SIMPLE, 4><<<grid, MEGA_THREADS, 0, s>>>(P); break;
   }
 }
@@ -689,7 +691,7 @@ static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s
 void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s) {
   if (!P.nslots) return;
   const bool b4 = P.rp.scene.bvh_kind == 4;
-  auto clampb = [](int b) { return b < 4 ? 4 : (b > 10 ? 10 : b); };
+  auto clampb = [](int b) { return b < 4 ? 4 : (b >= 16 ? 16 : (b > 12 ? 12 : (b == 11 ? 10 : b))); };
   if (P.simple_scene) { if (b4) launch_mega_t<4, true>(P, clampb(blocks_per_sm[1]), s); else launch_mega_t<2, true>(P, clampb(blocks_per_sm[0]), s); }
   else { if (b4) launch_mega_t<4, false>(P, clampb(blocks_per_sm[3]), s); else launch_mega_t<2, false>(P, clampb(blocks_per_sm[2]), s); }
 }

@@ -251,6 +251,11 @@ def test_segmented_accumulation_contract_b10(gpu_ok, meshes):
     orc.mb_render_exact(37, threads=4); orc.mb_render_exact(5, threads=4)
     rgb, cnt = pt.accum(); orgb, ocnt = orc.accum()
     assert np.array_equal(cnt, ocnt) and int(cnt.min()) == 42
+    # more than 64 samples in one call run as several launches of <= 8 segments: still the same segments in the same order
+    small, osmall = pair(2, W.CAM_BUNNY, 24, 16, meshes[3], rtype=W.NORMAL_NEE)
+    small.render_exact(150); osmall.mb_render_exact(150, threads=4)
+    assert np.array_equal(bits(small.accum()[0]), bits(osmall.accum()[0])) and int(small.accum()[1].min()) == 150
+    small.close()
     assert np.array_equal(bits(rgb), bits(orgb))
     st, ost = pt.stats(), orc.stats(0)
     assert (st["rays"], st["node_visits"], st["paths"]) == (ost["rays"], ost["node_visits"], ost["paths"])

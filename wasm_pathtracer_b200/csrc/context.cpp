@@ -381,7 +381,11 @@ void Context::render_exact(uint32_t spp) {
   ensure_slots(rx, ry, rw, rh);
   if (cfg.engine == 1) {   // the wavefront engine runs the segments of contract B10 one after the other
     for (uint32_t rem = spp; rem > 0;) { uint32_t m = std::min(rem, WPT_SEGMENT_LEN); run_wavefront(cfg.render_type, nullptr, m); rem -= m; }
-  } else run_persistent(cfg.render_type, nullptr, spp);
+  } else {
+    // at most 64 samples (8 segments) per pixel and launch: bounds the segment-sum buffer (128 B per pixel); the
+    // segments of later launches are added after those of earlier ones, i.e. in the same order as in one launch
+    for (uint32_t rem = spp; rem > 0;) { uint32_t m = std::min(rem, 8u * WPT_SEGMENT_LEN); run_persistent(cfg.render_type, nullptr, m); rem -= m; }
+  }
 }
 
 const uint8_t* Context::results(uint32_t show_sampling) {   // wasm_interface.rs:120-134

@@ -90,7 +90,7 @@ WPT_DEV uint32_t tree_walk(const DPhotonTree& t, uint32_t depth, F3 q) {   // fi
     depth--;
   }
 }
-__device__ __noinline__ void photon_sample(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* light, float* pdf_out) {
+WPT_DEV void photon_sample_inl(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* light, float* pdf_out) {
   const float size = 1024.0f;
   if (v.x < -size || v.y < -size || v.z < -size || v.x > size || v.y > size || v.z > size) {
     *light = rng.range(0, t.num_lights);
@@ -156,6 +156,8 @@ __device__ __noinline__ void photon_sample(const DPhotonTree& t, Rng& rng, F3 v,
   *light = res;
   *pdf_out = pdf;
 }
+// out-of-line copy for the kernels that take the render type at run time (k_shade, k_pool, the sample-batch probe)
+__device__ __noinline__ void photon_sample(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* light, float* pdf_out) { photon_sample_inl(t, rng, v, light, pdf_out); }
 
 // Triangle::pick_random (triangle.rs:91-114) on light `li`
 WPT_DEV void pick_random(const DScene& sc, uint32_t li, Rng& rng, F3* p, F3* n, F3* intensity, float* area, uint32_t* shape_id) {
@@ -184,9 +186,12 @@ struct ShadeOut {
   F3 next_o, next_d; // the bounce ray
   F3 sh_o, sh_d; float sh_len; int sh_light; F3 contrib;
 };
-template <bool SIMPLE>
+// RT: the render type when it is known at compile time (0 NoNEE, 1 NormalNEE, 2 PNEE: k_mega is instantiated per type — no
+// photon code in the NEE kernels, photon_sample inlined in the PNEE kernel: 9 % / 15 % faster than one kernel that branches
+// and calls), 3 = decided at run time (k_shade, k_pool: out-of-line photon_sample)
+template <bool SIMPLE, int RT = 3>
 WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_hit, PathRegs& ps, ShadeOut& out) {
-  const bool has_nee = rp.render_type != 0;
+  const bool has_nee = RT == 3 ? rp.render_type != 0 : RT != 0;
   out.finished = false; out.survive = false; out.shadow = false;
   bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
   bool entering = true; float2 uv = make_float2(0.0f, 0.0f);
@@ -266,7 +271,8 @@ WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_h
   ps.bounced = true;
   if (has_nee) {   // tracer.rs:267-313
     uint32_t light_id; float chance;
-    if (rp.render_type == 2) photon_sample(rp.photons, ps.rng, hit_point, &light_id, &chance);
+    if (RT == 2) photon_sample_inl(rp.photons, ps.rng, hit_point, &light_id, &chance);
+    else if (RT == 3 && rp.render_type == 2) photon_sample(rp.photons, ps.rng, hit_point, &light_id, &chance);
     else { light_id = ps.rng.range(0, rp.scene.num_lights); chance = 1.0f / (float)rp.scene.num_lights; }
     F3 pl, ln, inten; float area; uint32_t lsid;
     pick_random(rp.scene, light_id, ps.rng, &pl, &ln, &inten, &area, &lsid);
@@ -504,7 +510,7 @@ void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers
 enum : int { PH_NEED = 0, PH_LOGIC = 1, PH_TRAV = 2, PH_DONE = 3 };
 enum : int { ST_GEN = 0, ST_EXTEND = 1, ST_SHADOW = 2 };
 
-template <int BVH, bool SIMPLE, int MINB>
+template <int BVH, bool SIMPLE, int MINB, int RT>
 __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           else finish = true;
         } else {
           ShadeOut so;
-          shade_hit<SIMPLE>(P.rp, ray, g.id, g.t, ps, so);
+          shade_hit<SIMPLE, RT>(P.rp, ray, g.id, g.t, ps, so);
           if (so.finished) finish = true;
           else if (so.shadow) {
             ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
@@ -670,30 +676,43 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   if (lane == 1) atomicAdd(&P.counters[8], i_sh);
 #endif
 }
-template <int BVH, bool SIMPLE>
+// Register budgets (blocks of 128 threads per SM) instantiated per variant: the measured optimum (gpurun_out/sweep8.log,
+// sweep11.log) — triangles/planes BVH2 8 (64 registers), BVH4 5 and 8, generic 16 (32 registers) — or, with -DWPT_TUNING,
+// 4 / 5 / 8 / 12 / 16 for every variant (WPT_MEGA_MINB* then selects).
+template <int BVH, bool SIMPLE, int RT>
 static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
-  int grid = device_sm_count() * blocks_per_sm;
-  int need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS);
-  if (grid > need && !P.nslots_dev) grid = need;
-  switch (blocks_per_sm) {
-    case 5: k_mega<BVH, SIMPLE, 5><<<grid, MEGA_THREADS, 0, s>>>(P); break;
-    case 6: k_mega<BVH, SIMPLE, 6><<<grid, MEGA_THREADS, 0, s>>>(P); break;
-    case 7: k_mega<BVH, SIMPLE, 7><<<grid, MEGA_THREADS, 0, s>>>(P); break;
-    case 8: k_mega<BVH, SIMPLE, 8><<<grid, MEGA_THREADS, 0, s>>>(P); break;
-    case 9: k_mega<BVH, SIMPLE, 9><<<grid, MEGA_THREADS, 0, s>>>(P); break;
-    case 10: k_mega<BVH, SIMPLE, 10><<<grid, MEGA_THREADS, 0, s>>>(P); break;
-    case 12: k_mega<BVH, SIMPLE, 12><<<grid, MEGA_THREADS, 0, s>>>(P); break;
-    case 16: k_mega<BVH, SIMPLE, 16><<<grid, MEGA_THREADS, 0, s>>>(P); break;
-    default: k_mega<BVH, SIMPLE, 4><<<grid, MEGA_THREADS, 0, s>>>(P); break;
+  auto grid_for = [&](int b) { int grid = device_sm_count() * b, need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS); return (grid > need && !P.nslots_dev) ? need : grid; };
+#ifdef WPT_TUNING
+  int b = blocks_per_sm >= 16 ? 16 : blocks_per_sm >= 12 ? 12 : blocks_per_sm >= 8 ? 8 : blocks_per_sm >= 5 ? 5 : 4;
+  switch (b) {
+    case 5: k_mega<BVH, SIMPLE, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P); break;
+    case 8: k_mega<BVH, SIMPLE, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P); break;
+    case 12: k_mega<BVH, SIMPLE, 12, RT><<<grid_for(12), MEGA_THREADS, 0, s>>>(P); break;
+    case 16: k_mega<BVH, SIMPLE, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P); break;
+    default: k_mega<BVH, SIMPLE, 4, RT><<<grid_for(4), MEGA_THREADS, 0, s>>>(P); break;
+  }
+#else
+  (void)blocks_per_sm;
+  if (!SIMPLE) k_mega<BVH, SIMPLE, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
+  else if (BVH == 2 || RT == 2) k_mega<BVH, SIMPLE, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
+  else k_mega<BVH, SIMPLE, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P);
+#endif
+}
+template <int BVH, bool SIMPLE>
+static void launch_mega_rt(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
+  switch (P.rp.render_type) {
+    case 0: launch_mega_t<BVH, SIMPLE, 0>(P, blocks_per_sm, s); break;
+    case 2: launch_mega_t<BVH, SIMPLE, 2>(P, blocks_per_sm, s); break;
+    default: launch_mega_t<BVH, SIMPLE, 1>(P, blocks_per_sm, s); break;
   }
 }
 // blocks_per_sm[variant]: 0 = triangles/planes BVH2, 1 = triangles/planes BVH4, 2 = generic BVH2, 3 = generic BVH4
 void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s) {
   if (!P.nslots) return;
   const bool b4 = P.rp.scene.bvh_kind == 4;
-  auto clampb = [](int b) { return b < 4 ? 4 : (b >= 16 ? 16 : (b > 12 ? 12 : (b == 11 ? 10 : b))); };
-  if (P.simple_scene) { if (b4) launch_mega_t<4, true>(P, clampb(blocks_per_sm[1]), s); else launch_mega_t<2, true>(P, clampb(blocks_per_sm[0]), s); }
-  else { if (b4) launch_mega_t<4, false>(P, clampb(blocks_per_sm[3]), s); else launch_mega_t<2, false>(P, clampb(blocks_per_sm[2]), s); }
+  const int v = (P.simple_scene ? 0 : 2) + (b4 ? 1 : 0);
+  if (P.simple_scene) { if (b4) launch_mega_rt<4, true>(P, blocks_per_sm[v], s); else launch_mega_rt<2, true>(P, blocks_per_sm[v], s); }
+  else { if (b4) launch_mega_rt<4, false>(P, blocks_per_sm[v], s); else launch_mega_rt<2, false>(P, blocks_per_sm[v], s); }
 }
 
 // ------------------------------------------------------------------ block-pool path kernel

@@ -523,7 +523,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0;
   F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
-  uint32_t c_rays = 0, c_visits = 0, c_prims = 0, c_paths = 0;
+  // ray / visit / primitive-test / path counters live in shared memory (four registers less in a kernel that spills):
+  // fire-and-forget shared atomics, flushed to the global counters when the block is done
+  __shared__ unsigned int s_cnt[4];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
   uint32_t chunk_next = 0, chunk_end = 0, spare_next = 0, spare_end = 0; bool queue_empty = false;   // warp-uniform
   F3 acc_rgb = f3(0, 0, 0);   // sum of this segment's samples (contract B10), added to the pixel's accumulator (render_target.rs:8) when the segment is done
   uint32_t slot_id = 0;
@@ -625,7 +629,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
       bool start = false;
       if (what == (half == 0 ? ST_SHADOW : ST_EXTEND)) {
         GHit g = trav_result(tv);
-        c_rays += 1; c_visits += g.visits; c_prims += g.prims;
+        atomicAdd(&s_cnt[0], 1u); atomicAdd(&s_cnt[1], g.visits); if (g.prims) atomicAdd(&s_cnt[3], g.prims);
         bool finish = false;
         if (half == 0) {   // Scene::shadow_ray, scene.rs:114-132
           bool occluded = g.id >= 0 && g.t < sh_len && g.id != sh_light;
@@ -643,7 +647,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           } else if (so.survive) { ray = make_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
           else finish = true;
         }
-        if (finish) { acc_rgb = acc_rgb + ps.color; c_paths += 1; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
+        if (finish) { acc_rgb = acc_rgb + ps.color; atomicAdd(&s_cnt[2], 1u); s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
       }
       if (what == ST_GEN) {
         if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream
@@ -667,10 +671,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
     }
   }
   // ---- counters
-  unsigned long long r = warp_sum_u64(c_rays), v = warp_sum_u64(c_visits), pr = warp_sum_u64(c_prims), pa = warp_sum_u64(c_paths);
-  if (lane == 0 && r) {
-    atomicAdd(&P.counters[0], r); atomicAdd(&P.counters[1], v); atomicAdd(&P.counters[2], pa); atomicAdd(&P.counters[3], pr);
-  }
+  __syncthreads();
+  if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 #ifdef MEGA_INSTR
   if (lane == 0) { atomicAdd(&P.counters[4], i_lp); atomicAdd(&P.counters[5], i_ll); atomicAdd(&P.counters[6], i_ts); atomicAdd(&P.counters[7], i_tl); }
   if (lane == 1) atomicAdd(&P.counters[8], i_sh);

@@ -695,8 +695,8 @@ static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s
   }
 #else
   (void)blocks_per_sm;
-  if (!SIMPLE) k_mega<BVH, SIMPLE, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
-  else if (BVH == 2 || RT == 2) k_mega<BVH, SIMPLE, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
+  if constexpr (!SIMPLE) k_mega<BVH, SIMPLE, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
+  else if constexpr (BVH == 2 || RT == 2) k_mega<BVH, SIMPLE, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
   else k_mega<BVH, SIMPLE, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P);
 #endif
 }

@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 #endif
 }
 // Register budgets (blocks of 128 threads per SM) instantiated per variant: the measured optimum (gpurun_out/sweep8.log,
-// sweep11.log) — triangles/planes BVH2 8 (64 registers), BVH4 5 and 8, generic 16 (32 registers) — or, with -DWPT_TUNING,
+// sweep11.log, sweep12.log) — triangles/planes BVH2 8 (64 registers), BVH4 5 and 8, generic 16 (32 registers) — or, with -DWPT_TUNING,
 // 4 / 5 / 8 / 12 / 16 for every variant (WPT_MEGA_MINB* then selects).
 template <int BVH, bool SIMPLE, int RT>
 static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {

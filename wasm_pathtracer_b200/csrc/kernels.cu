@@ -69,8 +69,11 @@ WPT_DEV float tree_bin_prob(const DPhotonTree& t, uint32_t node, uint32_t i) {  
   return __ldg(cum + i + 1) - __ldg(cum + i);
 }
 WPT_DEV void axis_weight(float v, float c, float lo, float hi, float sz, float* w, float* w_adj, float* off) {   // photon_tree.rs:90-124
-  if (v > c) { float lw = (hi - (v - sz * 0.5f)) / sz; *w = lw; *w_adj = 1.0f - lw; *off = 1.0f; }
-  else { float rw = ((v + sz * 0.5f) - lo) / sz; *w = rw; *w_adj = 1.0f - rw; *off = -1.0f; }
+  // both branches of the reference end in one division by the cell size: select the numerator, divide once
+  const bool up = v > c;
+  const float num = up ? (hi - (v - sz * 0.5f)) : ((v + sz * 0.5f) - lo);
+  const float ww = num / sz;
+  *w = ww; *w_adj = 1.0f - ww; *off = up ? 1.0f : -1.0f;
 }
 // Same result as the reference's ten root-to-cell walks (find_leaf + find_node_cdf for the
 // sampled cell + 8 for the interpolated pdf) with one: find_leaf. The eight query points are
@@ -144,15 +147,20 @@ WPT_DEV void photon_sample_inl(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* l
     if (__ldg(cum + mid) <= r) low = mid; else high = mid;
   }
   uint32_t res = low;
+  // EmpiricalPDF::bin_prob (empirical_pdf.rs:64-75) of bin `res` in each of the eight cells: cum[res + 1] - cum[res], with
+  // 1.0 in place of cum[res + 1] for the last bin — the same subtraction either way, so the test is hoisted out
+  const bool last = res + 1 == t.num_lights;
+  const size_t L = t.num_lights;
+  auto bp = [&](uint32_t nd) { const float* c = t.cum + (size_t)nd * L + res; float a = __ldg(c); float hi = last ? 1.0f : __ldg(c + 1); return hi - a; };
   float pdf = 0.0f;   // the reference's order of the eight terms (photon_tree.rs:149-156)
-  pdf += tree_bin_prob(t, n8[0], res) * wx * wy * wz;
-  pdf += tree_bin_prob(t, n8[1], res) * ax * wy * wz;
-  pdf += tree_bin_prob(t, n8[2], res) * wx * ay * wz;
-  pdf += tree_bin_prob(t, n8[4], res) * wx * wy * az;
-  pdf += tree_bin_prob(t, n8[3], res) * ax * ay * wz;
-  pdf += tree_bin_prob(t, n8[6], res) * wx * ay * az;
-  pdf += tree_bin_prob(t, n8[5], res) * ax * wy * az;
-  pdf += tree_bin_prob(t, n8[7], res) * ax * ay * az;
+  pdf += bp(n8[0]) * wx * wy * wz;
+  pdf += bp(n8[1]) * ax * wy * wz;
+  pdf += bp(n8[2]) * wx * ay * wz;
+  pdf += bp(n8[4]) * wx * wy * az;
+  pdf += bp(n8[3]) * ax * ay * wz;
+  pdf += bp(n8[6]) * wx * ay * az;
+  pdf += bp(n8[5]) * ax * wy * az;
+  pdf += bp(n8[7]) * ax * ay * az;
   *light = res;
   *pdf_out = pdf;
 }

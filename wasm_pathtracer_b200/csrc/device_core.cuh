@@ -27,9 +27,14 @@ WPT_DEV F3 cross(F3 a, F3 t) { return f3(a.y * t.z - a.z * t.y, a.z * t.x - a.x 
 WPT_DEV float len(F3 a) { return sqrtf(dot(a, a)); }
 WPT_DEV F3 normalize(F3 a) { return a * (1.0f / len(a)); }   // vec3.rs:27-29
 WPT_DEV F3 orthogonal(F3 s) {                                 // vec3.rs:37-54
-  if (fabsf(s.z) > 0.1f) return normalize(f3(1.0f, 1.0f, -(s.x * 1.0f + s.y * 1.0f) / s.z));
-  if (fabsf(s.x) > 0.1f) return normalize(f3(-(s.y * 1.0f + s.z * 1.0f) / s.x, 1.0f, 1.0f));
-  return normalize(f3(1.0f, -(s.x * 1.0f + s.z * 1.0f) / s.y, 1.0f));
+  // the three cases differ only in which component is divided out: one division and one normalize on selected
+  // operands — the same operations on the same values as the reference's three branches, a third of the code
+  const bool cz = fabsf(s.z) > 0.1f, cx = !cz && fabsf(s.x) > 0.1f;
+  const float a = cz ? s.x : (cx ? s.y : s.x);
+  const float b = cz ? s.y : s.z;
+  const float den = cz ? s.z : (cx ? s.x : s.y);
+  const float q = -(a * 1.0f + b * 1.0f) / den;
+  return normalize(f3(cx ? q : 1.0f, (cz || cx) ? 1.0f : q, cz ? q : 1.0f));
 }
 WPT_DEV F3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
 

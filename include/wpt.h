@@ -115,7 +115,7 @@ typedef struct wpt_config {
   uint64_t photon_target;   /* diffuse-hit photons to collect (default 300000, tracer.rs:104)        */
   uint32_t region_x, region_y, region_w, region_h; /* logical sampling region (0 size = full frame)  */
   uint32_t rank, world;     /* this session renders rows {y : band(y) == rank} of the region         */
-  uint32_t engine;          /* 0 = persistent path kernel k_mega (default), 1 = multi-kernel wavefront, 2 = block-pool kernel k_pool */
+  uint32_t engine;          /* 0 = persistent path kernel k_mega (default), 1 = multi-kernel wavefront, 4 = experimental warp-pool kernel k_wpool */
   uint32_t reserved[3];
 } wpt_config;
 

@@ -350,15 +350,22 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { P.simple_scene = 0; break; }
   for (const HostMaterial& m : scene.mats) if (m.kind != MAT_DIFFUSE && m.kind != MAT_EMISSIVE) { P.simple_scene = 0; break; }
   if (std::getenv("WPT_NO_SIMPLE")) P.simple_scene = 0;
-  if (cfg.engine == 2) {   // block-pool kernel: refill threshold of the traversal warps, slots and blocks per SM
-    static const int p_tlo = std::getenv("WPT_POOL_TLO") ? std::atoi(std::getenv("WPT_POOL_TLO")) : 20;
-    static const int p_minb = std::getenv("WPT_POOL_MINB") ? std::atoi(std::getenv("WPT_POOL_MINB")) : 4;
-    static const int p_slots = std::getenv("WPT_POOL_SLOTS") ? std::atoi(std::getenv("WPT_POOL_SLOTS")) : 384;
-    static const int p_chunk = std::getenv("WPT_POOL_CHUNK") ? std::atoi(std::getenv("WPT_POOL_CHUNK")) : 256;
-    static const int p_thi = std::getenv("WPT_POOL_THI") ? std::atoi(std::getenv("WPT_POOL_THI")) : 24;       // logic warps want at least this many paths
-    static const int p_tsw = std::getenv("WPT_POOL_TSWITCH") ? std::atoi(std::getenv("WPT_POOL_TSWITCH")) : 16;
-    P.t_lo = (uint32_t)p_tlo; P.t_hi = (uint32_t)p_thi; P.t_switch = (uint32_t)p_tsw; P.chunk = (uint32_t)p_chunk;
-    launch_pool(P, p_minb, (uint32_t)p_slots, stream);
+  if (cfg.engine == 4) {
+    // experimental warp-pool kernel (wpool.cu): grid = SMs x blocks per SM; every warp owns pool_ctx path contexts of 160 B
+    static const int w_minb = std::getenv("WPT_WPOOL_MINB") ? std::atoi(std::getenv("WPT_WPOOL_MINB")) : 8;
+    static const int w_ctx = std::getenv("WPT_WPOOL_CTX") ? std::atoi(std::getenv("WPT_WPOOL_CTX")) : 96;
+    static const int w_thi = std::getenv("WPT_WPOOL_THI") ? std::atoi(std::getenv("WPT_WPOOL_THI")) : 32;
+    static const int w_tlo = std::getenv("WPT_WPOOL_TLO") ? std::atoi(std::getenv("WPT_WPOOL_TLO")) : 16;
+    static const int w_tsw = std::getenv("WPT_WPOOL_TSWITCH") ? std::atoi(std::getenv("WPT_WPOOL_TSWITCH")) : 16;
+    static const int w_ref = std::getenv("WPT_WPOOL_REFILL") ? std::atoi(std::getenv("WPT_WPOOL_REFILL")) : 8;
+    const int minb = w_minb >= 12 ? 12 : w_minb >= 8 ? 8 : 6;
+    int grid = device_sm_count() * minb;
+    if (!P.nslots_dev) grid = std::min(grid, (int)((P.nslots + 127) / 128));
+    P.pool_ctx = (uint32_t)std::min(128, std::max(32, w_ctx));
+    d_pool.alloc((size_t)wpool_warps(device_sm_count() * minb) * P.pool_ctx * (wpool_ctx_bytes() / sizeof(float4)));
+    P.pool = d_pool.p;
+    P.t_hi = (uint32_t)w_thi; P.t_lo = (uint32_t)w_tlo; P.t_switch = (uint32_t)w_tsw; P.t_refill = (uint32_t)std::max(1, w_ref);
+    launch_wpool(P, grid, minb, stream);
   } else launch_mega(P, env_minb, stream);
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());
@@ -368,7 +375,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   rgba_stale = true;
 }
 
-// cfg.engine: 0 = persistent kernel k_mega (default), 1 = multi-kernel wavefront, 2 = block-pool kernel k_pool
+// cfg.engine: 0 = persistent path kernel k_mega (default), 1 = multi-kernel wavefront, 4 = experimental warp-pool kernel k_wpool
 void Context::run_paths(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp) {
   if (cfg.engine == 1) run_wavefront(render_type, d_spp_per_slot, uniform_spp);
   else run_persistent(render_type, d_spp_per_slot, uniform_spp);
@@ -411,7 +418,7 @@ void Context::stats(uint64_t out[8]) {
   WPT_CUDA(cudaStreamSynchronize(stream));
   if (std::getenv("WPT_DEBUG_COUNTERS")) {
     std::fprintf(stderr, "wpt counters:");
-    for (int i = 0; i < 14; i++) std::fprintf(stderr, " %llu", h_counters[i]);
+    for (int i = 0; i < 16; i++) std::fprintf(stderr, " %llu", h_counters[i]);
     std::fprintf(stderr, "\n");
   }
   out[0] = h_counters[0] + photon_rays; out[1] = h_counters[2]; out[2] = h_counters[1] + photon_visits;

@@ -131,7 +131,8 @@ struct Context {
   DevBuf<unsigned long long> a_stats, a_block_tot, a_block_suffix;
   std::function<void()> exchange_hook;   // multi-GPU: gather all rows' accumulators between adaptive rounds
   std::function<void(uint32_t*, uint64_t)> reduce_hook;   // multi-GPU: in-place sum-allreduce of 32-bit words on `stream` (photon batches)
-  DevBuf<float4> d_seg_buf;    // k_mega / k_pool: segment sums of a multi-segment launch (contract B10)
+  DevBuf<float4> d_seg_buf;    // k_wpool / k_mega: segment sums of a multi-segment launch (contract B10)
+  DevBuf<float4> d_pool;       // k_wpool: path contexts, 160 B each, pool_ctx per warp
   DevBuf<uint32_t> d_seg_cnt, d_seg_off, d_seg_list, d_pass_spp; DevBuf<uint8_t> d_scan_tmp;   // strategy rounds: segment list (contract B10)
   DevBuf<float4> d_seg_acc;    // wavefront engine: the running segment, per pixel
   DevBuf<uint32_t> ph_dense;   // one photon batch: [meta | light | loc_w x 4] per shot slot

@@ -124,7 +124,7 @@ struct Roots4 {
     v[i] = x; n++;
   }
 };
-__device__ __noinline__ void d_quadratic_normalized(double a1, double a0, Roots4& r) {
+static __device__ __noinline__ void d_quadratic_normalized(double a1, double a0, Roots4& r) {
   double disc = a1 * a1 - 4.0 * a0;
   if (disc < 0.0) return;
   double h = a1 / 2.0;
@@ -133,7 +133,7 @@ __device__ __noinline__ void d_quadratic_normalized(double a1, double a0, Roots4
   r.add(-h - sq / 2.0);
   r.add(-h + sq / 2.0);
 }
-__device__ __noinline__ void d_quadratic(double a2, double a1, double a0, Roots4& r) {
+static __device__ __noinline__ void d_quadratic(double a2, double a1, double a0, Roots4& r) {
   if (a2 == 0.0) { if (a1 != 0.0) r.add(-a0 / a1); return; }
   double disc = a1 * a1 - 4.0 * a2 * a0;
   if (disc < 0.0) return;
@@ -143,7 +143,7 @@ __device__ __noinline__ void d_quadratic(double a2, double a1, double a0, Roots4
   r.add((-a1 - sq) / a2x2);
   r.add((-a1 + sq) / a2x2);
 }
-__device__ __noinline__ void d_cubic_normalized(double a2, double a1, double a0, Roots4& out) {
+static __device__ __noinline__ void d_cubic_normalized(double a2, double a1, double a0, Roots4& out) {
   double q = (3.0 * a1 - a2 * a2) / 9.0;
   double r = (9.0 * a2 * a1 - 27.0 * a0 - 2.0 * a2 * a2 * a2) / 54.0;
   double q3 = q * q * q;
@@ -164,12 +164,12 @@ __device__ __noinline__ void d_cubic_normalized(double a2, double a1, double a0,
     if (s == t && s + t != 0.0) out.add(-(s + t) / 2.0 - a2_div_3);
   }
 }
-__device__ __noinline__ void d_cubic(double a3, double a2, double a1, double a0, Roots4& r) {
+static __device__ __noinline__ void d_cubic(double a3, double a2, double a1, double a0, Roots4& r) {
   if (a3 == 0.0) { d_quadratic(a2, a1, a0, r); return; }
   if (a2 == 0.0 && a1 == 0.0 && a0 == 0.0) { r.add(0.0); return; }
   d_cubic_normalized(a2 / a3, a1 / a3, a0 / a3, r);
 }
-__device__ __noinline__ void d_biquadratic(double a4, double a2, double a0, Roots4& out) {
+static __device__ __noinline__ void d_biquadratic(double a4, double a2, double a0, Roots4& out) {
   Roots4 q; q.n = 0;
   d_quadratic(a4, a2, a0, q);
   for (int i = 0; i < q.n; i++) {
@@ -178,7 +178,7 @@ __device__ __noinline__ void d_biquadratic(double a4, double a2, double a0, Root
     else if (x == 0.0) out.add(0.0);
   }
 }
-__device__ __noinline__ void d_quartic_depressed(double a2, double a1, double a0, Roots4& out) {
+static __device__ __noinline__ void d_quartic_depressed(double a2, double a1, double a0, Roots4& out) {
   if (a1 == 0.0) { d_biquadratic(1.0, a2, a0, out); return; }
   if (a0 == 0.0) { d_cubic_normalized(0.0, a2, a1, out); out.add(0.0); return; }
   double a2_pow_2 = a2 * a2;
@@ -201,7 +201,7 @@ __device__ __noinline__ void d_quartic_depressed(double a2, double a1, double a0
     for (int i = 0; i < rb.n; i++) out.add(rb.v[i]);
   }
 }
-__device__ __noinline__ void d_quartic(double a4, double a3, double a2, double a1, double a0, Roots4& out) {
+static __device__ __noinline__ void d_quartic(double a4, double a3, double a2, double a1, double a0, Roots4& out) {
   out.n = 0;
   if (a4 == 0.0) { d_cubic(a3, a2, a1, a0, out); return; }
   if (a0 == 0.0) { d_cubic(a4, a3, a2, a1, out); out.add(0.0); return; }
@@ -243,7 +243,7 @@ __device__ __noinline__ void d_quartic(double a4, double a3, double a2, double a
 
 // ------------------------------------------------------------------ primitives
 // Torus::trace, torus.rs:61-126. Returns hit distance (f32) and outward-or-flipped normal.
-__device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray& ray, float* t_out, F3* n_out, bool* entering_out = nullptr) {
+static __device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray& ray, float* t_out, F3* n_out, bool* entering_out = nullptr) {
   double a = (double)q1.x, b = (double)q1.y;
   F3 d = ray.o - xyz(q0);
   F3 e = ray.d;
@@ -655,7 +655,7 @@ WPT_DEV GHit trace_g_t(const DScene& sc, const Ray& ray) {
   return trav_result(tv);
 }
 // generic version (any scene, either BVH): probes, photon emission, the wavefront engine
-__device__ __noinline__ GHit trace_g(const DScene& sc, const Ray& ray) {
+static __device__ __noinline__ GHit trace_g(const DScene& sc, const Ray& ray) {
   return sc.bvh_kind == 4 ? trace_g_t<4, false>(sc, ray) : trace_g_t<2, false>(sc, ray);
 }
 

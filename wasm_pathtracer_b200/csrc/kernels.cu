@@ -26,286 +26,9 @@ int device_sm_count() {
 #define TRACE_THREADS 128
 #define SHADE_THREADS 128
 
-// ------------------------------------------------------------------ helpers
-WPT_DEV unsigned long long warp_sum_u64(unsigned long long v) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
-  return v;
-}
-
-// tracer.rs:176-191 — camera ray through pixel (x,y) with jitter (j1,j2)
-WPT_DEV Ray camera_ray(const DCamera& c, uint32_t x, uint32_t y, float j1, float j2) {
-  float fx = (((float)x + j1) * c.w_inv - 0.5f) * c.ar;
-  float fy = 0.5f - ((float)y + j2) * c.h_inv;
-  F3 p = normalize(f3(fx, fy, 0.8f));
-  F3 rx = f3(p.x, c.cx * p.y - c.sx * p.z, c.sx * p.y + c.cx * p.z);        // rot_x, vec3.rs:108-119
-  F3 ry = f3(c.cy * rx.x + c.sy * rx.z, rx.y, -c.sy * rx.x + c.cy * rx.z);  // rot_y, vec3.rs:95-106
-  return make_ray(f3(c.ox, c.oy, c.oz), ry);
-}
-
-// ------------------------------------------------------------------ PNEE light choice
-// PhotonTree::sample (photon_tree.rs:80-159) on the flattened octree.
-struct Cell { float x0, y0, z0, x1, y1, z1; };
-WPT_DEV uint32_t octree_child(Cell& b, F3 v) {   // photon_tree.rs:235-251
-  float cx = 0.5f * (b.x0 + b.x1), cy = 0.5f * (b.y0 + b.y1), cz = 0.5f * (b.z0 + b.z1);
-  uint32_t i = (v.x < cx ? 0u : 4u) + (v.y < cy ? 0u : 2u) + (v.z < cz ? 0u : 1u);
-  if (v.x < cx) b.x1 = cx; else b.x0 = cx;
-  if (v.y < cy) b.y1 = cy; else b.y0 = cy;
-  if (v.z < cz) b.z1 = cz; else b.z0 = cz;
-  return i;
-}
-WPT_DEV uint32_t tree_find_node(const DPhotonTree& t, uint32_t depth, F3 v) {   // find_node_cdf, photon_tree.rs:216-231
-  Cell b = {-1024.0f, -1024.0f, -1024.0f, 1024.0f, 1024.0f, 1024.0f};
-  uint32_t node = 0;
-  for (;;) {
-    uint32_t cb = __ldg(t.child_base + node);
-    if (cb == 0xFFFFFFFFu || depth == 0) return node;
-    node = cb + octree_child(b, v);
-    depth--;
-  }
-}
-WPT_DEV float tree_bin_prob(const DPhotonTree& t, uint32_t node, uint32_t i) {   // empirical_pdf.rs:64-75
-  const float* cum = t.cum + (size_t)node * t.num_lights;
-  if (i + 1 == t.num_lights) return 1.0f - __ldg(cum + i);
-  return __ldg(cum + i + 1) - __ldg(cum + i);
-}
-WPT_DEV void axis_weight(float v, float c, float lo, float hi, float sz, float* w, float* w_adj, float* off) {   // photon_tree.rs:90-124
-  // both branches of the reference end in one division by the cell size: select the numerator, divide once
-  const bool up = v > c;
-  const float num = up ? (hi - (v - sz * 0.5f)) : ((v + sz * 0.5f) - lo);
-  const float ww = num / sz;
-  *w = ww; *w_adj = 1.0f - ww; *off = up ? 1.0f : -1.0f;
-}
-// Same result as the reference's ten root-to-cell walks (find_leaf + find_node_cdf for the
-// sampled cell + 8 for the interpolated pdf) with one: find_leaf. The eight query points are
-// the corners of a box one cell wide, so each of the seven others lies in the face / edge /
-// corner neighbour of the leaf: `nbr[leaf][27]` holds, per direction, the node the reference's
-// walk to the leaf's depth ends in (same depth, or the shallower leaf covering it), computed on
-// the host with the same f32 halving. A corner is only taken from the table if its coordinate
-// really lies inside the neighbour interval (f32 rounding of v + size can put it on the far
-// boundary; cells touching the +-1024 cube are excluded too) — otherwise the walk is redone.
-WPT_DEV uint32_t tree_walk(const DPhotonTree& t, uint32_t depth, F3 q) {   // find_node_cdf, photon_tree.rs:216-231
-  Cell c = {-1024.0f, -1024.0f, -1024.0f, 1024.0f, 1024.0f, 1024.0f};
-  uint32_t nd = 0;
-  for (;;) {
-    uint32_t cb = __ldg(t.child_base + nd);
-    if (cb == 0xFFFFFFFFu || depth == 0) return nd;
-    nd = cb + octree_child(c, q);
-    depth--;
-  }
-}
-WPT_DEV void photon_sample_inl(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* light, float* pdf_out) {
-  const float size = 1024.0f;
-  if (v.x < -size || v.y < -size || v.z < -size || v.x > size || v.y > size || v.z > size) {
-    *light = rng.range(0, t.num_lights);
-    *pdf_out = 1.0f / (float)t.num_lights;
-    return;
-  }
-  // find_leaf (photon_tree.rs:201-211)
-  Cell b = {-size, -size, -size, size, size, size};
-  uint32_t depth = 0, node = 0;
-  for (;;) {
-    uint32_t cb = __ldg(t.child_base + node);
-    if (cb == 0xFFFFFFFFu) break;
-    node = cb + octree_child(b, v);
-    depth++;
-  }
-  float xs = b.x1 - b.x0, ys = b.y1 - b.y0, zs = b.z1 - b.z0;
-  float wx, ax, ox, wy, ay, oy, wz, az, oz;
-  axis_weight(v.x, 0.5f * (b.x0 + b.x1), b.x0, b.x1, xs, &wx, &ax, &ox);
-  axis_weight(v.y, 0.5f * (b.y0 + b.y1), b.y0, b.y1, ys, &wy, &ay, &oy);
-  axis_weight(v.z, 0.5f * (b.z0 + b.z1), b.z0, b.z1, zs, &wz, &az, &oz);
-  bool self_x = rng.f32() <= wx;
-  bool self_y = rng.f32() <= wy;
-  bool self_z = rng.f32() <= wz;
-  // neighbour coordinates: v + (ajx, 0, 0) etc. (photon_tree.rs:141-156); adding +-0.0 keeps v
-  const float X1 = v.x + xs * ox, Y1 = v.y + ys * oy, Z1 = v.z + zs * oz;
-  // is the shifted coordinate strictly inside the adjacent interval (and that inside the cube)?
-  bool okx = ox > 0.0f ? (X1 >= b.x1 && X1 < b.x1 + xs && b.x1 + xs <= size) : (X1 >= b.x0 - xs && X1 < b.x0 && b.x0 - xs >= -size);
-  bool oky = oy > 0.0f ? (Y1 >= b.y1 && Y1 < b.y1 + ys && b.y1 + ys <= size) : (Y1 >= b.y0 - ys && Y1 < b.y0 && b.y0 - ys >= -size);
-  bool okz = oz > 0.0f ? (Z1 >= b.z1 && Z1 < b.z1 + zs && b.z1 + zs <= size) : (Z1 >= b.z0 - zs && Z1 < b.z0 && b.z0 - zs >= -size);
-  const int dx = ox > 0.0f ? 2 : 0, dy = oy > 0.0f ? 2 : 0, dz = oz > 0.0f ? 2 : 0;   // direction index 0,1,2 = -1,0,+1
-  const uint32_t* nb = t.nbr + (size_t)node * 27;
-  uint32_t n8[8];
-  n8[0] = node;
-#pragma unroll
-  for (int k = 1; k < 8; k++) {
-    const bool bx = k & 1, by = k & 2, bz = k & 4;
-    bool ok = (!bx || okx) && (!by || oky) && (!bz || okz);
-    if (ok) n8[k] = __ldg(nb + (bx ? dx : 1) + 3 * (by ? dy : 1) + 9 * (bz ? dz : 1));
-    else n8[k] = tree_walk(t, depth, f3(bx ? X1 : v.x, by ? Y1 : v.y, bz ? Z1 : v.z));
-  }
-  // EmpiricalPDF::sample (empirical_pdf.rs:43-61) on the sampled cell
-  uint32_t sel = (self_x ? 0u : 1u) + (self_y ? 0u : 2u) + (self_z ? 0u : 4u);
-  uint32_t sn = n8[0];
-#pragma unroll
-  for (int k = 1; k < 8; k++) if (sel == (uint32_t)k) sn = n8[k];
-  const float* cum = t.cum + (size_t)sn * t.num_lights;
-  float r = rng.f32();
-  uint32_t low = 0, high = t.num_lights;
-  while (low + 1 < high) {
-    uint32_t mid = (low + high) / 2;
-    if (__ldg(cum + mid) <= r) low = mid; else high = mid;
-  }
-  uint32_t res = low;
-  // EmpiricalPDF::bin_prob (empirical_pdf.rs:64-75) of bin `res` in each of the eight cells: cum[res + 1] - cum[res], with
-  // 1.0 in place of cum[res + 1] for the last bin — the same subtraction either way, so the test is hoisted out
-  const bool last = res + 1 == t.num_lights;
-  const size_t L = t.num_lights;
-  auto bp = [&](uint32_t nd) { const float* c = t.cum + (size_t)nd * L + res; float a = __ldg(c); float hi = last ? 1.0f : __ldg(c + 1); return hi - a; };
-  float pdf = 0.0f;   // the reference's order of the eight terms (photon_tree.rs:149-156)
-  pdf += bp(n8[0]) * wx * wy * wz;
-  pdf += bp(n8[1]) * ax * wy * wz;
-  pdf += bp(n8[2]) * wx * ay * wz;
-  pdf += bp(n8[4]) * wx * wy * az;
-  pdf += bp(n8[3]) * ax * ay * wz;
-  pdf += bp(n8[6]) * wx * ay * az;
-  pdf += bp(n8[5]) * ax * wy * az;
-  pdf += bp(n8[7]) * ax * ay * az;
-  *light = res;
-  *pdf_out = pdf;
-}
-// out-of-line copy for the kernels that take the render type at run time (k_shade, k_pool, the sample-batch probe)
-__device__ __noinline__ void photon_sample(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* light, float* pdf_out) { photon_sample_inl(t, rng, v, light, pdf_out); }
-
-// Triangle::pick_random (triangle.rs:91-114) on light `li`
-WPT_DEV void pick_random(const DScene& sc, uint32_t li, Rng& rng, F3* p, F3* n, F3* intensity, float* area, uint32_t* shape_id) {
-  float4 na = __ldg(&sc.lights[li].n_area), in = __ldg(&sc.lights[li].intensity);
-  uint32_t sid = __float_as_uint(in.w);
-  const float4* q = reinterpret_cast<const float4*>(sc.shapes + sid);
-  F3 v0 = xyz(__ldg(q)), v1 = xyz(__ldg(q + 1)), v2 = xyz(__ldg(q + 2));
-  float r1 = rng.f32();
-  float r2 = rng.f32();
-  float r1s = sqrtf(r1);
-  *p = (1.0f - r1s) * v0 + (r1s * (1.0f - r2)) * v1 + (r2 * r1s) * v2;
-  F3 nn = xyz(na);
-  if (rng.f32() > 0.5f) nn = -nn;
-  *n = nn; *intensity = xyz(in); *area = na.w; *shape_id = sid;
-}
-
-// ------------------------------------------------------------------ shading of one hit
-// One bounce of trace_original_color (tracer.rs:237-329) after Scene::trace returned shape
-// `id` (-1: miss) for `ray`. Shared by the wavefront shade kernel and the persistent kernel so
-// that both evaluate exactly the same f32 expressions in the same order.
-struct PathRegs { F3 color, T; Rng rng; bool bounced; };
-struct ShadeOut {
-  bool finished;     // path ended at this vertex (miss / emitter): `color` is final
-  bool survive;      // Russian roulette outcome (only meaningful if !finished)
-  bool shadow;       // a shadow ray has to be traced; `contrib` is added if it is unoccluded
-  F3 next_o, next_d; // the bounce ray
-  F3 sh_o, sh_d; float sh_len; int sh_light; F3 contrib;
-};
-// RT: the render type when it is known at compile time (0 NoNEE, 1 NormalNEE, 2 PNEE: k_mega is instantiated per type — no
-// photon code in the NEE kernels, photon_sample inlined in the PNEE kernel: 9 % / 15 % faster than one kernel that branches
-// and calls), 3 = decided at run time (k_shade, k_pool: out-of-line photon_sample)
-template <bool SIMPLE, int RT = 3>
-WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_hit, PathRegs& ps, ShadeOut& out) {
-  const bool has_nee = RT == 3 ? rp.render_type != 0 : RT != 0;
-  out.finished = false; out.survive = false; out.shadow = false;
-  bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
-  bool entering = true; float2 uv = make_float2(0.0f, 0.0f);
-  if (id >= 0) {   // scene.rs:140
-    if (SIMPLE) { shape_hit_normal_tri_plane(rp.scene.shapes, (uint32_t)id, ray, &n, &mat); t = t_hit; some = true; }
-    else some = shape_trace_full<false>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat, &entering, &uv);
-  }
-  if (!some) {   // tracer.rs:325-328
-    ps.color = ps.color + ps.T * f3(rp.scene.bg_r, rp.scene.bg_g, rp.scene.bg_b);
-    out.finished = true;
-    return;
-  }
-  float4 mc = __ldg(&rp.scene.mats[mat].c);
-  F3 hit_point = ray.o + t * ray.d;
-  if (mc.w == (float)MAT_EMISSIVE) {   // emissive, tracer.rs:245-254
-    if (rp.light_debug ? !ps.bounced : (!has_nee || !ps.bounced)) ps.color = ps.color + ps.T * xyz(mc);
-    out.finished = true;
-    return;
-  }
-  if (!SIMPLE && mc.w != (float)MAT_DIFFUSE) {   // ---- extension materials (parity unpinned)
-    float4 mp = __ldg(&rp.scene.mats[mat].p);
-    if (mc.w == (float)MAT_DIFFUSE_TEX) {   // Texture::at, texture.rs:23-31 (`as u32` saturates)
-      const DTexture tx = rp.scene.tex[__float_as_uint(mp.y)];
-      float fu = floorf(uv.x * (float)tx.width), fv = floorf(uv.y * (float)tx.height);
-      uint32_t iu = !(fu > 0.0f) ? 0u : (fu >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fu);
-      uint32_t iv = !(fv > 0.0f) ? 0u : (fv >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)fv);
-      const uint8_t* px = tx.rgb + (size_t)((iv % tx.height) * tx.width + (iu % tx.width)) * 3;
-      mc.x = (float)px[0] / 255.0f; mc.y = (float)px[1] / 255.0f; mc.z = (float)px[2] / 255.0f;
-    } else if (mc.w == (float)MAT_REFRACT || ps.rng.f32() < mp.x) {   // specular bounce (Reflect draws its share first)
-      F3 d = ray.d, wi;
-      float cos_in = dot(-d, n);
-      if (mc.w == (float)MAT_REFLECT) {
-        wi = (2.0f * cos_in) * n - (-d);   // Vec3::reflect, vec3.rs:85-87
-        ps.T = ps.T * xyz(mc);
-      } else {
-        float n1 = entering ? 1.0f : mp.x, n2 = entering ? mp.x : 1.0f;
-        if (!entering) ps.T = ps.T * f3(shared_exp_neg(mc.x * t), shared_exp_neg(mc.y * t), shared_exp_neg(mc.z * t));   // Beer's law
-        float r0 = (n1 - n2) / (n1 + n2); r0 = r0 * r0;   // Schlick with total internal reflection
-        float cosx = cos_in; bool tir = false;
-        if (n1 > n2) { float nr = n1 / n2; float sin2 = nr * nr * (1.0f - cosx * cosx); if (sin2 > 1.0f) tir = true; else cosx = sqrtf(1.0f - sin2); }
-        float x = 1.0f - cosx;
-        float fres = tir ? 1.0f : r0 + (1.0f - r0) * x * x * x * x * x;
-        if (ps.rng.f32() < fres) wi = (2.0f * cos_in) * n - (-d);
-        else {
-          float eta = n1 / n2;
-          float k = 1.0f - eta * eta * (1.0f - cos_in * cos_in);
-          wi = normalize(eta * d + (eta * cos_in - sqrtf(fmaxf(k, 0.0f))) * n);
-        }
-      }
-      out.next_o = hit_point + wi * WPT_EPSILON;
-      out.next_d = wi;
-      ps.bounced = false;   // a light seen through a specular bounce is not covered by NEE
-      float keep = fmaxf(fminf(fmaxf(fmaxf(ps.T.x, ps.T.y), ps.T.z), 0.9f), 0.1f);
-      out.survive = ps.rng.f32() < keep;
-      if (out.survive) ps.T = ps.T * (1.0f / keep);
-      return;
-    }
-  }
-  // material.rs:97-118 cosine-weighted bounce
-  float r1 = ps.rng.f32();
-  float r2 = ps.rng.f32();
-  float sa, ca;
-  shared_sincos(2.0f * WPT_PI * r1, &sa, &ca);
-  float x = ca * sqrtf(1.0f - r2);
-  float y = sqrtf(r2);
-  float z = sa * sqrtf(1.0f - r2);
-  F3 xn = orthogonal(n);
-  F3 zn = cross(n, xn);
-  F3 wi = normalize(x * xn + y * n + z * zn);
-  float pdf = dot(wi, n) / WPT_PI;
-  const float inv_pi = 1.0f / WPT_PI;   // Color3 / f32 = self * (1/v), clamped (color3.rs:54-95)
-  F3 brdf = f3(fminf(1.0f, fmaxf(0.0f, inv_pi * mc.x)), fminf(1.0f, fmaxf(0.0f, inv_pi * mc.y)), fminf(1.0f, fmaxf(0.0f, inv_pi * mc.z)));
-  float cos_i = dot(wi, n);
-  ps.T = ps.T * brdf * cos_i / pdf;   // tracer.rs:262
-  out.next_o = hit_point + wi * WPT_EPSILON;
-  out.next_d = wi;
-  ps.bounced = true;
-  if (has_nee) {   // tracer.rs:267-313
-    uint32_t light_id; float chance;
-    if (RT == 2) photon_sample_inl(rp.photons, ps.rng, hit_point, &light_id, &chance);
-    else if (RT == 3 && rp.render_type == 2) photon_sample(rp.photons, ps.rng, hit_point, &light_id, &chance);
-    else { light_id = ps.rng.range(0, rp.scene.num_lights); chance = 1.0f / (float)rp.scene.num_lights; }
-    F3 pl, ln, inten; float area; uint32_t lsid;
-    pick_random(rp.scene, light_id, ps.rng, &pl, &ln, &inten, &area, &lsid);
-    F3 to_light = pl - hit_point;
-    float dsq = dot(to_light, to_light);
-    float dlen = sqrtf(dsq);
-    to_light = to_light / dlen;
-    float cos_i2 = dot(to_light, n);
-    float cos_o = dot(-to_light, ln);
-    if (cos_i2 > 0.0f && cos_o > 0.0f) {
-      if (rp.light_debug) ps.color = ps.color + ps.T * inten;
-      else {
-        float solid_angle = (area * cos_o) / dsq;
-        out.contrib = ps.T * inten * solid_angle * cos_i2 * (1.0f / chance);
-        out.sh_o = hit_point + to_light * WPT_EPSILON;   // scene.rs:108
-        out.sh_d = to_light; out.sh_len = dlen; out.sh_light = (int)lsid;
-        out.shadow = true;
-      }
-    }
-  }
-  // Russian roulette, tracer.rs:318-324
-  float keep = fmaxf(fminf(fmaxf(fmaxf(ps.T.x, ps.T.y), ps.T.z), 0.9f), 0.1f);
-  out.survive = ps.rng.f32() < keep;
-  if (out.survive) ps.T = ps.T * (1.0f / keep);
-}
+}  // namespace wpt
+#include "device_shade.cuh"
+namespace wpt {
 
 // ------------------------------------------------------------------ slot setup
 __global__ void k_setup_slots(PathState st, const uint32_t* __restrict__ spp_per_slot, uint32_t uniform_spp, const float4* __restrict__ accum) {
@@ -723,434 +446,6 @@ void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s
   const int v = (P.simple_scene ? 0 : 2) + (b4 ? 1 : 0);
   if (P.simple_scene) { if (b4) launch_mega_rt<4, true>(P, blocks_per_sm[v], s); else launch_mega_rt<2, true>(P, blocks_per_sm[v], s); }
   else { if (b4) launch_mega_rt<4, false>(P, blocks_per_sm[v], s); else launch_mega_rt<2, false>(P, blocks_per_sm[v], s); }
-}
-
-// ------------------------------------------------------------------ block-pool path kernel
-// k_pool: k_mega's two stages decoupled from the lanes. A block owns S path slots whose state is
-// parked in shared memory (SoA, 33 words per slot); a slot is always in exactly one place: the
-// logic queue qL, the traversal queue qT, the registers of a lane in logic mode, or (its ray only)
-// the registers of a lane in traversal mode. Warps are symmetric and change mode only when they
-// hold nothing:
-//   logic mode     — empty lanes pop slots from qL; the two-half logic pass of k_mega runs on
-//                    all 32 lanes; lanes whose new ray has to enter the BVH park their state and
-//                    push the slot to qT (their ray ended at the root guard otherwise — 85 % of
-//                    the bunny scene's rays — and they just carry on).
-//   traversal mode — Aila & Laine's persistent while-while loop with refill: when few lanes are
-//                    still traversing, the idle ones pop new rays from qT; a finished lane writes
-//                    (t, id) into its slot and pushes it to qL.
-// So the shading code and the traversal loop each run with (almost) full warps instead of the
-// ~11 of 32 lanes k_mega reaches with one path pinned per lane. Pixels are handed out from a
-// block-level chunk of the global slot queue (slots are in 8x4 tile order). A pixel's samples are
-// still run one after the other by its slot, so the accumulation order — and every bit of the
-// result — is unchanged.
-#define POOL_THREADS 256
-#define POOL_NF 34
-#define POOL_EMPTY 0xFFFFFFFFu
-enum : int { PQ_HEAD = 0, PQ_TAIL = 1, PQ_COUNT = 2 };
-enum : int { PC_L = 0, PC_T = 4, PC_RETIRED = 8, PC_LOCK = 9, PC_EXH = 10, PC_CHUNK = 12 /* 64-bit, 8-byte aligned */, PC_WORDS = 16 };
-// state words
-enum : int { PF_O = 0, PF_D = 3, PF_T = 6, PF_COL = 9, PF_RNG = 12, PF_PIX = 13, PF_S = 14, PF_SEND = 15, PF_ACC = 16, PF_FLAGS = 19,
-             PF_RT = 20, PF_RID = 21, PF_EXO = 22, PF_EXD = 25, PF_CON = 28, PF_SHLEN = 31, PF_SHLIGHT = 32, PF_SLOT = 33 };
-
-// one lane reads the control word, every lane gets the same value (keeps the branches around the ballots uniform)
-WPT_DEV uint32_t pool_peek(volatile uint32_t* p, unsigned lane) {
-  uint32_t v = 0;
-  if (lane == 0) v = *p;
-  return __shfl_sync(0xFFFFFFFFu, v, 0);
-}
-// pop up to `want` entries for the lanes with `wants` (rank = index among them). Returns the number taken.
-__device__ __noinline__ uint32_t pool_pop(volatile uint32_t* q, volatile uint32_t* ring, uint32_t mask, uint32_t want, unsigned lane, bool wants, uint32_t rank, uint32_t* item) {
-  uint32_t take = 0, pos = 0;
-  if (lane == 0) {
-    uint32_t c = q[PQ_COUNT];
-    while (c != 0) {
-      uint32_t t = min(c, want);
-      uint32_t old = atomicCAS(const_cast<uint32_t*>(q + PQ_COUNT), c, c - t);
-      if (old == c) { take = t; break; }
-      c = old;
-    }
-    if (take) pos = atomicAdd(const_cast<uint32_t*>(q + PQ_HEAD), take);
-  }
-  take = __shfl_sync(0xFFFFFFFFu, take, 0);
-  pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-  if (wants && rank < take) {
-    uint32_t idx = (pos + rank) & mask, v;
-    while ((v = ring[idx]) == POOL_EMPTY) {}   // the producer reserved this entry and is about to write it
-    ring[idx] = POOL_EMPTY;
-    *item = v;
-  }
-  __threadfence_block();
-  return take;
-}
-// push `item` of every lane with `has`
-__device__ __noinline__ void pool_push(volatile uint32_t* q, volatile uint32_t* ring, uint32_t mask, unsigned lane, bool has, uint32_t item) {
-  unsigned m = __ballot_sync(0xFFFFFFFFu, has);
-  if (!m) return;
-  uint32_t n = (uint32_t)__popc(m), pos = 0;
-  if (lane == 0) pos = atomicAdd(const_cast<uint32_t*>(q + PQ_TAIL), n);
-  pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-  __threadfence_block();   // the slot's state is written before the entry becomes visible
-  if (has) ring[(pos + (uint32_t)__popc(m & ((1u << lane) - 1u))) & mask] = item;
-  __syncwarp();
-  if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<uint32_t*>(q + PQ_COUNT), n); }
-}
-// lane 0 only: take up to n consecutive global slots from the block's chunk (refilled from the global queue)
-__device__ __noinline__ void pool_pixels(volatile uint32_t* ctrl, uint32_t* work_counter, uint32_t chunk, uint32_t nslots, uint32_t n, uint32_t* base, uint32_t* k) {
-  volatile unsigned long long* pc = reinterpret_cast<volatile unsigned long long*>(ctrl + PC_CHUNK);
-  *k = 0; *base = 0;
-  for (;;) {
-    unsigned long long cur = *pc;
-    uint32_t nx = (uint32_t)cur, en = (uint32_t)(cur >> 32);
-    if (nx < en) {
-      uint32_t t = min(n, en - nx);
-      if (atomicCAS(const_cast<unsigned long long*>(pc), cur, ((unsigned long long)en << 32) | (nx + t)) == cur) { *base = nx; *k = t; return; }
-      continue;
-    }
-    if (ctrl[PC_EXH]) return;
-    if (atomicCAS(const_cast<uint32_t*>(ctrl + PC_LOCK), 0u, 1u) == 0u) {
-      cur = *pc; nx = (uint32_t)cur; en = (uint32_t)(cur >> 32);
-      if (nx >= en && !ctrl[PC_EXH]) {
-        uint32_t b = atomicAdd(work_counter, chunk);
-        if (b >= nslots) ctrl[PC_EXH] = 1u;
-        else *pc = ((unsigned long long)min(b + chunk, nslots) << 32) | b;
-      }
-      __threadfence_block();
-      atomicExch(const_cast<uint32_t*>(ctrl + PC_LOCK), 0u);
-    } else __nanosleep(40);
-  }
-}
-
-// park a path: write its state into its slot. The shadow-ray fields are only live while a
-// shadow ray is pending.
-template <bool FLUSH>
-WPT_DEV void pool_store(uint32_t* stw, float* stf, uint32_t S, uint32_t home, F3 ro, F3 rd, const PathRegs& ps, uint32_t pix, uint32_t slot_id, uint32_t s, uint32_t s_end, F3 acc_rgb,
-                        int what, bool alive_after_shadow, bool haspix, float res_t, int res_id, F3 ext_o, F3 ext_d, F3 contrib, float sh_len, int sh_light) {
-  uint32_t* w = stw + home; float* f = stf + home;
-  f[(PF_O + 0) * S] = ro.x; f[(PF_O + 1) * S] = ro.y; f[(PF_O + 2) * S] = ro.z;
-  f[(PF_D + 0) * S] = rd.x; f[(PF_D + 1) * S] = rd.y; f[(PF_D + 2) * S] = rd.z;
-  f[(PF_T + 0) * S] = ps.T.x; f[(PF_T + 1) * S] = ps.T.y; f[(PF_T + 2) * S] = ps.T.z;
-  f[(PF_COL + 0) * S] = ps.color.x; f[(PF_COL + 1) * S] = ps.color.y; f[(PF_COL + 2) * S] = ps.color.z;
-  w[PF_RNG * S] = ps.rng.s; w[PF_PIX * S] = pix; w[PF_S * S] = s; w[PF_SEND * S] = s_end; w[PF_SLOT * S] = slot_id;
-  f[(PF_ACC + 0) * S] = acc_rgb.x; f[(PF_ACC + 1) * S] = acc_rgb.y; f[(PF_ACC + 2) * S] = acc_rgb.z;
-  w[PF_FLAGS * S] = (uint32_t)what | (ps.bounced ? 4u : 0u) | (alive_after_shadow ? 8u : 0u) | (haspix ? 16u : 0u);
-  f[PF_RT * S] = res_t; w[PF_RID * S] = (uint32_t)res_id;
-  if (what == ST_SHADOW) {
-    f[(PF_EXO + 0) * S] = ext_o.x; f[(PF_EXO + 1) * S] = ext_o.y; f[(PF_EXO + 2) * S] = ext_o.z;
-    f[(PF_EXD + 0) * S] = ext_d.x; f[(PF_EXD + 1) * S] = ext_d.y; f[(PF_EXD + 2) * S] = ext_d.z;
-    f[(PF_CON + 0) * S] = contrib.x; f[(PF_CON + 1) * S] = contrib.y; f[(PF_CON + 2) * S] = contrib.z;
-    f[PF_SHLEN * S] = sh_len; w[PF_SHLIGHT * S] = (uint32_t)sh_light;
-  }
-}
-
-template <int BVH, bool SIMPLE, int MINB>
-__global__ void __launch_bounds__(POOL_THREADS, MINB) k_pool(MegaParams P, uint32_t S, uint32_t cap) {
-  extern __shared__ __align__(16) uint32_t pool_smem[];
-  volatile uint32_t* ctrl = pool_smem;
-  volatile uint32_t* ringL = pool_smem + PC_WORDS;
-  volatile uint32_t* ringT = ringL + cap;
-  uint32_t* stw = pool_smem + PC_WORDS + 2 * cap;          // state word f of slot i: stw[f * S + i]
-  float* stf = reinterpret_cast<float*>(stw);
-  const uint32_t mask = cap - 1u;
-  const DScene& sc = P.rp.scene;
-  const unsigned FULL = 0xFFFFFFFFu;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt = (1u << lane) - 1u;
-  uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
-  uint32_t c_rays = 0, c_visits = 0, c_prims = 0, c_paths = 0;
-#ifdef POOL_INSTR
-  unsigned long long i_lp = 0, i_lh = 0, i_ls = 0, i_tp = 0, i_ta = 0, i_idle = 0, i_flush = 0, i_ts = 0, i_tl = 0, i_sw = 0;
-#endif
-
-  // ---- block setup: every slot starts in qL without a pixel
-  for (uint32_t i = threadIdx.x; i < PC_WORDS; i += POOL_THREADS) pool_smem[i] = 0u;
-  for (uint32_t i = threadIdx.x; i < cap; i += POOL_THREADS) { ringL[i] = i < S ? i : POOL_EMPTY; ringT[i] = POOL_EMPTY; }
-  for (uint32_t i = threadIdx.x; i < S * POOL_NF; i += POOL_THREADS) stw[i] = 0u;
-  __syncthreads();
-  if (threadIdx.x == 0) { ctrl[PC_L + PQ_TAIL] = S; ctrl[PC_L + PQ_COUNT] = S; }
-  __syncthreads();
-
-  bool in_logic = true;
-  for (;;) {
-    if (in_logic) {
-      // =============================================================== logic mode
-      bool have = false, pend = false, haspix = false, alive_after_shadow = false;
-      int what = ST_GEN;
-      uint32_t home = 0, pix = 0, s = 0, s_end = 0, slot_id = 0;
-      PathRegs ps; ps.color = f3(0, 0, 0); ps.T = f3(1, 1, 1); ps.rng.s = 1u; ps.bounced = false;
-      F3 ro = f3(0, 0, 0), rd = f3(1, 1, 1), acc_rgb = f3(0, 0, 0);
-      F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
-      float sh_len = 0.0f, res_t = 0.0f; int sh_light = -1, res_id = -1;
-      bool leave = false, finished = false;
-      while (!leave) {
-        // ---- refill policy. A warp that holds few paths and cannot top up from qL does not keep
-        // running thin passes: it hands its paths back to qL (another logic warp consolidates
-        // them) and goes traversing. An empty warp goes where the work is.
-        unsigned hv = __ballot_sync(FULL, have);
-        uint32_t n_have = (uint32_t)__popc(hv);
-        if (n_have < 32u) {
-          uint32_t availL = pool_peek(ctrl + PC_L + PQ_COUNT, lane);
-          bool refill = availL != 0u;
-          if (n_have + availL < P.t_hi) {   // would stay under-filled
-            uint32_t availT = pool_peek(ctrl + PC_T + PQ_COUNT, lane);
-            if (availT >= P.t_switch || (n_have == 0u && availL == 0u && availT != 0u)) {
-              if (n_have) {   // flush: these paths are logic-ready (their result is in res_t / res_id)
-                if (have) pool_store<true>(stw, stf, S, home, ro, rd, ps, pix, slot_id, s, s_end, acc_rgb, what, alive_after_shadow, haspix, res_t, res_id, ext_o, ext_d, contrib, sh_len, sh_light);
-                pool_push(ctrl + PC_L, ringL, mask, lane, have, home);
-                have = false;
-              }
-              in_logic = false; leave = true;
-#ifdef POOL_INSTR
-              i_flush += n_have; i_sw += 1;
-#endif
-              continue;
-            }
-          }
-          if (refill) {
-            unsigned em = ~hv;
-            uint32_t item = 0, rank = (uint32_t)__popc(em & lt);
-            uint32_t got = pool_pop(ctrl + PC_L, ringL, mask, 32u - n_have, lane, !have, rank, &item);
-            if (!have && rank < got) {
-              home = item; have = true; pend = false;
-              const uint32_t* w = stw + home; const float* f = stf + home;
-              ro = f3(f[(PF_O + 0) * S], f[(PF_O + 1) * S], f[(PF_O + 2) * S]);
-              rd = f3(f[(PF_D + 0) * S], f[(PF_D + 1) * S], f[(PF_D + 2) * S]);
-              ps.T = f3(f[(PF_T + 0) * S], f[(PF_T + 1) * S], f[(PF_T + 2) * S]);
-              ps.color = f3(f[(PF_COL + 0) * S], f[(PF_COL + 1) * S], f[(PF_COL + 2) * S]);
-              ps.rng.s = w[PF_RNG * S]; pix = w[PF_PIX * S]; s = w[PF_S * S]; s_end = w[PF_SEND * S]; slot_id = w[PF_SLOT * S];
-              acc_rgb = f3(f[(PF_ACC + 0) * S], f[(PF_ACC + 1) * S], f[(PF_ACC + 2) * S]);
-              uint32_t fl = w[PF_FLAGS * S];
-              what = (int)(fl & 3u); ps.bounced = (fl & 4u) != 0; alive_after_shadow = (fl & 8u) != 0; haspix = (fl & 16u) != 0;
-              res_t = f[PF_RT * S]; res_id = (int)w[PF_RID * S];
-              if (what == ST_SHADOW) {
-                ext_o = f3(f[(PF_EXO + 0) * S], f[(PF_EXO + 1) * S], f[(PF_EXO + 2) * S]);
-                ext_d = f3(f[(PF_EXD + 0) * S], f[(PF_EXD + 1) * S], f[(PF_EXD + 2) * S]);
-                contrib = f3(f[(PF_CON + 0) * S], f[(PF_CON + 1) * S], f[(PF_CON + 2) * S]);
-                sh_len = f[PF_SHLEN * S]; sh_light = (int)w[PF_SHLIGHT * S];
-              }
-            }
-            hv = __ballot_sync(FULL, have);
-          }
-        }
-        if (!hv) {   // this warp holds nothing and found nothing
-          if (pool_peek(ctrl + PC_T + PQ_COUNT, lane) != 0u) { in_logic = false; leave = true; }
-          else if (pool_peek(ctrl + PC_RETIRED, lane) >= S) { finished = true; leave = true; }
-          else {
-            __nanosleep(200);
-#ifdef POOL_INSTR
-            i_idle += 1;
-#endif
-          }
-          continue;
-        }
-#ifdef POOL_INSTR
-        i_lp += 1; i_lh += __popc(hv);
-#endif
-        // ---- pixels for the lanes whose slot has none
-        bool needpix = have && what == ST_GEN && !haspix;
-        unsigned nm = __ballot_sync(FULL, needpix);
-        if (nm) {
-          uint32_t base = 0, k = 0;
-          if (lane == 0) pool_pixels(ctrl, P.work_counter, P.chunk, P.nslots_dev ? *P.nslots_dev : P.nslots, (uint32_t)__popc(nm), &base, &k);
-          base = __shfl_sync(FULL, base, 0); k = __shfl_sync(FULL, k, 0);
-          bool retire = false;
-          if (needpix) {
-            uint32_t rank = (uint32_t)__popc(nm & lt);
-            if (rank < k) {
-              uint32_t idx = base + rank, pslot = idx, j = 0;
-              if (P.seg_list) { uint32_t e = P.seg_list[idx]; pslot = e >> 3; j = e & 7u; }
-              else if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
-              slot_id = idx;
-              pix = P.pixel[pslot];
-              uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;
-              uint32_t s0 = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
-              uint32_t b = min(j * P.seg_len, spp);
-              s = s0 + b;
-              s_end = s0 + min(b + P.seg_len, spp);
-              acc_rgb = f3(0.0f, 0.0f, 0.0f);   // contract B10: segment sum from +0
-              haspix = true;
-            } else if (k == 0) { retire = true; have = false; }   // the global queue is exhausted: the slot retires
-          }
-          unsigned rm = __ballot_sync(FULL, retire);
-          if (rm && lane == 0) atomicAdd(const_cast<uint32_t*>(ctrl + PC_RETIRED), (uint32_t)__popc(rm));
-        }
-        // ---- logic pass, two halves (see k_mega)
-#pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-#ifdef POOL_INSTR
-          if (half == 1) i_ls += __popc(__ballot_sync(FULL, have && !pend && haspix && what == ST_EXTEND));
-#endif
-          if (!have || pend || !haspix) continue;
-          bool start = false;
-          if (what == (half == 0 ? ST_SHADOW : ST_EXTEND)) {
-            bool finish = false;
-            if (half == 0) {   // Scene::shadow_ray, scene.rs:114-132
-              bool occluded = res_id >= 0 && res_t < sh_len && res_id != sh_light;
-              if (!occluded) ps.color = ps.color + contrib;
-              if (alive_after_shadow) { ro = ext_o; rd = ext_d; what = ST_EXTEND; start = true; }
-              else finish = true;
-            } else {
-              ShadeOut so;
-              Ray ray; ray.o = ro; ray.d = rd; ray.inv = f3(0, 0, 0);   // triangles / planes: shading reads origin and direction only
-              if (!SIMPLE) ray = make_ray(ro, rd);
-              shade_hit<SIMPLE>(P.rp, ray, res_id, res_t, ps, so);
-              if (so.finished) finish = true;
-              else if (so.shadow) {
-                ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
-                alive_after_shadow = so.survive;
-                ro = so.sh_o; rd = so.sh_d; what = ST_SHADOW; start = true;
-              } else if (so.survive) { ro = so.next_o; rd = so.next_d; what = ST_EXTEND; start = true; }
-              else finish = true;
-            }
-            if (finish) { acc_rgb = acc_rgb + ps.color; c_paths += 1; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
-          }
-          if (what == ST_GEN) {
-            if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream
-              ps.rng.s = stream_seed(pix, s, STREAM_PATH, P.rp.base_seed);
-              float j1 = ps.rng.f32();
-              float j2 = ps.rng.f32();
-              uint32_t py = pix / P.rp.W, px = pix - py * P.rp.W;
-              Ray cr = camera_ray(P.rp.cam, px, py, j1, j2);
-              ro = cr.o; rd = cr.d;
-              ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
-              what = ST_EXTEND; start = true;
-            } else {
-              if (P.nseg > 1 || P.seg_list) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
-              else {
-                float4 a = P.accum[pix];
-                P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));
-              }
-              haspix = false;
-            }
-          }
-          if (start) {
-            Ray ray = make_ray(ro, rd);
-            Trav tv;
-            bool enter = trav_begin<BVH, SIMPLE>(sc, ray, tv);
-            res_t = tv.inf_t; res_id = tv.inf_id;   // the result if the BVH is not entered; the request otherwise
-            if (enter) pend = true;
-            else { c_rays += 1; c_visits += tv.visits; }
-          }
-        }
-        // ---- park the lanes whose ray has to traverse the BVH
-        bool park = have && pend;
-        if (__ballot_sync(FULL, park)) {
-          if (park) pool_store<false>(stw, stf, S, home, ro, rd, ps, pix, slot_id, s, s_end, acc_rgb, what, alive_after_shadow, haspix, res_t, res_id, ext_o, ext_d, contrib, sh_len, sh_light);
-          pool_push(ctrl + PC_T, ringT, mask, lane, park, home);
-          if (park) { have = false; pend = false; }
-        }
-      }
-      if (finished) break;
-    } else {
-      // =============================================================== traversal mode
-      bool act = false; uint32_t home = 0;
-      Ray ray = make_ray(f3(0, 0, 0), f3(1, 1, 1));
-      Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0;
-      bool leave = false, finished = false;
-      while (!leave) {
-        unsigned am = __ballot_sync(FULL, act);
-        if ((uint32_t)__popc(am) <= P.t_lo && pool_peek(ctrl + PC_T + PQ_COUNT, lane) != 0u) {   // refill the idle lanes from qT
-          uint32_t item = 0, rank = (uint32_t)__popc(~am & lt);
-          uint32_t got = pool_pop(ctrl + PC_T, ringT, mask, 32u - (uint32_t)__popc(am), lane, !act, rank, &item);
-          if (!act && rank < got) {
-            home = item; act = true;
-            const float* f = stf + home;
-            F3 o = f3(f[(PF_O + 0) * S], f[(PF_O + 1) * S], f[(PF_O + 2) * S]);
-            F3 d = f3(f[(PF_D + 0) * S], f[(PF_D + 1) * S], f[(PF_D + 2) * S]);
-            ray = make_ray(o, d);
-            tv.inf_t = f[PF_RT * S]; tv.inf_id = (int)stw[PF_RID * S + home];
-            tv.bound = tv.inf_id >= 0 ? tv.inf_t : WPT_INF;   // as trav_begin left it
-            tv.best_id = -1; tv.sp = 0; tv.prims = 0;
-            if (BVH == 4) { tv.lf = 0u; tv.cnt = 0u; tv.visits = 0; }
-            else {
-              float4 rb = __ldg(reinterpret_cast<const float4*>(sc.nodes2) + 1);
-              tv.lf = __float_as_uint(rb.z); tv.cnt = __float_as_uint(rb.w); tv.visits = 1;   // the root guard was counted (scene.rs:207)
-            }
-          }
-          am = __ballot_sync(FULL, act);
-        }
-        if (!am) {
-          if (pool_peek(ctrl + PC_L + PQ_COUNT, lane) != 0u) { in_logic = true; leave = true; }
-          else if (pool_peek(ctrl + PC_RETIRED, lane) >= S) { finished = true; leave = true; }
-          else __nanosleep(200);
-          continue;
-        }
-#ifdef POOL_INSTR
-        i_tp += 1; i_ta += __popc(am);
-#endif
-        // ---- while-while burst: inner steps until (almost) every traversing lane waits at a leaf,
-        // then one leaf step; lanes that finish drop out. Leave when a refill is worthwhile.
-        bool fin = false;
-        unsigned trav = am;
-        do {
-          const bool tr = act && !fin;
-          const bool leaf = tr && trav_at_leaf<BVH>(tv);
-          const int n_inner = __popc(__ballot_sync(FULL, tr && !leaf));
-          bool need_pop = false;
-          if (n_inner == __popc(trav) || n_inner * (int)P.t_inner > __popc(trav)) {
-#ifdef POOL_INSTR
-            i_ts += 1; i_tl += n_inner;
-#endif
-            if (tr && !leaf) need_pop = trav_inner<BVH>(sc, ray, tv, stack_n, stack_d);
-          } else if (leaf) { trav_leaf<BVH, SIMPLE>(sc, ray, tv); need_pop = true; }
-          if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) fin = true;
-          trav = __ballot_sync(FULL, act && !fin);
-        } while ((uint32_t)__popc(trav) > P.t_lo);
-        // ---- finished lanes hand their slot back to the logic queue
-        if (fin) {
-          GHit g = trav_result(tv);
-          stf[PF_RT * S + home] = g.t; stw[PF_RID * S + home] = (uint32_t)g.id;
-          c_rays += 1; c_visits += g.visits; c_prims += g.prims;
-        }
-        pool_push(ctrl + PC_L, ringL, mask, lane, fin, home);
-        if (fin) act = false;
-      }
-      if (finished) break;
-    }
-  }
-  // ---- counters
-  unsigned long long r = warp_sum_u64(c_rays), v = warp_sum_u64(c_visits), pr = warp_sum_u64(c_prims), pa = warp_sum_u64(c_paths);
-  if (lane == 0 && (r | pa)) {
-    atomicAdd(&P.counters[0], r); atomicAdd(&P.counters[1], v); atomicAdd(&P.counters[2], pa); atomicAdd(&P.counters[3], pr);
-  }
-#ifdef POOL_INSTR
-  if (lane == 0) {
-    atomicAdd(&P.counters[4], i_lp); atomicAdd(&P.counters[5], i_lh); atomicAdd(&P.counters[6], i_ls); atomicAdd(&P.counters[7], i_tp);
-    atomicAdd(&P.counters[8], i_ta); atomicAdd(&P.counters[9], i_idle); atomicAdd(&P.counters[10], i_flush); atomicAdd(&P.counters[11], i_ts);
-    atomicAdd(&P.counters[12], i_tl); atomicAdd(&P.counters[13], i_sw);
-  }
-#endif
-}
-
-size_t pool_smem_bytes(uint32_t S, uint32_t cap) { return (size_t)(PC_WORDS + 2 * cap + S * POOL_NF) * sizeof(uint32_t); }
-
-template <int BVH, bool SIMPLE, int MINB>
-static void launch_pool_t(const MegaParams& P, uint32_t S, uint32_t cap, int grid, cudaStream_t s) {
-  size_t bytes = pool_smem_bytes(S, cap);
-  static size_t configured = 0;
-  if (configured != bytes) {
-    cudaFuncSetAttribute(k_pool<BVH, SIMPLE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    cudaFuncSetAttribute(k_pool<BVH, SIMPLE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = bytes;
-  }
-  k_pool<BVH, SIMPLE, MINB><<<grid, POOL_THREADS, bytes, s>>>(P, S, cap);
-}
-void launch_pool(const MegaParams& P, int blocks_per_sm, uint32_t slots_per_block, cudaStream_t s) {
-  if (!P.nslots) return;
-  uint32_t S = slots_per_block < POOL_THREADS ? POOL_THREADS : slots_per_block;
-  uint32_t cap = 1; while (cap < S) cap <<= 1;
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
-  if (blocks_per_sm > 4) blocks_per_sm = 4;
-  const bool b4 = P.rp.scene.bvh_kind == 4;
-  if (!(P.simple_scene && !b4) && blocks_per_sm > 2) blocks_per_sm = 2;   // the other variants need > 64 registers
-  int grid = device_sm_count() * blocks_per_sm;
-  int need = (int)((P.nslots + S - 1) / S);
-  if (grid > need && !P.nslots_dev) grid = need;
-  if (P.simple_scene) {
-    if (b4) launch_pool_t<4, true, 2>(P, S, cap, grid, s);
-    else if (blocks_per_sm == 4) launch_pool_t<2, true, 4>(P, S, cap, grid, s);
-    else if (blocks_per_sm == 3) launch_pool_t<2, true, 3>(P, S, cap, grid, s);
-    else launch_pool_t<2, true, 2>(P, S, cap, grid, s);
-  } else { if (b4) launch_pool_t<4, false, 2>(P, S, cap, grid, s); else launch_pool_t<2, false, 2>(P, S, cap, grid, s); }
 }
 
 // ------------------------------------------------------------------ segments (contract B10)

@@ -59,15 +59,20 @@ struct MegaParams {
   uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
   uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
   uint32_t inner_reps;            // k_mega: inner-node steps per vote inside a burst
-  uint32_t t_switch;              // k_pool: an under-filled logic warp flushes and goes traversing when qT holds at least this many rays
+  uint32_t t_switch;              // k_wpool: a logic run that cannot refill leaves when fewer than this many lanes still hold a context
+  uint32_t t_refill;              // k_wpool: idle lanes of a traversal burst refill from the queue when at least this many are idle
+  float4* pool;                   // k_wpool: path contexts, [warp][pool_ctx][10 x float4]
+  uint32_t pool_ctx;              // k_wpool: contexts per warp (<= 128)
   uint32_t chunk;                 // slots a warp fetches at a time (multiple of 32)
   uint32_t simple_scene;          // shapes are triangles and planes only: kernel variant without torus / box code
   uint32_t* work_counter;         // zeroed before the launch
   unsigned long long* counters;
 };
 void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s);   // per kernel variant, see kernels.cu
-// Block-pool path kernel (k_pool): path states parked in shared memory, warps alternate between logic and traversal mode.
-void launch_pool(const MegaParams& P, int blocks_per_sm, uint32_t slots_per_block, cudaStream_t s);
+// Warp-pool path kernel (k_wpool, wpool.cu): a warp owns a pool of path contexts and alternates between logic runs and traversal bursts.
+void launch_wpool(const MegaParams& P, int grid, int blocks_per_sm, cudaStream_t s);
+uint32_t wpool_warps(int grid);
+size_t wpool_ctx_bytes();
 
 void launch_setup_slots(const PathState& st, const uint32_t* spp_per_slot, uint32_t uniform_spp, const float4* accum, cudaStream_t s);
 void launch_trace(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);

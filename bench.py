@@ -8,7 +8,7 @@ A "step" is one full render of that frame from cleared accumulators.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
   python bench.py --impl reference ...                           # CPU restatement (oracle), all host threads
-  torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU, rows interleaved
+  torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU, 4-row bands dealt round-robin
 
 ray  = one Scene::trace_g call (camera, bounce and shadow rays; src/graphics/scene.rs:162)
 path = one trace_original_color call = one sample (src/tracer.rs:224)
@@ -107,14 +107,19 @@ def cpu_reference(spp, threads):
     return st["rays"], st["paths"], dt
 
 
+WORKLOAD = "bunny scene, stand-in mesh 81920 tris, BVH%d 16 bins, 1920x1080, %d spp per GPU (%d total), NormalNEE, diffuse+emissive, mode-B per-path streams"
+
+
 def run_reference(args):
+    """--impl reference: the reference's CPU path (its C++ restatement: no Rust toolchain exists here) on all host
+    threads, one step = the same 1920x1080 x 16 spp frame the GPU arm renders per GPU."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    spp = 4   # bounded sample: 1920x1080 x 4 spp per step (~0.8 s on 16 threads; 1-spp steps under-report the CPU by ~20 %: thread start-up)
+    spp = args.spp
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference(spp, threads)
+        cpu_reference(1, threads)
     tot_r = tot_p = 0
     tot_t = 0.0
     for _ in range(args.steps):
@@ -124,10 +129,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mrays/s (bunny 1080p, 16 spp, NormalNEE, BVH2)", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (procedural stand-in mesh, 81920 triangles)",
-            "config": {"workload": "bunny scene, stand-in mesh 81920 tris, BVH2 16 bins, 1920x1080, 16 spp per GPU (%d total), NormalNEE, diffuse+emissive, mode-B per-path streams" % (16 * max(1, args.gpus)),
-                       "sample": "4 spp per step (of the 16 spp frame)"},
+            "config": {"workload": WORKLOAD % (2, args.spp, args.spp * max(1, args.gpus)),
+                       "sample": "one whole 1920x1080 x %d spp frame per step (the GPU arm's per-GPU frame), %d host threads" % (spp, threads)},
             "mpaths_per_s": tot_p / tot_t / 1e6,
-            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": "1920x1080 x 4 spp per step, %d steps" % args.steps},
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": "1920x1080 x %d spp per step, %d steps" % (spp, args.steps)},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -142,6 +147,8 @@ def main():
     ap.add_argument("--bvh", type=int, default=2)
     ap.add_argument("--engine", type=int, default=0, help="0 = persistent path kernel, 1 = multi-kernel wavefront")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-target", action="store_true", help="skip the strong-scaled target record and the mesh-filling record")
+    ap.add_argument("--target-spp", type=int, default=64, help="sample budget (spp x pixels) of the strong-scaled target frame")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -150,6 +157,7 @@ def main():
     import numpy as np
     import torch
     import wasm_pathtracer_b200 as W
+    from wasm_pathtracer_b200.dist import attach
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,7 +170,7 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    spp_total = args.spp * world           # weak scaling: 16 spp per GPU, rows interleaved over ranks
+    spp_total = args.spp * world           # weak scaling: 16 spp per GPU, 4-row bands dealt round-robin to the ranks
     # in-tree library: only rank 0 may (re)build it and write the generated mesh; the others wait for it
     if rank == 0:
         W.build_library()
@@ -172,19 +180,13 @@ def main():
     verts = W.parse_obj(open(mesh_path()).read(), True)
     pt = W.PathTracer(W_, H_, W.SCENE_BUNNY, *W.CAM_BUNNY, device=local)
     pt.store_mesh(W.api.MESH_BUNNY_HIGH, verts)
-    pt.set_config(bvh_kind=args.bvh, render_type=W.NORMAL_NEE, rank=rank, world=world, engine=args.engine)
+    pt.set_config(bvh_kind=args.bvh, render_type=W.NORMAL_NEE, engine=args.engine)
+    attach(pt, rank, world)                # band partition + the library's native NCCL plane (torch only carries the unique id)
     # time on the stream the kernels are launched on (torch.cuda.Event only sees the stream it is recorded on)
     stream = torch.cuda.ExternalStream(pt.device_buffers()["stream"])
 
-    def gather_frame():
-        """Framebuffer exchange: every rank ends up with every row's accumulators (NCCL all_gather)."""
-        if dist is None:
-            return
-        from wasm_pathtracer_b200.dist import allgather_rows
-        allgather_rows(pt, rank, world)
-
     # L2 flush between timed iterations: a 256 MiB buffer (> 126 MB L2) is overwritten on the session's stream
-    # before every step (it costs ~40 us of the ~20 ms step and is inside the timed region)
+    # before every step (it costs ~40 us of the ~17 ms step and is inside the timed region)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step():
@@ -192,12 +194,21 @@ def main():
             flush_buf.zero_()
         pt.reset()
         pt.render_exact(spp_total)
-        gather_frame()
+        pt.gather_frame()                  # framebuffer exchange: ncclAllGather of the accumulator rows inside libwpt
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def over_ranks(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=op)
+        return [float(x) for x in t]
+
+    MAX = dist.ReduceOp.MAX if dist is not None else None
+    SUM = dist.ReduceOp.SUM if dist is not None else None
 
     # clocks are sampled from before the warm-up until after the e2e leg (all under load)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -212,7 +223,6 @@ def main():
     barrier()
     # ---- value: device-timed, inputs (scene, BVH) resident in HBM; L2 is flushed before every step (see step()).
     pt.profile(True)
-    st0 = pt.stats()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -225,16 +235,10 @@ def main():
     pt.profile(False)
     st1 = pt.stats()
     rays_step = prof["rays"] / args.steps
-    # stats() is reset by step(); take per-step counts from the last step
-    paths_step = st1["paths"]
+    paths_step = st1["paths"]             # stats() is reset by step(): per-step counts of the last step
     launches_step = st1["launches"]
-    t = torch.tensor([ms, float(rays_step), float(paths_step)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms = float(tmax[0]); rays_all = float(tsum[1]); paths_all = float(tsum[2])
-    else:
-        rays_all, paths_all = float(rays_step), float(paths_step)
+    ms = over_ranks([ms], MAX)[0]
+    rays_all, paths_all, visits_all = over_ranks([float(rays_step), float(paths_step), prof["node_visits"] / args.steps], SUM)
     ms_step = ms / args.steps
     value = rays_all / (ms_step * 1e-3) / 1e6
     mpaths = paths_all / (ms_step * 1e-3) / 1e6
@@ -250,64 +254,137 @@ def main():
         h2d = pt.upload_scene()
         pt.update_camera(*cam)
         pt.render_exact(spp_total)
-        gather_frame()
+        pt.gather_frame()
         img = pt.results(0)
         d2h = img.nbytes
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = rays_all / float(te[0]) / 1e6
+    e2e_s = over_ranks([(time.perf_counter() - t0) / args.steps], MAX)[0]
+    e2e_value = rays_all / e2e_s / 1e6
     clocks = sampler.finish() if sampler else None
+
+    # ---- target record (north_star's target configuration, strong scaling): bunny, BVH4, photon-based NEE over
+    # 300 000 photons + adaptive sampling, 1920x1080, a FIXED budget of target_spp x pixels ticks shared by all ranks
+    target = None
+    if not args.no_target:
+        tp = W.PathTracer(W_, H_, W.SCENE_BUNNY, *W.CAM_BUNNY, device=local)
+        tp.store_mesh(W.api.MESH_BUNNY_HIGH, verts)
+        tp.set_config(bvh_kind=4, render_type=W.PNEE, photon_target=300000)
+        attach(tp, rank, world)
+        tstream = torch.cuda.ExternalStream(tp.device_buffers()["stream"])
+        budget = W_ * H_ * args.target_spp
+        barrier()
+        t0 = time.perf_counter()
+        tp.build_photons()                 # shots split over the ranks, merged with ncclAllReduce(uint32, sum)
+        tp.synchronize()
+        warm_ms = over_ranks([(time.perf_counter() - t0) * 1e3], MAX)[0]
+        tp.render_adaptive(budget); tp.synchronize()     # untimed warm-up frame
+        reps = 3
+        tp.profile(True)
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record(tstream)
+        for _ in range(reps):
+            tp.reset()                     # keeps the photon tree (update_camera semantics, tracer.rs:84-88)
+            tp.render_adaptive(budget)
+        a1.record(tstream)
+        barrier()
+        tms = over_ranks([a0.elapsed_time(a1) / reps], MAX)[0]
+        rp = tp.profile_read_rounds()
+        tprof = tp.profile_read()
+        tp.profile(False)
+        tst = tp.stats()
+        t_rays, t_paths = over_ranks([tprof["rays"] / reps, float(tst["paths"])], SUM)
+        per_rank = [rp["render_ms"] / reps, rp["error_map_ms"] / reps, rp["exchange_ms"] / reps, tprof["trace_ms"] / reps]
+        if dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, per_rank)
+        else:
+            gathered = [per_rank]
+        cnt = tp.accum()[1]
+        target = {"config": "bunny (stand-in mesh), BVH4, PNEE over 300000 photons + adaptive sampling, 1920x1080, budget %d spp x pixels = %d ticks in total (NOT multiplied by the GPU count)" % (args.target_spp, budget),
+                  "scaling": "strong", "n_gpus": world, "ms_per_frame": tms, "mrays_per_s": t_rays / (tms * 1e-3) / 1e6, "mpaths_per_s": t_paths / (tms * 1e-3) / 1e6,
+                  "rays_per_frame": t_rays, "paths_per_frame": t_paths, "photon_warmup_ms": warm_ms, "photons": int(tst["photons_stored"]) if tst["photons_stored"] else 300000,
+                  "adaptive_rounds_per_frame": rp["rounds"] / reps, "spp_min": int(cnt.min()), "spp_max": int(cnt.max()),
+                  "per_rank_ms": {"render": [g[0] for g in gathered], "error_map": [g[1] for g in gathered], "exchange": [g[2] for g in gathered], "path_kernel": [g[3] for g in gathered]},
+                  "collectives": "ncclAllGather of the accumulator rows after every round + ncclAllReduce(uint32) of the photon batches, issued by libwpt on the session's stream" if world > 1 else "none (1 GPU)"}
+        tp.detach_nccl(); tp.close()
+
+    # ---- mesh-filling camera (rank 0 only): the reference camera sees the mesh in ~9 % of the pixels, so the headline says
+    # little about BVH traversal; the same scene from close up, with node visits per second
+    filling = None
+    if rank == 0 and not args.no_target:
+        fp = W.PathTracer(W_, H_, W.SCENE_BUNNY, 0.0, 1.3, 3.0, 0.05, 0.0, device=local)
+        fp.store_mesh(W.api.MESH_BUNNY_HIGH, verts)
+        fp.set_config(bvh_kind=args.bvh, render_type=W.NORMAL_NEE, engine=args.engine)
+        ids = fp.primary_probe()[0]
+        cover = float((ids >= fp.scene_info()["num_inf"]).mean())
+        fp.render_exact(args.spp); fp.synchronize()
+        fp.profile(True)
+        for _ in range(3):
+            fp.reset(); fp.render_exact(args.spp)
+        fprof = fp.profile_read(); fp.profile(False)
+        fms = fprof["trace_ms"] / 3
+        filling = {"config": "same scene and settings, camera (0, 1.3, 3.0) rot_x 0.05: the mesh covers %.0f %% of the primary pixels" % (100 * cover),
+                   "mesh_coverage": cover, "ms_per_frame": fms, "mrays_per_s": fprof["rays"] / 3 / (fms * 1e-3) / 1e6,
+                   "node_visits_per_s": fprof["node_visits"] / 3 / (fms * 1e-3), "visits_per_ray": fprof["node_visits"] / max(1, fprof["rays"]),
+                   "prims_per_ray": fprof["prim_tests"] / max(1, fprof["rays"])}
+        fp.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # Algorithmic bytes of the dominant kernel (k_trace), SURVEY.md 8(d): per ray
+        # Algorithmic bytes of the dominant kernel, SURVEY.md 8(d): per ray
         # 32*V + 36*P_tri + 24*num_inf + 36 (ray in) + 16 (hit out); V, P counted by the kernel.
         alg_bytes = 32.0 * prof["node_visits"] + 36.0 * prof["prim_tests"] + (24.0 * 2 + 36 + 16) * prof["rays"]
         trace_s = prof["trace_ms"] * 1e-3
         achieved = alg_bytes / trace_s / 1e9 if trace_s > 0 else None
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        traffic_src = None
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if args.engine == 0 and world == 1 and args.spp == SPP and args.bvh == 2 and os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")   # dram read + write of one launch, ncu --set full
+            tj = json.load(open(tpath))
+            traffic = tj.get("traffic_bytes_per_launch")   # dram read + write of one launch, ncu --set full
+            traffic_src = "profiles/r2_traffic.json (%s)" % tj.get("source", "ncu --set full")
         extra = {}
         ppath = os.path.join(ROOT, "profiles", "r1c_peaks.json")   # L2 / L1 / FP32 roofs measured with tools/wpt_peaks on a B200 of this pool
         if os.path.exists(ppath) and achieved:
             pk = json.load(open(ppath))
             extra = {"l2_peak_gbs": pk["l2_read_gbs"], "frac_of_l2": achieved / pk["l2_read_gbs"], "l1_peak_gbs": pk["l1_read_gbs"], "frac_of_l1": achieved / pk["l1_read_gbs"],
                      "fp32_peak_tflops": pk["fp32_fma_tflops"]}
-        roofline = {"bound": "hbm", "kernel": "k_trace" if args.engine == 1 else "k_mega", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                    "traffic": traffic, "peak_source": peak_src,
+        roofline = {"bound": "issue/latency", "kernel": "k_trace" if args.engine == 1 else "k_mega", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "alg_bytes_per_launch": alg_bytes / max(1, prof["trace_launches"]), "avg_launch_ms": prof["trace_ms"] / max(1, prof["trace_launches"]),
-                    "kernel_share_of_step": prof["trace_ms"] / ms if ms else None, "shade_kernel_share_of_step": prof["shade_ms"] / ms if ms else None,
+                    "kernel_share_of_step": prof["trace_ms"] / (ms_step * args.steps) if ms_step else None, "shade_kernel_share_of_step": prof["shade_ms"] / (ms_step * args.steps) if ms_step else None,
                     "visits_per_ray": prof["node_visits"] / max(1, prof["rays"]), "prims_per_ray": prof["prim_tests"] / max(1, prof["rays"]),
+                    "node_visits_per_s": prof["node_visits"] / trace_s if trace_s > 0 else None,
                     **extra,
-                    "note": "achieved = algorithmic bytes (SURVEY 8d) / kernel time; the scene (~10 MB) is cache resident (measured DRAM traffic is ~3% of the algorithmic bytes, mostly local-memory evictions): the real bounds are instruction issue under divergence and load latency (DESIGN.md 5, profiles/r1c_k_mega_bench_full.md)"}
+                    "note": "frac = algorithmic bytes (SURVEY 8d) / kernel time over the measured HBM copy peak, kept because the schema asks for it: those bytes are served by L1 / L2 (the scene is ~10 MB; measured DRAM traffic = `traffic`), so HBM is NOT what binds. The binding resource is instruction issue under divergence plus load latency (12 of 32 lanes per instruction, 71 % of the issue slots busy): frac_of_l2 / frac_of_l1 are the fractions of the cache roofs (DESIGN.md 5, profiles/)"}
         line = {"metric": "Mrays/s (bunny 1080p, 16 spp, NormalNEE, BVH%d)" % args.bvh, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (procedural stand-in mesh, 81920 triangles; reference bunny2.obj is a stripped blob)",
-                "config": {"workload": "bunny scene, stand-in mesh 81920 tris, BVH%d 16 bins, 1920x1080, %d spp per GPU (%d total), NormalNEE, diffuse+emissive, mode-B per-path streams" % (args.bvh, args.spp, spp_total),
-                           "partition": "rows interleaved over %d rank(s), NCCL all_gather of accumulators; a pixel's samples run as segments of 8 on separate lanes (contract B10)" % world,
-                           "engine": "persistent path kernel (k_mega)" if args.engine == 0 else "multi-kernel wavefront (k_trace + k_shade)",
+                "config": {"workload": WORKLOAD % (args.bvh, args.spp, spp_total),
+                           "partition": "4-row bands dealt round-robin to %d rank(s), ncclAllGather of the accumulator rows inside libwpt; a pixel's samples run as segments of 8 on separate lanes (contract B10)" % world,
+                           "engine": "persistent path kernel (k_mega)" if args.engine == 0 else "engine %d" % args.engine,
                            "l2": "flushed before every timed step: a 256 MiB buffer is overwritten on the kernel's stream (inside the timed region)"},
-                "mpaths_per_s": mpaths, "rays_per_step": rays_all, "paths_per_step": paths_all,
+                "mpaths_per_s": mpaths, "rays_per_step": rays_all, "paths_per_step": paths_all, "node_visits_per_s": visits_all / (ms_step * 1e-3),
                 "roofline": roofline,
-                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te[0]) * 1e3},
-                "gpu_launches": int(launches_step) * args.steps, "clocks": clocks}
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+                "gpu_launches": int(launches_step) * args.steps, "clocks": clocks, "target": target, "mesh_filling": filling}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            tr = tp = 0
+            tr = tp_ = 0
             tt = 0.0
             frames = 0
             while tt < 10.0 and frames < 8:      # bounded sample: whole 16-spp frames until >= 10 s of CPU work
                 r, p, dt = cpu_reference(args.spp, threads)
-                tr += r; tp += p; tt += dt; frames += 1
+                tr += r; tp_ += p; tt += dt; frames += 1
+            r1, p1, t1 = cpu_reference(1, 1)     # one reference WASM instance is single-threaded (wasm_interface.rs:59-62): 1 spp frame on one thread
             line["cpu_baseline"] = {"value": tr / tt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                                     "sample": "%d full frame(s) of the same workload (1920x1080 x %d spp), %.1f s on %d threads" % (frames, args.spp, tt, threads),
-                                    "mpaths_per_s": tp / tt / 1e6}
+                                    "mpaths_per_s": tp_ / tt / 1e6,
+                                    "single_thread": {"value": r1 / t1 / 1e6, "unit": "Mrays/s", "cores": 1, "mpaths_per_s": p1 / t1 / 1e6,
+                                                      "sample": "one 1920x1080 x 1 spp frame of the same scene, %.1f s on 1 thread" % t1}}
         print(json.dumps(line))
+    pt.detach_nccl()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

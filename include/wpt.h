@@ -140,6 +140,19 @@ int wpt_ctx_set_exchange_callback(wpt_ctx* ctx, void (*callback)(void* user), vo
  * on the session's stream (e.g. ncclAllReduce(ncclUint32, ncclSum)). NULL removes it: every
  * rank then emits all shots itself. */
 int wpt_ctx_set_reduce_callback(wpt_ctx* ctx, void (*callback)(void* user, void* dev_words, uint64_t n_words), void* user);
+/* Native multi-GPU plane: NCCL inside the library — replaces the reference's only cross-worker data hand-off,
+ * the SharedArrayBuffer copy of src_ts/worker/worker.ts:84-89 (and the old 8-worker pixel split, README.md:87).
+ * One process (or thread) per GPU. Rank 0 calls wpt_nccl_unique_id and the host distributes the 128 bytes by any means
+ * (MPI, a file, torch.distributed); every rank then attaches its session: ncclCommInitRank, config.rank / world, and the
+ * built-in exchange (accumulator all-gather of the region's rows, between adaptive rounds and on wpt_ctx_gather_frame)
+ * and photon-batch reduction (ncclAllReduce of uint32, sum) replace the two callbacks above. All collectives are issued
+ * on the session's stream. NCCL is dlopen()ed at attach time (libnccl.so.2). `_comm` borrows an existing ncclComm_t. */
+int wpt_nccl_unique_id(uint8_t out[128]);
+int wpt_ctx_attach_nccl(wpt_ctx* ctx, const uint8_t id[128], uint32_t rank, uint32_t world);
+int wpt_ctx_attach_nccl_comm(wpt_ctx* ctx, void* nccl_comm, uint32_t rank, uint32_t world);
+int wpt_ctx_detach_nccl(wpt_ctx* ctx);
+/* All-gather the accumulators of the region's rows over the attached ranks (every rank ends up with the whole region). */
+int wpt_ctx_gather_frame(wpt_ctx* ctx);
 /* Photon warm-up (tracer.rs:103-152) + octree light-CDF build (photon_tree.rs). */
 int wpt_ctx_build_photons(wpt_ctx* ctx);
 /* Block until queued GPU work is finished. */
@@ -190,6 +203,9 @@ int64_t wpt_ctx_upload_scene(wpt_ctx* ctx);
  * last wpt_ctx_profile call. */
 int wpt_ctx_profile(wpt_ctx* ctx, int enable);
 int wpt_ctx_profile_read(wpt_ctx* ctx, double out[8]);
+/* Strategy rounds since wpt_ctx_profile(ctx, 1): out[0] = adaptive rounds, [1] = error-map ms, [2] = round render ms, [3] = exchange ms
+ * (CUDA events on the session's stream), [4] = wall-clock ms of the last photon warm-up, [5] = NCCL collectives issued. */
+int wpt_ctx_profile_read_rounds(wpt_ctx* ctx, double out[8]);
 
 /* Device pointers for zero-copy collectives (multi-GPU plumbing lives above this ABI). */
 int wpt_ctx_device_buffers(wpt_ctx* ctx, uint64_t ptrs[8], uint64_t sizes[8]);

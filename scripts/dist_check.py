@@ -1,10 +1,10 @@
-"""Run under torchrun (NCCL): row-partitioned render + all_gather must equal a single-session render bit for bit."""
+"""Run under torchrun: band-partitioned render + the native NCCL all-gather must equal a single-session render bit for bit."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
 import wasm_pathtracer_b200 as W
-from wasm_pathtracer_b200.dist import allgather_rows, attach
+from wasm_pathtracer_b200.dist import attach
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -16,10 +16,10 @@ for rtype, mode in ((W.NORMAL_NEE, "exact"), (W.PNEE, "exact"), (W.NORMAL_NEE, "
     pt = W.PathTracer(w, h, W.SCENE_BUNNY, *W.CAM_BUNNY, device=local)
     pt.store_mesh(1, verts)
     pt.set_config(render_type=rtype, photon_target=20000)
-    attach(pt, rank, world)     # row partition + accumulator all-gather + photon shots split over ranks (NCCL sum-allreduce)
+    attach(pt, rank, world)     # band partition + the library's native NCCL plane: accumulator all-gather, photon shots split over ranks (uint32 sum-allreduce)
     if mode == "exact":
         pt.render_exact(3)
-        allgather_rows(pt, rank, world)
+        pt.gather_frame()
     else:
         pt.render_adaptive(w * h * 11 + 123)
     rgb, cnt = pt.accum()
@@ -37,7 +37,7 @@ for rtype, mode in ((W.NORMAL_NEE, "exact"), (W.PNEE, "exact"), (W.NORMAL_NEE, "
     same = np.array_equal(cnt, rcnt) and np.array_equal(rgb.view(np.uint32), rrgb.view(np.uint32)) and np.array_equal(pt.results(0), ref.results(0))
     print("rank %d type %d %s: partitioned == single session: %s" % (rank, rtype, mode, same), flush=True)
     ok = ok and same
-    pt.set_exchange_callback(None); pt.set_reduce_callback(None)
+    pt.detach_nccl()
     pt.close(); ref.close()
 dist.barrier()
 dist.destroy_process_group()

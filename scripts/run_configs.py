@@ -12,7 +12,7 @@ dist = None
 if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-from wasm_pathtracer_b200.dist import allgather_rows, attach
+from wasm_pathtracer_b200.dist import attach
 verts = W.parse_obj(open(mesh_path()).read(), True)
 which = sys.argv[1:] or ["2", "3", "3m", "4", "5"]
 scale = float(os.environ.get("WPT_CFG_SCALE", "1"))   # scale the sample budgets (1 = BASELINE sizes)
@@ -23,7 +23,7 @@ def run(name, scene, cam, w, h, bvh, rtype, mode, spp):
     if scene == W.SCENE_BUNNY:
         pt.store_mesh(1, verts)
     pt.set_config(bvh_kind=bvh, render_type=rtype)
-    attach(pt, rank, world)   # row partition, accumulator all-gather between adaptive rounds, photon shots split over ranks
+    attach(pt, rank, world)   # band partition + native NCCL plane: accumulator all-gather between adaptive rounds, photon shots split over ranks
     t0 = time.perf_counter()
     if rtype == W.PNEE:
         pt.build_photons()
@@ -32,7 +32,7 @@ def run(name, scene, cam, w, h, bvh, rtype, mode, spp):
     t0 = time.perf_counter()
     if mode == "exact":
         pt.render_exact(spp)
-        if world > 1: allgather_rows(pt, rank, world)
+        pt.gather_frame()
     else:
         pt.render_adaptive(int(w * h * spp))
     img = pt.results(0)
@@ -50,7 +50,7 @@ def run(name, scene, cam, w, h, bvh, rtype, mode, spp):
                           "seconds": dt, "photon_warmup_s": t_ph, "Mrays_per_s": rays / dt / 1e6, "Mpaths_per_s": paths / dt / 1e6,
                           "rays": rays, "paths": paths, "spp_min": int(cnt.min()), "spp_max": int(cnt.max()), "mean_rgb": [float(x) for x in (rgb.sum((0, 1)) / max(1, cnt.sum()))],
                           "photons": st["photons_stored"], "photon_shots": st["photons_shot"]}), flush=True)
-    pt.set_exchange_callback(None); pt.set_reduce_callback(None)
+    pt.detach_nccl()
     pt.close()
 
 

@@ -9,14 +9,16 @@ import cv2
 import numpy as np
 
 
-def panel_rows(rgb, min_area=12):
+def panel_rows(rgb, min_area=None):
     """rgb: float array (h, w, 3) in 0..1 -> list of rows (top to bottom), each a list of (r, g, b) codes left to right."""
+    if min_area is None:
+        min_area = max(12, int(0.00012 * rgb.shape[0] * rgb.shape[1]))
     mask = (rgb.max(-1) > 0.93).astype(np.uint8)
     n, lab, stats, cent = cv2.connectedComponentsWithStats(mask, connectivity=8)
     blobs = []
     for i in range(1, n):
         x, y, w, h, area = stats[i]
-        if area < min_area or w < 4:
+        if area < min_area or w < 4 or area < 0.42 * w * h:      # light panels are solid quads; firefly clusters are not
             continue
         c = rgb[lab == i].mean(0)
         blobs.append((float(cent[i][1]), float(cent[i][0]), tuple(2 if v > 0.9 else (1 if v > 0.45 else 0) for v in c)))

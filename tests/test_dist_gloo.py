@@ -1,4 +1,4 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: row partition + framebuffer exchange."""
+"""world_size-2 / -3 gloo tests (CPU) of the multi-GPU host logic: band partition, framebuffer exchange, id broadcast."""
 import os
 import sys
 
@@ -35,17 +35,22 @@ def _run(world, H):
     for p in procs: p.join(60)
     want = np.zeros((H, 5, 4), np.float32)
     for y in range(H):
-        want[y] = float(y % world + 1) * 1000 + y
+        want[y] = float((y // 4) % world + 1) * 1000 + y      # 4-row bands, band b belongs to rank b % world
     for r in range(world):
         assert np.array_equal(res[r], want)
 
 
 def test_exchange_rows_even():
-    _run(2, 8)
+    _run(2, 16)
 
 
 def test_exchange_rows_ragged():
-    _run(2, 7)     # odd height: rank 0 owns one more row than rank 1
+    _run(2, 7)     # one full band for rank 0, a ragged 3-row band for rank 1
+    _run(3, 10)    # rank 2 owns only the ragged last band; and a world that does not divide the band count
+
+
+def test_exchange_rows_more_ranks_than_bands():
+    _run(3, 5)     # rank 2 owns nothing
 
 
 def test_rows_of_rank_cover_the_region():
@@ -60,7 +65,12 @@ def _reduce_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from wasm_pathtracer_b200.dist import allreduce_words
+    from wasm_pathtracer_b200.dist import broadcast_bytes
+    uid = broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128)     # the NCCL unique id travels like this
+    assert uid == bytes(range(128))
+
+    def allreduce_words(t):   # what ncclAllReduce(ncclUint32, ncclSum) does inside libwpt (csrc/dist_nccl.cpp)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
     # the photon-batch merge: slot i is written by rank i % world only (raw float bits viewed as int32), zeros elsewhere
     n = 1000
     rng = np.random.default_rng(7)

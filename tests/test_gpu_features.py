@@ -263,13 +263,14 @@ def test_segmented_accumulation_contract_b10(gpu_ok, meshes):
         pt.reset(); pt.set_config(engine=engine); pt.render_exact(37); pt.render_exact(5)
         r2, c2 = pt.accum()
         assert np.array_equal(bits(rgb), bits(r2)) and np.array_equal(cnt, c2), engine
-    # two row-interleaved ranks, each rendering its rows: together the same frame
+    # two ranks, each rendering its 4-row bands: together the same frame
     parts = []
     for rank in range(2):
         q = W.PathTracer(w, h, 2, *W.CAM_BUNNY, device=0); q.store_mesh(1, meshes[3])
         q.set_config(render_type=W.NORMAL_NEE, rank=rank, world=2)
         q.render_exact(37); q.render_exact(5)
         parts.append(q.accum()[0]); q.close()
-    merged = parts[0].copy(); merged[1::2] = parts[1][1::2]
+    from wasm_pathtracer_b200.dist import rows_of_rank
+    merged = parts[0].copy(); r1 = rows_of_rank(h, 1, 2); merged[r1] = parts[1][r1]
     assert np.array_equal(bits(merged), bits(rgb))
     pt.close()

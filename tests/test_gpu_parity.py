@@ -133,17 +133,18 @@ def test_full_size_properties_1080p(gpu_ok, built):
     a.reset(); a.render_exact(16); a.render_exact(16)
     rgb_d, _ = a.accum()
     assert np.array_equal(bits(rgb_c), bits(rgb_d))
-    # (2) two interleaved row partitions == one full-frame render, and the counters add up
+    # (2) two band partitions (4-row bands, alternating ranks) == one full-frame render, and the counters add up
+    from wasm_pathtracer_b200.dist import rows_of_rank
     parts = []
     tot = {"rays": 0, "node_visits": 0, "paths": 0}
     for r in range(2):
         a.reset(); a.set_config(rank=r, world=2); a.render_exact(4)
         rgb, cnt = a.accum()
-        assert (cnt[r::2] == 4).all() and (cnt[1 - r::2] == 0).all()
+        assert (cnt[rows_of_rank(1080, r, 2)] == 4).all() and (cnt[rows_of_rank(1080, 1 - r, 2)] == 0).all()
         parts.append(rgb)
         s = a.stats()
         for k in tot: tot[k] += s[k]
-    merged = parts[0].copy(); merged[1::2] = parts[1][1::2]
+    merged = parts[0].copy(); r1 = rows_of_rank(1080, 1, 2); merged[r1] = parts[1][r1]
     assert np.array_equal(bits(merged), bits(rgb_a))
     assert tot == {k: st_a[k] for k in tot}
     # (3) primary ids: every hit id is a valid shape, visit counts >= 1 (the root guard)

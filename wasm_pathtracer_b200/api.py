@@ -89,6 +89,11 @@ def load_library():
         "wpt_ctx_set_exchange_callback": (i32, [vp, C.c_void_p, vp]),
         "wpt_ctx_set_reduce_callback": (i32, [vp, C.c_void_p, vp]),
         "wpt_ctx_synchronize": (i32, [vp]),
+        "wpt_nccl_unique_id": (i32, [P(C.c_uint8)]),
+        "wpt_ctx_attach_nccl": (i32, [vp, P(C.c_uint8), u32, u32]),
+        "wpt_ctx_attach_nccl_comm": (i32, [vp, vp, u32, u32]),
+        "wpt_ctx_detach_nccl": (i32, [vp]),
+        "wpt_ctx_gather_frame": (i32, [vp]),
         "wpt_ctx_stats": (i32, [vp, P(u64)]),
         "wpt_ctx_primary_probe": (i32, [vp, P(C.c_int32), P(u32), P(f32)]),
         "wpt_ctx_accum": (i32, [vp, P(f32), P(u32)]),
@@ -109,6 +114,7 @@ def load_library():
         "wpt_ctx_upload_scene": (C.c_int64, [vp]),
         "wpt_ctx_profile": (i32, [vp, i32]),
         "wpt_ctx_profile_read": (i32, [vp, P(C.c_double)]),
+        "wpt_ctx_profile_read_rounds": (i32, [vp, P(C.c_double)]),
         "wpt_ctx_mark_accum_dirty": (i32, [vp]),
         "wpt_ctx_load_obj": (C.c_int64, [vp, u32, C.c_char_p, i32]),
         "wpt_parse_obj": (C.c_int64, [C.c_char_p, u64, i32, P(f32), u64]),
@@ -136,6 +142,15 @@ def parse_obj(text, client_scale=True):
     out = np.empty(n, np.float32)
     L.wpt_parse_obj(b, len(b), int(client_scale), _p(out, C.c_float), n)
     return out.reshape(-1, 3)
+
+
+def nccl_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the host sends it to the other ranks)."""
+    L = load_library()
+    buf = (C.c_uint8 * 128)()
+    if L.wpt_nccl_unique_id(buf) != 0:
+        raise WptError(L.wpt_last_error().decode())
+    return bytes(buf)
 
 
 class PathTracer:
@@ -270,6 +285,17 @@ class PathTracer:
         self._rcb = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)(lambda _u, p, n: fn(int(p), int(n)))
         self._chk(self.L.wpt_ctx_set_reduce_callback(self.h, C.cast(self._rcb, C.c_void_p), None))
 
+    def attach_nccl(self, unique_id, rank, world):
+        """Native multi-GPU plane: `unique_id` = the 128 bytes of nccl_unique_id() of rank 0 (None when world == 1)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        self._chk(self.L.wpt_ctx_attach_nccl(self.h, buf, rank, world))
+
+    def detach_nccl(self):
+        self._chk(self.L.wpt_ctx_detach_nccl(self.h))
+
+    def gather_frame(self):
+        self._chk(self.L.wpt_ctx_gather_frame(self.h))
+
     def build_photons(self):
         self._chk(self.L.wpt_ctx_build_photons(self.h))
 
@@ -386,6 +412,11 @@ class PathTracer:
         self._chk(self.L.wpt_ctx_profile_read(self.h, _p(out, C.c_double)))
         return dict(trace_ms=out[0], trace_launches=int(out[1]), shade_ms=out[2], shade_launches=int(out[3]),
                     prim_tests=int(out[4]), rays=int(out[5]), node_visits=int(out[6]))
+
+    def profile_read_rounds(self):
+        out = np.zeros(8, np.float64)
+        self._chk(self.L.wpt_ctx_profile_read_rounds(self.h, _p(out, C.c_double)))
+        return dict(rounds=int(out[0]), error_map_ms=out[1], render_ms=out[2], exchange_ms=out[3], photon_warmup_ms=out[4], collectives=int(out[5]))
 
     def mark_accum_dirty(self):
         self._chk(self.L.wpt_ctx_mark_accum_dirty(self.h))

@@ -16,12 +16,26 @@ static void fail(const char* what) {
   g_err = what;
   if (strict_mode()) { std::fprintf(stderr, "wpt: %s\n", what); std::abort(); }   // the reference traps
 }
+// Every entry point runs on the session's own device: C() selects it (allocations, pinned memory and launches of a
+// session must not land on whatever device the calling thread happened to use last) and the guard puts the caller's
+// device back afterwards.
+struct DeviceRestore {
+  int prev = -1; bool have = false;
+  DeviceRestore() { have = cudaGetDevice(&prev) == cudaSuccess; if (!have) cudaGetLastError(); }
+  ~DeviceRestore() { int now = -1; if (have && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev); }
+};
 template <class F> static int guard(F&& f) {
+  DeviceRestore restore;
   try { f(); return 0; }
   catch (const std::exception& e) { fail(e.what()); return -1; }
   catch (...) { fail("unknown error"); return -1; }
 }
-static Context* C(wpt_ctx* c) { if (!c) throw std::runtime_error("init not called"); return reinterpret_cast<Context*>(c); }
+static Context* C(wpt_ctx* c) {
+  if (!c) throw std::runtime_error("init not called");
+  Context* x = reinterpret_cast<Context*>(c);
+  if (x->has_device) WPT_CUDA(cudaSetDevice(x->device));
+  return x;
+}
 
 extern "C" {
 
@@ -47,7 +61,7 @@ wpt_ctx* wpt_ctx_create(int device, uint32_t width, uint32_t height, uint32_t sc
       }) != 0) return nullptr;
   return reinterpret_cast<wpt_ctx*>(c);
 }
-void wpt_ctx_destroy(wpt_ctx* ctx) { if (ctx == reinterpret_cast<wpt_ctx*>(g_ctx)) g_ctx = nullptr; delete reinterpret_cast<Context*>(ctx); }
+void wpt_ctx_destroy(wpt_ctx* ctx) { DeviceRestore restore; if (ctx == reinterpret_cast<wpt_ctx*>(g_ctx)) g_ctx = nullptr; delete reinterpret_cast<Context*>(ctx); }
 
 const uint8_t* wpt_ctx_results(wpt_ctx* ctx, uint32_t show) {
   const uint8_t* p = nullptr;
@@ -160,6 +174,16 @@ int wpt_ctx_set_reduce_callback(wpt_ctx* ctx, void (*cb)(void*, void*, uint64_t)
   return guard([&] { Context* c = C(ctx); if (cb) c->reduce_hook = [cb, user](uint32_t* p, uint64_t n) { cb(user, p, n); }; else c->reduce_hook = nullptr; });
 }
 int wpt_ctx_build_photons(wpt_ctx* ctx) { return guard([&] { C(ctx)->build_photons(); }); }
+// ---- native multi-GPU plane (dist_nccl.cpp)
+int wpt_nccl_unique_id(uint8_t out[128]) { return guard([&] { if (!out) throw std::runtime_error("null id buffer"); nccl_unique_id(out); }); }
+int wpt_ctx_attach_nccl(wpt_ctx* ctx, const uint8_t id[128], uint32_t rank, uint32_t world) {
+  return guard([&] { if (!id && world > 1) throw std::runtime_error("null NCCL id"); C(ctx)->attach_nccl(id, nullptr, rank, world); });
+}
+int wpt_ctx_attach_nccl_comm(wpt_ctx* ctx, void* comm, uint32_t rank, uint32_t world) {
+  return guard([&] { if (!comm && world > 1) throw std::runtime_error("null NCCL communicator"); C(ctx)->attach_nccl(nullptr, comm, rank, world); });
+}
+int wpt_ctx_detach_nccl(wpt_ctx* ctx) { return guard([&] { Context* c = C(ctx); c->detach_nccl(); c->cfg.rank = 0; c->cfg.world = 1; c->slots = 0; }); }
+int wpt_ctx_gather_frame(wpt_ctx* ctx) { return guard([&] { C(ctx)->exchange_native(); }); }
 int wpt_ctx_synchronize(wpt_ctx* ctx) { return guard([&] { Context* c = C(ctx); c->require_device(); WPT_CUDA(cudaStreamSynchronize(c->stream)); }); }
 int wpt_ctx_stats(wpt_ctx* ctx, uint64_t out[8]) { return guard([&] { C(ctx)->stats(out); }); }
 
@@ -292,6 +316,7 @@ int64_t wpt_ctx_upload_scene(wpt_ctx* ctx) {
 }
 int wpt_ctx_profile(wpt_ctx* ctx, int enable) { return guard([&] { C(ctx)->set_profiling(enable != 0); }); }
 int wpt_ctx_profile_read(wpt_ctx* ctx, double out[8]) { return guard([&] { C(ctx)->profile_read(out); }); }
+int wpt_ctx_profile_read_rounds(wpt_ctx* ctx, double out[8]) { return guard([&] { C(ctx)->profile_read_rounds(out); }); }
 
 int wpt_ctx_device_buffers(wpt_ctx* ctx, uint64_t ptrs[8], uint64_t sizes[8]) {
   return guard([&] {

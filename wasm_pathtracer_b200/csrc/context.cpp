@@ -46,6 +46,7 @@ Context::~Context() {
   if (!has_device) return;
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
+  try { detach_nccl(); } catch (...) {}
   for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : ev_free) cudaEventDestroy(e);
   if (own_stream) cudaStreamDestroy(own_stream);
@@ -171,14 +172,26 @@ void Context::ev_harvest() {   // call after a stream synchronize
   }
   ev_pending.clear();
 }
+void Context::ev_mark(int kind, bool begin) {
+  if (!profiling) return;
+  if (begin) { ev_open[kind] = ev_get(); WPT_CUDA(cudaEventRecord(ev_open[kind], stream)); }
+  else if (ev_open[kind]) { cudaEvent_t b = ev_get(); WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{ev_open[kind], b, kind}); ev_open[kind] = nullptr; }
+}
 void Context::set_profiling(bool on) {
   require_device();
   WPT_CUDA(cudaStreamSynchronize(stream));
   ev_harvest();
   profiling = on;
-  prof_ms[0] = prof_ms[1] = 0; prof_n[0] = prof_n[1] = 0;
+  for (int i = 0; i < 6; i++) { prof_ms[i] = 0; prof_n[i] = 0; ev_open[i] = nullptr; }
+  adaptive_rounds = 0;
   read_counters(prof_base);
   for (int i = 0; i < 4; i++) prof_base[i] += life[i];
+}
+void Context::profile_read_rounds(double out[8]) {   // rounds, error-map ms, render ms, exchange ms, photon warm-up ms (wall), collectives
+  require_device();
+  WPT_CUDA(cudaStreamSynchronize(stream));
+  ev_harvest();
+  out[0] = (double)adaptive_rounds; out[1] = prof_ms[2]; out[2] = prof_ms[3]; out[3] = prof_ms[4]; out[4] = photon_build_ms; out[5] = (double)collectives; out[6] = out[7] = 0;
 }
 void Context::profile_read(double out[8]) {
   require_device();
@@ -217,13 +230,13 @@ void Context::region(uint32_t* rx, uint32_t* ry, uint32_t* rw, uint32_t* rh) con
   if (*rx + *rw > W || *ry + *rh > H) throw std::runtime_error("region outside the viewport");
 }
 
-// One slot per pixel of this session's rows of the region: rows ry + rank, ry + rank + world, ...
+// One slot per pixel of this session's rows of the region: the 4-row bands b with b % world == rank (wpt_types.h)
 void Context::ensure_slots(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh) {
   require_device();
   uint32_t world = cfg.world ? cfg.world : 1, rank = cfg.rank;
   uint32_t key[6] = {rx, ry, rw, rh, rank, world};
   if (slots && !std::memcmp(key, slot_region, sizeof key)) return;
-  uint32_t rows = rh > rank ? (rh - rank + world - 1) / world : 0;
+  uint32_t rows = band_rows(rh, rank, world);
   uint32_t n = rows * rw;
   s_ray_o.alloc(n); s_ray_d.alloc(n); s_col.alloc(n); s_sh_o.alloc(n); s_sh_d.alloc(n); s_sh_c.alloc(n); s_tail.alloc(n);
   s_misc.alloc(n); s_hit.alloc(n); s_pixel.alloc(n); s_spp.alloc(n);
@@ -349,7 +362,18 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   P.simple_scene = 1;
   for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { P.simple_scene = 0; break; }
   for (const HostMaterial& m : scene.mats) if (m.kind != MAT_DIFFUSE && m.kind != MAT_EMISSIVE) { P.simple_scene = 0; break; }
+  if (scene.num_inf > 2) P.simple_scene = 0;   // the variant reads its (at most two) infinite planes from the kernel parameters
   if (std::getenv("WPT_NO_SIMPLE")) P.simple_scene = 0;
+  if (P.simple_scene) {
+    const DShape* shp = reinterpret_cast<const DShape*>((const char*)h_scene_blob + blob_off[2]);
+    for (uint32_t i = 0; i < scene.num_inf; i++) P.inf_q1[i] = shp[i].q1;
+    const DNode2* n2 = reinterpret_cast<const DNode2*>((const char*)h_scene_blob + blob_off[0]);
+    if (blob_len[0] >= sizeof(DNode2)) { P.root_a = n2[0].a; P.root_b = n2[0].b; }
+  }
+  {
+    auto mix32 = [](uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; };
+    P.seed_path = mix32((uint32_t)STREAM_PATH ^ cfg.base_seed);
+  }
   if (cfg.engine == 4) {
     // experimental warp-pool kernel (wpool.cu): grid = SMs x blocks per SM; every warp owns pool_ctx path contexts of 160 B
     static const int w_minb = std::getenv("WPT_WPOOL_MINB") ? std::atoi(std::getenv("WPT_WPOOL_MINB")) : 8;
@@ -389,9 +413,12 @@ void Context::render_exact(uint32_t spp) {
   if (cfg.engine == 1) {   // the wavefront engine runs the segments of contract B10 one after the other
     for (uint32_t rem = spp; rem > 0;) { uint32_t m = std::min(rem, WPT_SEGMENT_LEN); run_wavefront(cfg.render_type, nullptr, m); rem -= m; }
   } else {
-    // at most 64 samples (8 segments) per pixel and launch: bounds the segment-sum buffer (128 B per pixel); the
-    // segments of later launches are added after those of earlier ones, i.e. in the same order as in one launch
-    for (uint32_t rem = spp; rem > 0;) { uint32_t m = std::min(rem, 8u * WPT_SEGMENT_LEN); run_persistent(cfg.render_type, nullptr, m); rem -= m; }
+    // one launch per call where the segment-sum buffer allows it (16 B per pixel and segment, capped at 2 GiB and 64
+    // segments = 512 samples per pixel): one ramp-up and one tail. The segments of later launches are added after
+    // those of earlier ones, i.e. in the same order as in one launch.
+    const uint64_t per_seg = (uint64_t)std::max(1u, slots) * sizeof(float4);
+    const uint32_t max_seg = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(8, (2ull << 30) / per_seg));
+    for (uint32_t rem = spp; rem > 0;) { uint32_t m = std::min(rem, max_seg * WPT_SEGMENT_LEN); run_persistent(cfg.render_type, nullptr, m); rem -= m; }
   }
 }
 

@@ -2,6 +2,7 @@
 // at a time (the reference is single-threaded per instance, wasm_interface.rs:59-62).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstring>
 #include <functional>
 #include <map>
 #include <list>
@@ -15,6 +16,7 @@ namespace wpt {
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 void cuda_check(cudaError_t e, const char* what);
+void nccl_unique_id(uint8_t out[128]);
 #define WPT_CUDA(x) ::wpt::cuda_check((x), #x)
 
 template <class T> struct DevBuf {
@@ -106,7 +108,11 @@ struct Context {
   struct EvPair { cudaEvent_t a, b; int kind; };
   std::vector<EvPair> ev_pending;
   std::vector<cudaEvent_t> ev_free;
-  double prof_ms[2] = {0, 0}; uint64_t prof_n[2] = {0, 0};
+  double prof_ms[6] = {0, 0, 0, 0, 0, 0}; uint64_t prof_n[6] = {0, 0, 0, 0, 0, 0};   // 0 path kernel, 1 shade kernel, 2 error map, 3 round render, 4 exchange, 5 photon warm-up
+  cudaEvent_t ev_open[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void ev_mark(int kind, bool begin);   // profiling only: bracket a phase with events on the session's stream
+  uint64_t adaptive_rounds = 0;
+  double photon_build_ms = 0;             // wall clock of the last build_photons()
   unsigned long long prof_base[4] = {0, 0, 0, 0};
   unsigned long long life[4] = {0, 0, 0, 0};   // counters folded in by reset()
   void read_counters(unsigned long long out[4]);
@@ -114,6 +120,7 @@ struct Context {
   void ev_harvest();
   void set_profiling(bool on);
   void profile_read(double out[8]);
+  void profile_read_rounds(double out[8]);
 
   // sampling strategies (sampling_strategy.rs) per logical region
   struct Strategy {
@@ -130,6 +137,14 @@ struct Context {
   std::list<Strategy> strategies;
   DevBuf<unsigned long long> a_stats, a_block_tot, a_block_suffix;
   std::function<void()> exchange_hook;   // multi-GPU: gather all rows' accumulators between adaptive rounds
+  // native NCCL plane (dist_nccl.cpp): communicator + staging for the accumulator all-gather
+  void* nccl_comm = nullptr; bool nccl_own = false;
+  DevBuf<float4> x_send, x_recv;
+  uint64_t collectives = 0;
+  void attach_nccl(const uint8_t id128[128], void* existing_comm, uint32_t rank, uint32_t world);
+  void detach_nccl();
+  void exchange_native();
+  void reduce_native(uint32_t* dev_words, uint64_t n);
   std::function<void(uint32_t*, uint64_t)> reduce_hook;   // multi-GPU: in-place sum-allreduce of 32-bit words on `stream` (photon batches)
   DevBuf<float4> d_seg_buf;    // k_wpool / k_mega: segment sums of a multi-segment launch (contract B10)
   DevBuf<float4> d_pool;       // k_wpool: path contexts, 160 B each, pool_ctx per warp
@@ -138,6 +153,7 @@ struct Context {
   DevBuf<uint32_t> ph_dense;   // one photon batch: [meta | light | loc_w x 4] per shot slot
   Strategy& strategy_for(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh);
   void clear_strategies();
+  void region_error_launch(Strategy& s);
   void region_error(Strategy& s, float stats3[3]);
   void render_take(Strategy& s, uint32_t render_type, bool bounded);
   uint64_t run_adaptive(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange);

@@ -18,6 +18,7 @@ namespace wpt {
 void Context::build_photons() {
   require_device();
   if (photons_ready) return;
+  const auto t_begin = std::chrono::steady_clock::now();
   const uint32_t L = (uint32_t)scene.lights.size();
   if (L == 0) throw std::runtime_error("Invalid range");   // rng.rs:27 — next_in_range(0, 0) panics
   const uint64_t target = cfg.photon_target;
@@ -174,6 +175,8 @@ void Context::build_photons() {
     if (is_node) for (int c = 7; c >= 0; c--) st.push_back(child_base[n] + c);
   }
   photons_ready = true;
+  photon_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  if (std::getenv("WPT_TRACE_PHOTONS")) std::fprintf(stderr, "wpt photon warm-up: %.2f ms (%llu shots, %llu photons, %u octree nodes)\n", photon_build_ms, (unsigned long long)shots, (unsigned long long)stored, nodes);
 }
 
 void Context::photon_sample_batch(const float* pts3, const uint32_t* seeds, uint64_t n, uint32_t* light, float* pdf) {
@@ -201,14 +204,18 @@ Context::Strategy& Context::strategy_for(uint32_t rx, uint32_t ry, uint32_t rw, 
 void Context::clear_strategies() { strategies.clear(); }
 
 // error map + {min, avg, max} of the region (sampling_strategy.rs:133-151, mode-B reduction)
-void Context::region_error(Strategy& s, float stats3[3]) {
+void Context::region_error_launch(Strategy& s) {   // error map + {sum, min, max} into a_stats, no host synchronisation
   const uint32_t N = s.rw * s.rh;
   s.mse.alloc(N);
   a_stats.alloc(4);
-  unsigned long long init[4] = {0ull, 0x7F800000ull, 0ull, 0ull};
+  static const unsigned long long init[4] = {0ull, 0x7F800000ull, 0ull, 0ull};
   WPT_CUDA(cudaMemcpyAsync(a_stats.p, init, sizeof init, cudaMemcpyHostToDevice, stream));
   launch_error_map(d_accum.p, W, H, s.rx, s.ry, s.rw, s.rh, s.mse.p, a_stats.p, stream);
   launches += 1;
+}
+void Context::region_error(Strategy& s, float stats3[3]) {
+  const uint32_t N = s.rw * s.rh;
+  region_error_launch(s);
   unsigned long long out[4];
   WPT_CUDA(cudaMemcpyAsync(out, a_stats.p, sizeof out, cudaMemcpyDeviceToHost, stream));
   WPT_CUDA(cudaStreamSynchronize(stream));
@@ -269,11 +276,7 @@ void Context::render_take(Strategy& s, uint32_t render_type, bool bounded) {
 // Every rank evaluates the (cheap) error map of the whole region from the gathered
 // accumulators, so no reduction is needed; each rank renders only its own rows.
 uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange) {
-  // WPT_TRACE_ROUNDS=1: wall-clock split of the rounds (error map / render / exchange), printed once per call
-  static const bool trace = std::getenv("WPT_TRACE_ROUNDS") != nullptr;
-  double t_err = 0, t_render = 0, t_xchg = 0; uint32_t rounds = 0;
-  auto now = [&] { if (trace) cudaStreamSynchronize(stream); return std::chrono::steady_clock::now(); };
-  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  // with profiling on, CUDA events split every round into error map / render / exchange (prof_ms[2..4], no extra host syncs)
   const uint32_t N = s.rw * s.rh;
   if (!N) return 0;
   if (s.round_left.n < N) { s.round_left.alloc(N); s.take.alloc(N); s.round_spp.alloc(N); launch_fill_u32(s.round_left.p, N, 0, stream); s.left_total = 0; s.started = false; }
@@ -287,19 +290,16 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
         s.left_total = 4ull * N;
         s.started = true;
       } else {
-        float st3[3];
-        auto t0 = now();
-        region_error(s, st3);
-        launch_adaptive_spp(s.mse.p, N, st3[0], st3[1], st3[2], s.round_left.p, d_sampling.p, W, s.rx, s.ry, s.rw, stream);
-        a_stats.alloc(4);
-        WPT_CUDA(cudaMemsetAsync(a_stats.p, 0, sizeof(unsigned long long), stream));
-        launch_sum_u32(s.round_left.p, N, a_stats.p, stream);
-        launches += 2;
-        unsigned long long tot = 0;
-        WPT_CUDA(cudaMemcpyAsync(&tot, a_stats.p, sizeof tot, cudaMemcpyDeviceToHost, stream));
+        // error map, {sum, min, max} and the samples per pixel stay on the device; the host reads back one word, the
+        // round's total (it decides whether the budget ends inside this round)
+        ev_mark(2, true);
+        region_error_launch(s);
+        launch_adaptive_spp(s.mse.p, N, a_stats.p, s.round_left.p, d_sampling.p, W, s.rx, s.ry, s.rw, stream);
+        launches += 1;
+        ev_mark(2, false);
+        WPT_CUDA(cudaMemcpyAsync(h_counters + 15, a_stats.p + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         WPT_CUDA(cudaStreamSynchronize(stream));
-        s.left_total = tot;
-        if (trace) t_err += secs(t0, now());
+        s.left_total = h_counters[15];
       }
       WPT_CUDA(cudaMemcpyAsync(s.round_spp.p, s.round_left.p, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
     }
@@ -321,17 +321,16 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
       launches += 2;
       taken = room;
     }
-    auto t1 = now();
+    ev_mark(3, true);
     render_take(s, render_type, true);   // an adaptive round holds at most 33 samples per pixel
     launch_sub_u32(s.round_left.p, s.take.p, N, stream);
     launches += 1;
+    ev_mark(3, false);
     s.left_total -= taken;
     used += taken;
-    auto t2 = now();
-    if (exchange) exchange();   // multi-GPU: gather the other ranks' rows before the next error map
-    if (trace) { auto t3 = now(); t_render += secs(t1, t2); t_xchg += secs(t2, t3); rounds++; }
+    if (exchange) { ev_mark(4, true); exchange(); ev_mark(4, false); }   // multi-GPU: gather the other ranks' rows before the next error map
+    adaptive_rounds += 1;
   }
-  if (trace) std::fprintf(stderr, "wpt adaptive (rank %u): %u rounds, error map %.3f s, render %.3f s, exchange %.3f s\n", cfg.rank, rounds, t_err, t_render, t_xchg);
   return used;
 }
 
@@ -385,7 +384,7 @@ void Context::compute(uint64_t num_samples) {
       launch_fill_region_rgba(d_sampling.p, W, h.x, 0, h.w, H, 0xFFFF0000u, stream);
       s.painted = true;
     }
-    if (h.hs.adaptive) run_adaptive(s, h.hs.type, ticks, nullptr);
+    if (h.hs.adaptive) run_adaptive(s, h.hs.type, ticks, exchange_hook);   // multi-GPU: the error map needs every rank's rows
     else run_random(s, h.hs.type, ticks);
   }
 }

@@ -12,15 +12,16 @@
 
 namespace wpt {
 
-static int g_sm_count = 0;
-int device_sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+int device_sm_count() {   // of the current device (sessions on different GPUs may differ)
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cache[dev & 63];
+  if (!c) {
+    cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+    if (c <= 0) c = 148;
   }
-  return g_sm_count;
+  return c;
 }
 
 #define TRACE_THREADS 128
@@ -61,12 +62,39 @@ __global__ void k_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t
     uint32_t k = i - nA - nB;
     row = R4 + k / w; col = k % w;
   }
-  pixel[i] = (y0 + row * world + rank) * W + x0 + col;
+  pixel[i] = (y0 + band_row(row, rank, world)) * W + x0 + col;
 }
 void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t rank, uint32_t world, cudaStream_t s) {
-  uint32_t rows = h > rank ? (h - rank + world - 1) / world : 0;
+  uint32_t rows = band_rows(h, rank, world);
   if (!rows || !w) return;
   k_fill_pixels<<<(w * rows + 255) / 256, 256, 0, s>>>(pixel, W, x0, y0, w, rows, rank, world);
+}
+
+// ------------------------------------------------------------------ multi-GPU row exchange (band partition, wpt_types.h)
+__global__ void k_pack_rows(const float4* __restrict__ accum, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rows, uint32_t rank, uint32_t world, float4* __restrict__ send) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * rw) return;
+  uint32_t k = i / rw, col = i - k * rw;
+  send[i] = accum[(size_t)(ry + band_row(k, rank, world)) * W + rx + col];
+}
+__global__ void k_unpack_rows(const float4* __restrict__ recv, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t self, uint32_t world, uint32_t per, float4* __restrict__ accum) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)world * per * rw) return;
+  uint32_t r = (uint32_t)(i / ((size_t)per * rw));
+  uint32_t rem = (uint32_t)(i - (size_t)r * per * rw), k = rem / rw, col = rem - k * rw;
+  if (r == self || k >= band_rows(rh, r, world)) return;   // own rows are in place; the padding of ranks with fewer rows
+  accum[(size_t)(ry + band_row(k, r, world)) * W + rx + col] = recv[i];
+}
+void launch_pack_rows(const float4* accum, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t rank, uint32_t world, uint32_t per, float4* send, cudaStream_t s) {
+  (void)per;
+  uint32_t rows = band_rows(rh, rank, world);
+  if (!rows || !rw) return;
+  k_pack_rows<<<(rows * rw + 255) / 256, 256, 0, s>>>(accum, W, rx, ry, rw, rows, rank, world, send);
+}
+void launch_unpack_rows(const float4* recv, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t rank, uint32_t world, uint32_t per, float4* accum, cudaStream_t s) {
+  size_t n = (size_t)world * per * rw;
+  if (!n) return;
+  k_unpack_rows<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(recv, W, rx, ry, rw, rh, rank, world, per, accum);
 }
 
 // ------------------------------------------------------------------ trace
@@ -241,6 +269,36 @@ void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers
 enum : int { PH_NEED = 0, PH_LOGIC = 1, PH_TRAV = 2, PH_DONE = 3 };
 enum : int { ST_GEN = 0, ST_EXTEND = 1, ST_SHADOW = 2 };
 
+// Scene::trace_g up to the BVH for the triangles / planes variant (scene.rs:162-212): at most two infinite shapes, all planes
+// (plane.rs:80-99), and the root guard, all read from the kernel parameters (constant bank) instead of memory. Same tests in
+// the same order as trav_begin: the first plane hit is accepted as is (scene.rs:438-440), a later one needs 0 < t < best.
+template <int BVH>
+WPT_DEV bool trav_begin_const(const MegaParams& P, const Ray& ray, Trav& tv) {
+  bool have = false; float it = 0.0f; int iid = -1;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    if ((uint32_t)i < P.rp.scene.num_inf) {
+      const float4 q1 = P.inf_q1[i];
+      const F3 nr = xyz(q1);
+      const float n_dot_dir = dot(nr, ray.d);
+      const float t = (q1.w - dot(nr, ray.o)) / n_dot_dir;
+      const bool ok = n_dot_dir != 0.0f && t > 0.0f && (have ? t < it : t <= WPT_INF);
+      if (ok) { have = true; it = t; iid = i; }
+    }
+  }
+  tv.inf_t = it; tv.inf_id = iid;
+  tv.bound = have ? it : WPT_INF;
+  tv.best_id = -1;
+  tv.visits = 0; tv.prims = 0; tv.sp = 0;
+  if (BVH == 4) { tv.lf = 0u; tv.cnt = 0u; return true; }
+  const float4 ra = P.root_a, rb = P.root_b;
+  tv.visits = 1;
+  float h;
+  if (!(box_hit(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, ray, &h) && h < tv.bound)) return false;
+  tv.lf = __float_as_uint(rb.z); tv.cnt = __float_as_uint(rb.w);
+  return true;
+}
+
 template <int BVH, bool SIMPLE, int MINB, int RT>
 __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
@@ -248,17 +306,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const unsigned FULL = 0xFFFFFFFFu;
   const unsigned lane = threadIdx.x & 31u;
   int phase = PH_NEED, what = ST_GEN;
-  uint32_t pix = 0, s = 0, s_end = 0;
+  uint32_t pixp = 0, s = 0, s_end = 0;   // pixp = px | py << 16 of the slot's pixel
   PathRegs ps; ps.color = f3(0, 0, 0); ps.T = f3(1, 1, 1); ps.rng.s = 1u; ps.bounced = false;
   Ray ray = make_ray(f3(0, 0, 0), f3(1, 1, 1));
   Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0;
   F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
-  // ray / visit / primitive-test / path counters live in shared memory (four registers less in a kernel that spills):
-  // fire-and-forget shared atomics, flushed to the global counters when the block is done
-  __shared__ unsigned int s_cnt[4];
-  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
-  __syncthreads();
+  // ray / visit / primitive-test / path counters: warp sums (ballot + redux.sync) in uniform registers, one set of global
+  // atomics per warp at the end — no per-ray atomics
+  uint32_t n_rays = 0, n_visits = 0, n_paths = 0, n_prims = 0;
   uint32_t chunk_next = 0, chunk_end = 0, spare_next = 0, spare_end = 0; bool queue_empty = false;   // warp-uniform
   F3 acc_rgb = f3(0, 0, 0);   // sum of this segment's samples (contract B10), added to the pixel's accumulator (render_target.rs:8) when the segment is done
   uint32_t slot_id = 0;
@@ -292,7 +348,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           if (P.seg_list) { uint32_t e = P.seg_list[idx]; pslot = e >> 3; j = e & 7u; }   // strategy round: (pixel slot, segment) from the list
           else if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
           slot_id = idx;
-          pix = P.pixel[pslot];
+          const uint32_t pix = P.pixel[pslot];
+          const uint32_t py = pix / P.rp.W;   // once per slot, not per sample
+          pixp = (pix - py * P.rp.W) | (py << 16);
           uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;
           uint32_t s0 = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
           uint32_t b = min(j * P.seg_len, spp);
@@ -315,13 +373,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
     unsigned logic = __ballot_sync(FULL, phase == PH_LOGIC);
     if (!(trav | logic)) break;
     if (__popc(trav) >= (int)P.t_hi || !logic) {
-      // ---- traversal burst, while-while: cheap inner steps until (almost) every lane of the
-      // burst waits at a leaf, then one leaf step with all of them (triangle tests are the
-      // expensive body: run them with as many lanes as possible)
+      // ---- traversal burst, while-while: one step per iteration — an inner-node step while enough of the burst's lanes
+      // are at inner nodes, else a leaf step with every lane that waits at a leaf (triangle tests are the expensive
+      // body: run them with as many lanes as possible), then one shared pop
       do {
-        // one step per iteration: an inner-node step while enough of the burst's lanes are at
-        // inner nodes, else a leaf step with every lane that waits at a leaf (triangle tests are
-        // the expensive body: run them with as many lanes as possible); then one shared pop
         const bool tr = phase == PH_TRAV;
         const bool leaf = tr && trav_at_leaf<BVH>(tv);
         const int n_inner = __popc(__ballot_sync(FULL, tr && !leaf));
@@ -354,15 +409,25 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
     // whose ray of half 0 ended at the root guard — is shaded. Both halves regenerate finished
     // lanes. So all lanes of the warp meet in the (expensive) shading code once per pass instead
     // of alternating shade / shadow-resolve in two populations that never line up.
+    // (MEGA_ONE_BEGIN: one pass = every LOGIC lane consumes one result — shadow or hit — and starts at most one ray,
+    //  so the plane tests + root guard have a single code site.)
+#ifdef MEGA_ONE_BEGIN
+    {
+      const bool cons = phase == PH_LOGIC && what != ST_GEN;
+#else
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
-      if (phase != PH_LOGIC) continue;
-      bool start = false;
-      if (what == (half == 0 ? ST_SHADOW : ST_EXTEND)) {
-        GHit g = trav_result(tv);
-        atomicAdd(&s_cnt[0], 1u); atomicAdd(&s_cnt[1], g.visits); if (g.prims) atomicAdd(&s_cnt[3], g.prims);
-        bool finish = false;
-        if (half == 0) {   // Scene::shadow_ray, scene.rs:114-132
+      const bool cons = phase == PH_LOGIC && what == (half == 0 ? ST_SHADOW : ST_EXTEND);
+#endif
+      bool start = false, finish = false;
+      GHit g; g.t = 0.0f; g.id = -1; g.visits = 0; g.prims = 0;
+      if (cons) g = trav_result(tv);
+      {
+        const unsigned mc = __ballot_sync(FULL, cons);
+        if (mc) { n_rays += (uint32_t)__popc(mc); n_visits += __reduce_add_sync(FULL, g.visits); n_prims += __reduce_add_sync(FULL, g.prims); }
+      }
+      if (cons) {
+        if (what == ST_SHADOW) {   // Scene::shadow_ray, scene.rs:114-132
           bool occluded = g.id >= 0 && g.t < sh_len && g.id != sh_light;
           if (!occluded) ps.color = ps.color + contrib;
           if (alive_after_shadow) { ray = make_ray(ext_o, ext_d); what = ST_EXTEND; start = true; }
@@ -378,14 +443,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           } else if (so.survive) { ray = make_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
           else finish = true;
         }
-        if (finish) { acc_rgb = acc_rgb + ps.color; atomicAdd(&s_cnt[2], 1u); s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
+        if (finish) { acc_rgb = acc_rgb + ps.color; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
       }
-      if (what == ST_GEN) {
-        if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream
-          ps.rng.s = stream_seed(pix, s, STREAM_PATH, P.rp.base_seed);
+      n_paths += (uint32_t)__popc(__ballot_sync(FULL, finish));
+      if (phase == PH_LOGIC && what == ST_GEN) {
+        const uint32_t px = pixp & 0xFFFFu, py = pixp >> 16, pix = py * P.rp.W + px;
+        if (s < s_end) {   // tracer.rs:176-196 — sample s of this pixel on its own stream (stream_seed with the constant part from the host)
+          uint32_t sd = mix32(pix + mix32(s + P.seed_path));
+          ps.rng.s = sd == 0 ? 0xBABABEBEu : sd;
           float j1 = ps.rng.f32();
           float j2 = ps.rng.f32();
-          uint32_t py = pix / P.rp.W, px = pix - py * P.rp.W;
           ray = camera_ray(P.rp.cam, px, py, j1, j2);
           ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
           what = ST_EXTEND; start = true;
@@ -398,12 +465,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           phase = PH_NEED;
         }
       }
-      if (start && trav_begin<BVH, SIMPLE>(sc, ray, tv)) phase = PH_TRAV;
+      if (start && (SIMPLE ? trav_begin_const<BVH>(P, ray, tv) : trav_begin<BVH, SIMPLE>(sc, ray, tv))) phase = PH_TRAV;
     }
   }
   // ---- counters
-  __syncthreads();
-  if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  if (lane == 0) {
+    if (n_rays) atomicAdd(&P.counters[0], (unsigned long long)n_rays);
+    if (n_visits) atomicAdd(&P.counters[1], (unsigned long long)n_visits);
+    if (n_paths) atomicAdd(&P.counters[2], (unsigned long long)n_paths);
+    if (n_prims) atomicAdd(&P.counters[3], (unsigned long long)n_prims);
+  }
 #ifdef MEGA_INSTR
   if (lane == 0) { atomicAdd(&P.counters[4], i_lp); atomicAdd(&P.counters[5], i_ll); atomicAdd(&P.counters[6], i_ts); atomicAdd(&P.counters[7], i_tl); }
   if (lane == 1) atomicAdd(&P.counters[8], i_sh);
@@ -742,23 +813,32 @@ void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, 
 }
 WPT_DEV uint32_t sampling_rgba(F3 v) { return 0xFF000000u | to_u8(v.x) | (to_u8(v.y) << 8) | (to_u8(v.z) << 16); }
 // error -> samples this round (1..33) + the sampling-density view (sampling_strategy.rs:154-174)
-__global__ void k_adaptive_spp(const float* __restrict__ mse, uint32_t n, float mn, float avg, float mx, uint32_t* round_left, uint32_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw) {
+// stats (device): [0] = sum of the errors in 2^-40 fixed point, [1] = min bits, [2] = max bits (k_error_map), [3] = total of the
+// samples this round allocates (written here): the host reads one word per round instead of synchronising twice
+__global__ void k_adaptive_spp(const float* __restrict__ mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint32_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float e = mse[i];
-  float sc = (e < avg) ? 0.5f * ((e - mn) / (avg - mn)) : 0.5f + 0.5f * ((e - avg) / (mx - avg));
-  sc = fmaxf(fminf(sc, 1.0f), 0.0f);
-  float c = ceilf(1.0f + sc * 32.0f);
-  round_left[i] = c > 0.0f ? (uint32_t)c : 0u;
-  F3 col;
-  if (mn == mx) col = f3(0, 0, 0);
-  else if (sc < 0.5f) col = f3(0.0f, 1.0f, 0.0f) * (1.0f - 2.0f * sc) + f3(0.0f, 0.0f, 1.0f) * 2.0f * sc;   // mix_color, :224-230
-  else col = f3(0.0f, 0.0f, 1.0f) * (1.0f - 2.0f * (sc - 0.5f)) + f3(1.0f, 0.0f, 0.0f) * 2.0f * (sc - 0.5f);
-  sampling_rgba8[(size_t)(ry + i / rw) * W + rx + i % rw] = sampling_rgba(col);
+  const float mn = __uint_as_float((uint32_t)stats[1]), mx = __uint_as_float((uint32_t)stats[2]);
+  const float avg = (float)(((double)stats[0] * (1.0 / 1099511627776.0)) / (double)n);
+  unsigned long long mine = 0;
+  if (i < n) {
+    float e = mse[i];
+    float sc = (e < avg) ? 0.5f * ((e - mn) / (avg - mn)) : 0.5f + 0.5f * ((e - avg) / (mx - avg));
+    sc = fmaxf(fminf(sc, 1.0f), 0.0f);
+    float c = ceilf(1.0f + sc * 32.0f);
+    uint32_t spp = c > 0.0f ? (uint32_t)c : 0u;
+    round_left[i] = spp; mine = spp;
+    F3 col;
+    if (mn == mx) col = f3(0, 0, 0);
+    else if (sc < 0.5f) col = f3(0.0f, 1.0f, 0.0f) * (1.0f - 2.0f * sc) + f3(0.0f, 0.0f, 1.0f) * 2.0f * sc;   // mix_color, :224-230
+    else col = f3(0.0f, 0.0f, 1.0f) * (1.0f - 2.0f * (sc - 0.5f)) + f3(1.0f, 0.0f, 0.0f) * 2.0f * (sc - 0.5f);
+    sampling_rgba8[(size_t)(ry + i / rw) * W + rx + i % rw] = sampling_rgba(col);
+  }
+  mine = warp_sum_u64(mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&stats[3], mine);
 }
-void launch_adaptive_spp(const float* mse, uint32_t n, float mn, float avg, float mx, uint32_t* round_left, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, cudaStream_t s) {
+void launch_adaptive_spp(const float* mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, cudaStream_t s) {
   if (!n) return;
-  k_adaptive_spp<<<(n + 255) / 256, 256, 0, s>>>(mse, n, mn, avg, mx, round_left, reinterpret_cast<uint32_t*>(sampling_rgba8), W, rx, ry, rw);
+  k_adaptive_spp<<<(n + 255) / 256, 256, 0, s>>>(mse, n, stats, round_left, reinterpret_cast<uint32_t*>(sampling_rgba8), W, rx, ry, rw);
 }
 // fill a region of the sampling view / a u32 array
 __global__ void k_fill_region_rgba(uint32_t* rgba, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t value) {

@@ -64,7 +64,10 @@ struct MegaParams {
   float4* pool;                   // k_wpool: path contexts, [warp][pool_ctx][10 x float4]
   uint32_t pool_ctx;              // k_wpool: contexts per warp (<= 128)
   uint32_t chunk;                 // slots a warp fetches at a time (multiple of 32)
-  uint32_t simple_scene;          // shapes are triangles and planes only: kernel variant without torus / box code
+  uint32_t simple_scene;          // triangles and planes only, at most two infinite shapes: kernel variant without torus / box code
+  float4 inf_q1[2];               // simple_scene: (normal, normal.location) of the infinite planes (shape record q1)
+  float4 root_a, root_b;          // simple_scene: the BVH2 root node (box + left_first, count)
+  uint32_t seed_path;             // mix32(STREAM_PATH ^ base_seed): the constant part of a path's stream seed
   uint32_t* work_counter;         // zeroed before the launch
   unsigned long long* counters;
 };
@@ -89,6 +92,9 @@ void launch_clear_pixels(float4* buf, const uint32_t* pixel, uint32_t npix, cuda
 void launch_resolve_rgba(const float4* accum, uint8_t* rgba, uint32_t n, cudaStream_t s);
 void launch_primary_probe(const RenderParams& rp, int32_t* ids, uint32_t* visits, float* dist, cudaStream_t s);
 void launch_trace_batch(const RenderParams& rp, const float* o, const float* d, uint64_t n, int32_t* ids, float* dist, uint32_t* visits, float* normals, cudaStream_t s);
+// multi-GPU accumulator exchange: this rank's rows of the region -> contiguous staging (padded to `per` rows), and back from all ranks' staging
+void launch_pack_rows(const float4* accum, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t rank, uint32_t world, uint32_t per, float4* send, cudaStream_t s);
+void launch_unpack_rows(const float4* recv, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t rank, uint32_t world, uint32_t per, float4* accum, cudaStream_t s);
 void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t rank, uint32_t world, cudaStream_t s);
 
 // photons
@@ -99,7 +105,7 @@ void launch_octree_cdf(const unsigned long long* fx, float* bins, float* cum, ui
 void launch_photon_sample_batch(const DPhotonTree& t, const float* pts, const uint32_t* seeds, uint64_t n, uint32_t* light, float* pdf, cudaStream_t s);
 // adaptive / random strategies
 void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, cudaStream_t s);
-void launch_adaptive_spp(const float* mse, uint32_t n, float mn, float avg, float mx, uint32_t* round_left, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, cudaStream_t s);
+void launch_adaptive_spp(const float* mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, cudaStream_t s);
 void launch_fill_region_rgba(uint8_t* rgba, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t value, cudaStream_t s);
 void launch_fill_u32(uint32_t* a, uint32_t n, uint32_t v, cudaStream_t s);
 void launch_sum_u32(const uint32_t* a, uint32_t n, unsigned long long* out, cudaStream_t s);

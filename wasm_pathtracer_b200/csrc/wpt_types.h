@@ -79,6 +79,26 @@ struct DScene {
   DTexture tex[WPT_MAX_TEXTURES];   // extension: textured diffuse
 };
 
+// Multi-GPU pixel partition: the region's rows are cut into bands of WPT_BAND rows and rank r of `world`
+// owns the bands b with b % world == r — whole 8x4 warp tiles on every rank, and the bunny / sky imbalance still averaged out.
+#define WPT_BAND 4u
+#if defined(__CUDACC__)
+#define WPT_HD __host__ __device__ inline
+#else
+#define WPT_HD inline
+#endif
+WPT_HD uint32_t band_rows(uint32_t h, uint32_t rank, uint32_t world) {   // rows of an h-row region owned by `rank`
+  const uint32_t nb = (h + WPT_BAND - 1u) / WPT_BAND;
+  const uint32_t mine = nb > rank ? (nb - rank + world - 1u) / world : 0u;
+  if (!mine) return 0u;
+  uint32_t rows = mine * WPT_BAND;
+  if (rank + (mine - 1u) * world == nb - 1u) rows -= nb * WPT_BAND - h;   // the ragged last band
+  return rows;
+}
+WPT_HD uint32_t band_row(uint32_t r, uint32_t rank, uint32_t world) {     // the rank's r-th row -> row of the region
+  return ((r / WPT_BAND) * world + rank) * WPT_BAND + (r % WPT_BAND);
+}
+
 // Mode-B accumulation contract B10: render_exact sums a pixel's samples in segments of this length
 #define WPT_SEGMENT_LEN 8u
 

@@ -15,8 +15,17 @@
 //              [--seconds S] [--ticks N] [--samples N] [--tick-ms 50] [--sampling-view]
 //              [--out frame.png|frame.ppm] [--camera x,y,z,rx,ry] [--quiet]
 //
+// Frame mode — one full-frame render on 1..N GPUs through the library's native NCCL plane (no Python anywhere):
+//   wpt_render --frame-spp S [--type 0|1|2] [--bvh 2|4] [--adaptive] [--photons N]
+//              [--world N --rank R --nccl-id-file PATH] [--device D]        (defaults: WORLD_SIZE / RANK / LOCAL_RANK)
+// One process per GPU, e.g.  for r in 0 1; do tools/wpt_render --frame-spp 16 --world 2 --rank $r --nccl-id-file /tmp/id ... & done; wait
+// (or under torchrun / mpirun, which set the environment variables). Rank 0 creates the NCCL unique id and writes it to
+// the file, the others wait for it; every rank renders its 4-row bands, wpt_ctx_gather_frame() all-gathers the
+// accumulators, rank 0 stores the image. The FNV-1a hash of the RGBA8 frame is printed: it equals the 1-GPU run's.
+//
 // Build: g++ -O2 -std=c++17 tools/wpt_render.cpp -Iinclude -Lwasm_pathtracer_b200 -lwpt -Wl,-rpath,'$ORIGIN/../wasm_pathtracer_b200' -o tools/wpt_render
 #include <chrono>
+#include <ctime>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -84,8 +93,71 @@ static bool write_ppm(const std::string& path, const uint8_t* rgba, uint32_t w, 
   return (bool)f;
 }
 
+static uint64_t fnv1a(const uint8_t* p, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+static uint32_t env_u32(const char* name, uint32_t dflt) { const char* v = std::getenv(name); return v ? (uint32_t)std::atoi(v) : dflt; }
+
+// Frame mode: handle API + native NCCL plane (include/wpt.h, "Native multi-GPU plane").
+static int frame_mode(uint32_t scene, uint32_t w, uint32_t h, const float cam[5], const std::string& obj, uint32_t type, uint32_t bvh, bool adaptive, uint32_t spp,
+                      uint64_t photons, uint32_t rank, uint32_t world, int device, const std::string& id_file, const std::string& out, bool quiet) {
+  wpt_ctx* c = wpt_ctx_create(device, w, h, scene, cam[0], cam[1], cam[2], cam[3], cam[4]);
+  if (!c) die("ctx_create");
+  if (!obj.empty() && wpt_ctx_load_obj(c, 1, obj.c_str(), 1) < 0) die("load_obj");
+  wpt_config cfg;
+  if (wpt_ctx_get_config(c, &cfg) != 0) die("get_config");
+  cfg.bvh_kind = bvh; cfg.render_type = type; if (photons) cfg.photon_target = photons;
+  if (wpt_ctx_set_config(c, &cfg) != 0) die("set_config");
+  uint8_t id[128] = {0};
+  if (world > 1) {
+    if (id_file.empty()) { std::fprintf(stderr, "wpt_render: --nccl-id-file is needed when --world > 1\n"); return 2; }
+    if (rank == 0) {
+      if (wpt_nccl_unique_id(id) != 0) die("nccl_unique_id");
+      std::string tmp = id_file + ".tmp";
+      { std::ofstream f(tmp, std::ios::binary); f.write((const char*)id, 128); }
+      std::rename(tmp.c_str(), id_file.c_str());
+    } else {
+      for (int tries = 0;; tries++) {
+        std::ifstream f(id_file, std::ios::binary);
+        if (f && f.read((char*)id, 128)) break;
+        if (tries > 6000) { std::fprintf(stderr, "wpt_render: no NCCL id in %s\n", id_file.c_str()); return 1; }
+        struct timespec ts = {0, 10 * 1000 * 1000}; nanosleep(&ts, nullptr);
+      }
+    }
+  }
+  if (wpt_ctx_attach_nccl(c, id, rank, world) != 0) die("attach_nccl");
+  using clock = std::chrono::steady_clock;
+  auto t0 = clock::now();
+  if (type == WPT_PNEE && wpt_ctx_build_photons(c) != 0) die("build_photons");
+  wpt_ctx_synchronize(c);
+  double warm = std::chrono::duration<double>(clock::now() - t0).count();
+  t0 = clock::now();
+  if (adaptive) { if (wpt_ctx_render_adaptive(c, (uint64_t)w * h * spp) < 0) die("render_adaptive"); }   // exchanges between the rounds
+  else { if (wpt_ctx_render_exact(c, spp) != 0) die("render_exact"); if (wpt_ctx_gather_frame(c) != 0) die("gather_frame"); }
+  const uint8_t* frame = wpt_ctx_results(c, 0);
+  if (!frame) die("results");
+  double secs = std::chrono::duration<double>(clock::now() - t0).count();
+  uint64_t st[8] = {0};
+  wpt_ctx_stats(c, st);
+  std::printf("{\"rank\": %u, \"world\": %u, \"seconds\": %.4f, \"photon_warmup_s\": %.4f, \"rays\": %llu, \"paths\": %llu, \"node_visits\": %llu, \"frame_fnv1a\": \"%016llx\"}\n",
+              rank, world, secs, warm, (unsigned long long)st[0], (unsigned long long)st[1], (unsigned long long)st[2], (unsigned long long)fnv1a(frame, (size_t)w * h * 4));
+  int rc = 0;
+  if (rank == 0 && !out.empty()) {
+    bool ok = out.size() > 4 && out.substr(out.size() - 4) == ".ppm" ? write_ppm(out, frame, w, h) : write_png(out, frame, w, h);
+    if (!ok) { std::fprintf(stderr, "wpt_render: cannot write %s\n", out.c_str()); rc = 1; }
+  }
+  (void)quiet;
+  wpt_ctx_detach_nccl(c);
+  wpt_ctx_destroy(c);
+  return rc;
+}
+
 int main(int argc, char** argv) {
   uint32_t scene = WPT_SCENE_BUNNY, w = 512, h = 512;
+  uint32_t f_spp = 0, f_type = WPT_NORMAL_NEE, f_bvh = 2, f_rank = env_u32("RANK", 0), f_world = env_u32("WORLD_SIZE", 1); bool f_adaptive = false;
+  int f_device = (int)env_u32("LOCAL_RANK", 0); uint64_t f_photons = 0; std::string id_file;
   uint32_t left = WPT_NORMAL_NEE, right = WPT_PNEE, left_ad = 0, right_ad = 1, light_debug = 0;   // the reference's defaults (wasm_interface.rs:90-101)
   double seconds = 2.0, tick_ms = 50.0;
   uint64_t max_ticks = 0, max_samples = 0;
@@ -110,10 +182,21 @@ int main(int argc, char** argv) {
     else if (a == "--sampling-view") sampling_view = true;
     else if (a == "--quiet") quiet = true;
     else if (a == "--out") out = next();
+    else if (a == "--frame-spp") f_spp = (uint32_t)std::atoi(next());
+    else if (a == "--type") f_type = (uint32_t)std::atoi(next());
+    else if (a == "--bvh") f_bvh = (uint32_t)std::atoi(next());
+    else if (a == "--adaptive") f_adaptive = true;
+    else if (a == "--photons") f_photons = std::strtoull(next(), nullptr, 10);
+    else if (a == "--rank") f_rank = (uint32_t)std::atoi(next());
+    else if (a == "--world") f_world = (uint32_t)std::atoi(next());
+    else if (a == "--device") f_device = std::atoi(next());
+    else if (a == "--nccl-id-file") id_file = next();
     else if (a == "--camera") { if (std::sscanf(next(), "%f,%f,%f,%f,%f", cam, cam + 1, cam + 2, cam + 3, cam + 4) != 5) { std::fprintf(stderr, "--camera x,y,z,rx,ry\n"); return 2; } cam_set = true; }
     else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
   if (!cam_set && scene == WPT_SCENE_MUSEUM) { const float m[5] = {0.0f, 16.34f, -23.76f, 0.54f, 0.0f}; std::memcpy(cam, m, sizeof m); }   // index.ts:156
+
+  if (f_spp) return frame_mode(scene, w, h, cam, obj, f_type, f_bvh, f_adaptive, f_spp, f_photons, f_rank, f_world, f_device, id_file, out, quiet);
 
   // handleInit
   wpt_init(w, h, scene, cam[0], cam[1], cam[2], cam[3], cam[4]);

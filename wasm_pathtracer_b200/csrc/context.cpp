@@ -359,14 +359,19 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   P.t_hi = (uint32_t)env_hi; P.t_lo = (uint32_t)env_lo; P.t_inner = (uint32_t)env_ti; P.inner_reps = (uint32_t)std::max(1, env_reps);
   static const int env_chunk = std::getenv("WPT_MEGA_CHUNK") ? std::atoi(std::getenv("WPT_MEGA_CHUNK")) : 32;
   P.chunk = (uint32_t)env_chunk;
-  P.simple_scene = 1;
-  for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { P.simple_scene = 0; break; }
-  for (const HostMaterial& m : scene.mats) if (m.kind != MAT_DIFFUSE && m.kind != MAT_EMISSIVE) { P.simple_scene = 0; break; }
-  if (scene.num_inf > 2) P.simple_scene = 0;   // the variant reads its (at most two) infinite planes from the kernel parameters
-  if (std::getenv("WPT_NO_SIMPLE")) P.simple_scene = 0;
-  if (P.simple_scene) {
+  // kernel variant by scene content: triangles + planes only / the reference's primitives and materials / everything
+  P.scene_kind = 0;
+  for (const HostShape& sh : scene.shapes) {
+    if (sh.type == SH_SPHERE || sh.type == SH_SQUARE) { P.scene_kind = 2; break; }
+    if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) P.scene_kind = 1;
+  }
+  for (const HostMaterial& m : scene.mats) if (m.kind != MAT_DIFFUSE && m.kind != MAT_EMISSIVE) { P.scene_kind = 2; break; }
+  if (std::getenv("WPT_NO_SIMPLE")) P.scene_kind = 2;
+  {
+    // the infinite shapes are planes (only a Plane has no finite box, bvh.rs:376-394), at most two in the reference's
+    // scenes: they and the BVH2 root node travel in the kernel parameters (constant bank)
     const DShape* shp = reinterpret_cast<const DShape*>((const char*)h_scene_blob + blob_off[2]);
-    for (uint32_t i = 0; i < scene.num_inf; i++) P.inf_q1[i] = shp[i].q1;
+    for (uint32_t i = 0; i < scene.num_inf && i < 2; i++) P.inf_q1[i] = shp[i].q1;
     const DNode2* n2 = reinterpret_cast<const DNode2*>((const char*)h_scene_blob + blob_off[0]);
     if (blob_len[0] >= sizeof(DNode2)) { P.root_a = n2[0].a; P.root_b = n2[0].b; }
   }
@@ -401,7 +406,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
 
 // cfg.engine: 0 = persistent path kernel k_mega (default), 1 = multi-kernel wavefront, 4 = experimental warp-pool kernel k_wpool
 void Context::run_paths(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp) {
-  if (cfg.engine == 1) run_wavefront(render_type, d_spp_per_slot, uniform_spp);
+  if (use_wavefront()) run_wavefront(render_type, d_spp_per_slot, uniform_spp);
   else run_persistent(render_type, d_spp_per_slot, uniform_spp);
 }
 
@@ -410,7 +415,7 @@ void Context::render_exact(uint32_t spp) {
   uint32_t rx, ry, rw, rh;
   region(&rx, &ry, &rw, &rh);
   ensure_slots(rx, ry, rw, rh);
-  if (cfg.engine == 1) {   // the wavefront engine runs the segments of contract B10 one after the other
+  if (use_wavefront()) {   // the wavefront engine runs the segments of contract B10 one after the other
     for (uint32_t rem = spp; rem > 0;) { uint32_t m = std::min(rem, WPT_SEGMENT_LEN); run_wavefront(cfg.render_type, nullptr, m); rem -= m; }
   } else {
     // one launch per call where the segment-sum buffer allows it (16 B per pixel and segment, capped at 2 GiB and 64

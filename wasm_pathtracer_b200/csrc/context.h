@@ -178,6 +178,8 @@ struct Context {
   WaveBuffers wave_buffers();
   void region(uint32_t* rx, uint32_t* ry, uint32_t* rw, uint32_t* rh) const;
 
+  // the persistent kernels read at most two infinite planes from their parameters: scenes with more run on the wavefront engine
+  bool use_wavefront() const { return cfg.engine == 1 || scene.num_inf > 2; }
   // drivers
   void run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp);
   void run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slot, uint32_t uniform_spp);

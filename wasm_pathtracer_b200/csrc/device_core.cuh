@@ -11,6 +11,9 @@ namespace wpt {
 #define WPT_DEV __device__ __forceinline__
 #define WPT_STACK 64          // (node, entry distance) entries; host checks BVH depth against it
 #define WPT_INF CUDART_INF_F
+// kernel variants by scene content: triangles + planes only / the reference's primitives and materials (+ torus, box) /
+// everything incl. the extension (sphere, square, textures, reflect / refract — DESIGN.md 9)
+enum : int { K_SIMPLE = 0, K_REF = 1, K_EXT = 2 };
 
 // ------------------------------------------------------------------ vectors (math/vec3.rs)
 struct F3 { float x, y, z; };
@@ -114,6 +117,13 @@ WPT_DEV float box_hit_x4(float x0, float y0, float z0, float x1, float y1, float
 }
 
 // ------------------------------------------------------------------ roots 0.0.4 quartic (f64)
+// The solver is rarely-executed code that has to stay small (instruction cache): one out-of-line copy of every f64
+// library routine, division and square root it uses — the same routines, hence the same bits, a third of the code.
+static __device__ __noinline__ double nl_div(double a, double b) { return a / b; }
+static __device__ __noinline__ double nl_sqrt(double a) { return sqrt(a); }
+static __device__ __noinline__ double nl_cos(double a) { return cos(a); }
+static __device__ __noinline__ double nl_acos(double a) { return acos(a); }
+static __device__ __noinline__ double nl_cbrt(double a) { return cbrt(a); }
 struct Roots4 {
   int n; double v[4];
   WPT_DEV void add(double x) {
@@ -129,37 +139,37 @@ static __device__ __noinline__ void d_quadratic_normalized(double a1, double a0,
   if (disc < 0.0) return;
   double h = a1 / 2.0;
   if (disc == 0.0) { r.add(-h); return; }
-  double sq = sqrt(disc);
+  double sq = nl_sqrt(disc);
   r.add(-h - sq / 2.0);
   r.add(-h + sq / 2.0);
 }
 static __device__ __noinline__ void d_quadratic(double a2, double a1, double a0, Roots4& r) {
-  if (a2 == 0.0) { if (a1 != 0.0) r.add(-a0 / a1); return; }
+  if (a2 == 0.0) { if (a1 != 0.0) r.add(nl_div(-a0, a1)); return; }
   double disc = a1 * a1 - 4.0 * a2 * a0;
   if (disc < 0.0) return;
   double a2x2 = 2.0 * a2;
-  if (disc == 0.0) { r.add(-a1 / a2x2); return; }
-  double sq = sqrt(disc);
-  r.add((-a1 - sq) / a2x2);
-  r.add((-a1 + sq) / a2x2);
+  if (disc == 0.0) { r.add(nl_div(-a1, a2x2)); return; }
+  double sq = nl_sqrt(disc);
+  r.add(nl_div(-a1 - sq, a2x2));
+  r.add(nl_div(-a1 + sq, a2x2));
 }
 static __device__ __noinline__ void d_cubic_normalized(double a2, double a1, double a0, Roots4& out) {
-  double q = (3.0 * a1 - a2 * a2) / 9.0;
-  double r = (9.0 * a2 * a1 - 27.0 * a0 - 2.0 * a2 * a2 * a2) / 54.0;
+  double q = nl_div(3.0 * a1 - a2 * a2, 9.0);
+  double r = nl_div(9.0 * a2 * a1 - 27.0 * a0 - 2.0 * a2 * a2 * a2, 54.0);
   double q3 = q * q * q;
   double d = q3 + r * r;
-  double a2_div_3 = a2 / 3.0;
+  double a2_div_3 = nl_div(a2, 3.0);
   if (d < 0.0) {
-    double phi_3 = acos(r / sqrt(-q3)) / 3.0;
-    double sqrt_q_2 = 2.0 * sqrt(-q);
+    double phi_3 = nl_div(nl_acos(nl_div(r, nl_sqrt(-q3))), 3.0);
+    double sqrt_q_2 = 2.0 * nl_sqrt(-q);
     const double two_third_pi = 2.0943951023931954923;
-    out.add(sqrt_q_2 * cos(phi_3) - a2_div_3);
-    out.add(sqrt_q_2 * cos(phi_3 - two_third_pi) - a2_div_3);
-    out.add(sqrt_q_2 * cos(phi_3 + two_third_pi) - a2_div_3);
+    out.add(sqrt_q_2 * nl_cos(phi_3) - a2_div_3);
+    out.add(sqrt_q_2 * nl_cos(phi_3 - two_third_pi) - a2_div_3);
+    out.add(sqrt_q_2 * nl_cos(phi_3 + two_third_pi) - a2_div_3);
   } else {
-    double sqrt_d = sqrt(d);
-    double s = cbrt(r + sqrt_d);
-    double t = cbrt(r - sqrt_d);
+    double sqrt_d = nl_sqrt(d);
+    double s = nl_cbrt(r + sqrt_d);
+    double t = nl_cbrt(r - sqrt_d);
     out.add(s + t - a2_div_3);
     if (s == t && s + t != 0.0) out.add(-(s + t) / 2.0 - a2_div_3);
   }
@@ -167,14 +177,14 @@ static __device__ __noinline__ void d_cubic_normalized(double a2, double a1, dou
 static __device__ __noinline__ void d_cubic(double a3, double a2, double a1, double a0, Roots4& r) {
   if (a3 == 0.0) { d_quadratic(a2, a1, a0, r); return; }
   if (a2 == 0.0 && a1 == 0.0 && a0 == 0.0) { r.add(0.0); return; }
-  d_cubic_normalized(a2 / a3, a1 / a3, a0 / a3, r);
+  d_cubic_normalized(nl_div(a2, a3), nl_div(a1, a3), nl_div(a0, a3), r);
 }
 static __device__ __noinline__ void d_biquadratic(double a4, double a2, double a0, Roots4& out) {
   Roots4 q; q.n = 0;
   d_quadratic(a4, a2, a0, q);
   for (int i = 0; i < q.n; i++) {
     double x = q.v[i];
-    if (x > 0.0) { double s = sqrt(x); out.add(-s); out.add(s); }
+    if (x > 0.0) { double s = nl_sqrt(x); out.add(-s); out.add(s); }
     else if (x == 0.0) out.add(0.0);
   }
 }
@@ -191,9 +201,9 @@ static __device__ __noinline__ void d_quartic_depressed(double a2, double a1, do
   double y = res.v[res.n - 1];
   double a2_plus_2y = a2 + 2.0 * y;
   if (a2_plus_2y > 0.0) {
-    double s = sqrt(a2_plus_2y);
-    double q0a = a2 + y - a1_div_2 / s;
-    double q0b = a2 + y + a1_div_2 / s;
+    double s = nl_sqrt(a2_plus_2y);
+    double q0a = a2 + y - nl_div(a1_div_2, s);
+    double q0b = a2 + y + nl_div(a1_div_2, s);
     Roots4 ra; ra.n = 0; Roots4 rb; rb.n = 0;
     d_quadratic_normalized(s, q0a, ra);
     d_quadratic_normalized(-s, q0b, rb);
@@ -222,23 +232,24 @@ static __device__ __noinline__ void d_quartic(double a4, double a3, double a2, d
     bool triple = delta0 == 0.0;
     bool quadruple = triple && dd == 0.0;
     bool no_roots = dd == 0.0 && pp > 0.0 && rr == 0.0;
-    if (quadruple) { out.add(-a3 / (4.0 * a4)); return; }
+    if (quadruple) { out.add(nl_div(-a3, 4.0 * a4)); return; }
     if (triple) {
-      double x0 = (-72.0 * a4 * a4 * a0 + 10.0 * a4 * a2 * a2 - 3.0 * a3 * a3 * a2) /
-                  (9.0 * (8.0 * a4 * a4 * a1 - 4.0 * a4 * a3 * a2 + a3 * a3 * a3));
+      double x0 = nl_div(-72.0 * a4 * a4 * a0 + 10.0 * a4 * a2 * a2 - 3.0 * a3 * a3 * a2,
+                         9.0 * (8.0 * a4 * a4 * a1 - 4.0 * a4 * a3 * a2 + a3 * a3 * a3));
       out.add(x0);
-      out.add(-(a3 / a4 + 3.0 * x0));
+      out.add(-(nl_div(a3, a4) + 3.0 * x0));
       return;
     }
     if (no_roots) return;
   } else if (discriminant > 0.0 && (pp > 0.0 || dd > 0.0)) return;
   double a4_pow_2 = a4 * a4, a4_pow_3 = a4_pow_2 * a4, a4_pow_4 = a4_pow_2 * a4_pow_2;
-  double p = pp / (8.0 * a4_pow_2);
-  double q = rr / (8.0 * a4_pow_3);
-  double r = (dd + 16.0 * a4_pow_2 * (12.0 * a0 * a4 - 3.0 * a1 * a3 + a2 * a2)) / (256.0 * a4_pow_4);
+  double p = nl_div(pp, 8.0 * a4_pow_2);
+  double q = nl_div(rr, 8.0 * a4_pow_3);
+  double r = nl_div(dd + 16.0 * a4_pow_2 * (12.0 * a0 * a4 - 3.0 * a1 * a3 + a2 * a2), 256.0 * a4_pow_4);
   Roots4 dep; dep.n = 0;
   d_quartic_depressed(p, q, r, dep);
-  for (int i = 0; i < dep.n; i++) out.add(dep.v[i] - a3 / (4.0 * a4));
+  const double shift = nl_div(a3, 4.0 * a4);
+  for (int i = 0; i < dep.n; i++) out.add(dep.v[i] - shift);
 }
 
 // ------------------------------------------------------------------ primitives
@@ -265,7 +276,7 @@ static __device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray&
     double px = (double)d.x + (double)e.x * closest;
     double py = (double)d.y + (double)e.y * closest;
     double pz = (double)d.z + (double)e.z * closest;
-    double alpha = 1.0 - a / sqrt(px * px + pz * pz);
+    double alpha = 1.0 - nl_div(a, nl_sqrt(px * px + pz * pz));
     F3 n = normalize(f3((float)(alpha * px), (float)py, (float)(alpha * pz)));
     *n_out = (np % 2 == 1) ? -n : n;   // odd number of positive roots: inside (torus.rs:120-124)
     if (entering_out) *entering_out = (np % 2 == 0);
@@ -311,7 +322,7 @@ WPT_DEV bool square_t(float4 q0, float4 q1, const Ray& ray, float* t_out, float*
 // Tracable::trace_simple for shape record `s`. `limit`/`strict` implement the acceptance test
 // of trace_shapes_md (scene.rs:450-472): the first candidate needs t <= max_dis, later ones
 // 0 < t < best. Rejecting on t before the edge tests does not change any result.
-template <bool SIMPLE>
+template <int KIND>
 WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float limit, bool strict, float* t_out) {
   const float4* p = reinterpret_cast<const float4*>(shapes + idx);
   float4 q0 = __ldg(p), q1 = __ldg(p + 1);
@@ -336,7 +347,7 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
     return true;
   }
   float t;
-  if (SIMPLE || type == SH_PLANE) {      // plane.rs:80-99 (SIMPLE scenes hold triangles and planes only)
+  if (KIND == K_SIMPLE || type == SH_PLANE) {      // plane.rs:80-99 (K_SIMPLE scenes hold triangles and planes only)
     F3 nr = xyz(q1);
     float n_dot_dir = dot(nr, ray.d);
     if (n_dot_dir == 0.0f) return false;
@@ -352,10 +363,10 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
     if (tmin > 0.0f) t = tmin;
     else if (tmax > 0.0f) t = tmax;
     else return false;
-  } else if (type == SH_SPHERE) {
+  } else if (KIND == K_EXT && type == SH_SPHERE) {
     bool ent;
     if (!sphere_t(q0, q1, ray, &t, &ent)) return false;
-  } else if (type == SH_SQUARE) {   // ray.rs:110-116 default = trace().distance
+  } else if (KIND == K_EXT && type == SH_SQUARE) {   // ray.rs:110-116 default = trace().distance
     float u, v;
     if (!square_t(q0, q1, ray, &t, &u, &v)) return false;
   } else {                     // torus: ray.rs:110-116 default = trace().distance
@@ -368,7 +379,7 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
 
 // Tracable::trace for the winning shape (scene.rs:140): distance, Hit::new-normalised normal,
 // material index. Returns false if the full intersection reports no hit.
-template <bool SIMPLE>
+template <int KIND>
 WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float* t_out, F3* n_out, uint32_t* mat_out, bool* entering_out = nullptr, float2* uv_out = nullptr) {
   const float4* p = reinterpret_cast<const float4*>(shapes + idx);
   float4 q0 = __ldg(p), q1 = __ldg(p + 1);
@@ -393,7 +404,7 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
     if (!(dot(nn, cross(v0 - v2, pt - v2)) + slack >= 0.0f)) return false;
     n = (n_dot_d > 0.0f) ? -nn : nn;
     entering = !(n_dot_d > 0.0f);
-  } else if (SIMPLE || type == SH_PLANE) {   // plane.rs:45-77
+  } else if (KIND == K_SIMPLE || type == SH_PLANE) {   // plane.rs:45-77
     F3 nr = xyz(q1);
     float n_dot_dir = dot(nr, ray.d);
     if (n_dot_dir == 0.0f) return false;
@@ -418,13 +429,13 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
       else if (tmax == ty1) n = f3(0, 1, 0); else if (tmax == ty2) n = f3(0, -1, 0);
       else if (tmax == tz1) n = f3(0, 0, 1); else n = f3(0, 0, -1);
     } else return false;
-  } else if (type == SH_SPHERE) {   // sphere.rs:49-101
+  } else if (KIND == K_EXT && type == SH_SPHERE) {   // sphere.rs:49-101
     bool ent;
     if (!sphere_t(q0, q1, ray, &t, &ent)) return false;
     n = ((ray.o + t * ray.d) - xyz(q0)) / q1.x;
     if (!ent) n = -n;
     entering = ent;
-  } else if (type == SH_SQUARE) {   // square.rs:56-99
+  } else if (KIND == K_EXT && type == SH_SQUARE) {   // square.rs:56-99
     float u, v;
     if (!square_t(q0, q1, ray, &t, &u, &v)) return false;
     n = ray.d.y > 0.0f ? f3(0, -1, 0) : f3(0, 1, 0);
@@ -465,13 +476,43 @@ struct GHit { float t; int id; uint32_t visits; uint32_t prims; };
 
 // trace_shapes_md over a leaf (scene.rs:450-472); updates (best_t, best_id) if the leaf
 // reports a hit — a later leaf wins exact ties because the test is t <= max_dis.
-template <bool SIMPLE>
+// Tori (KIND != K_SIMPLE): the hit distance of a torus does not depend on what the scan has accepted so far, only the
+// acceptance test does. So the leaf's tori are intersected first — all lanes of the warp's leaf step that hold a torus run
+// the f64 solver together, once per torus slot, instead of one by one at whatever position the torus has in each lane's
+// leaf — and the ordered scan below takes their distances from a small cache: same tests, same order, same results.
+#define WPT_LEAF_TORI 12
+template <int KIND>
 WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const Ray& ray, float& bound, int& best_id, uint32_t& prims) {
   prims += count;
   bool have = false; float bt = 0.0f; uint32_t bi = 0;
-  for (uint32_t i = 0; i < count; i++) {
-    float t;
-    if (shape_trace_simple<SIMPLE>(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) { have = true; bt = t; bi = first + i; }
+  if (KIND != K_SIMPLE && count <= 32u) {
+    uint32_t tor = 0u, hit = 0u;   // bit i: shape first + i is a torus / its solver found a root
+    for (uint32_t i = 0; i < count; i++)
+      if ((__float_as_uint(__ldg(&reinterpret_cast<const float4*>(sc.shapes + first + i)->w)) & 0xFFu) == SH_TORUS) tor |= 1u << i;
+    float tt[WPT_LEAF_TORI];
+    uint32_t cached = 0u, k = 0;
+    for (uint32_t m = tor; m && k < WPT_LEAF_TORI; m &= m - 1u, k++) {
+      const uint32_t i = (uint32_t)__ffs((int)m) - 1u;
+      const float4* p = reinterpret_cast<const float4*>(sc.shapes + first + i);
+      float t = 0.0f;
+      if (torus_trace(__ldg(p), __ldg(p + 1), ray, &t, nullptr)) hit |= 1u << i;
+      tt[k] = t; cached |= 1u << i;
+    }
+    k = 0;
+    for (uint32_t i = 0; i < count; i++) {
+      float t;
+      if (cached >> i & 1u) {   // Tracable::trace_simple of a torus = trace().distance (ray.rs:110-116) + the acceptance test of shape_trace_simple
+        t = tt[k++];
+        const float limit = have ? bt : bound;
+        if (!(hit >> i & 1u) || (have ? !(0.0f < t && t < limit) : !(t <= limit))) continue;
+      } else if (!shape_trace_simple<KIND>(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) continue;
+      have = true; bt = t; bi = first + i;
+    }
+  } else {
+    for (uint32_t i = 0; i < count; i++) {
+      float t;
+      if (shape_trace_simple<KIND>(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) { have = true; bt = t; bi = first + i; }
+    }
   }
   if (have) { bound = bt; best_id = (int)bi; }
 }
@@ -524,12 +565,12 @@ WPT_DEV void sort_small(int* id, float* d, uint32_t n) {
 
 // trace_shapes over the infinite shapes + the root guard. Returns true if the BVH has to be
 // traversed (then call trav_step until it returns false).
-template <int BVH, bool SIMPLE>
+template <int BVH, int KIND>
 WPT_DEV bool trav_begin(const DScene& sc, const Ray& ray, Trav& tv) {
   bool have = false; float it = 0.0f; int iid = -1;
   for (uint32_t i = 0; i < sc.num_inf; i++) {   // scene.rs:426-445: first hit accepted as is
     float t;
-    if (shape_trace_simple<SIMPLE>(sc.shapes, i, ray, have ? it : WPT_INF, have, &t)) { have = true; it = t; iid = (int)i; }
+    if (shape_trace_simple<KIND>(sc.shapes, i, ray, have ? it : WPT_INF, have, &t)) { have = true; it = t; iid = (int)i; }
   }
   tv.inf_t = it; tv.inf_id = iid;
   tv.bound = have ? it : WPT_INF;
@@ -620,11 +661,11 @@ WPT_DEV bool trav_inner(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* st
   return !(hl || hr);
 }
 // Scan the leaf the lane waits at (the lane pops afterwards).
-template <int BVH, bool SIMPLE>
+template <int BVH, int KIND>
 WPT_DEV void trav_leaf(const DScene& sc, const Ray& ray, Trav& tv) {
   tv.visits += 1;
-  if (BVH == 4) { uint32_t code = tv.lf; leaf_scan<SIMPLE>(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims); }
-  else leaf_scan<SIMPLE>(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
+  if (BVH == 4) { uint32_t code = tv.lf; leaf_scan<KIND>(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims); }
+  else leaf_scan<KIND>(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
 }
 // true if the node the lane is about to enter is a leaf
 template <int BVH>
@@ -640,14 +681,14 @@ WPT_DEV GHit trav_result(const Trav& tv) {
   return g;
 }
 
-template <int BVH, bool SIMPLE>
+template <int BVH, int KIND>
 WPT_DEV GHit trace_g_t(const DScene& sc, const Ray& ray) {
   Trav tv;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
-  if (trav_begin<BVH, SIMPLE>(sc, ray, tv)) {
+  if (trav_begin<BVH, KIND>(sc, ray, tv)) {
     for (;;) {
       bool need_pop = true;
-      if (trav_at_leaf<BVH>(tv)) trav_leaf<BVH, SIMPLE>(sc, ray, tv);
+      if (trav_at_leaf<BVH>(tv)) trav_leaf<BVH, KIND>(sc, ray, tv);
       else need_pop = trav_inner<BVH>(sc, ray, tv, stack_n, stack_d);
       if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) break;
     }
@@ -656,7 +697,7 @@ WPT_DEV GHit trace_g_t(const DScene& sc, const Ray& ray) {
 }
 // generic version (any scene, either BVH): probes, photon emission, the wavefront engine
 static __device__ __noinline__ GHit trace_g(const DScene& sc, const Ray& ray) {
-  return sc.bvh_kind == 4 ? trace_g_t<4, false>(sc, ray) : trace_g_t<2, false>(sc, ray);
+  return sc.bvh_kind == 4 ? trace_g_t<4, K_EXT>(sc, ray) : trace_g_t<2, K_EXT>(sc, ray);
 }
 
 }  // namespace wpt

@@ -178,15 +178,15 @@ struct ShadeOut {
 // RT: the render type when it is known at compile time (0 NoNEE, 1 NormalNEE, 2 PNEE: k_mega is instantiated per type — no
 // photon code in the NEE kernels, photon_sample inlined in the PNEE kernel: 9 % / 15 % faster than one kernel that branches
 // and calls), 3 = decided at run time (k_shade, k_pool: out-of-line photon_sample)
-template <bool SIMPLE, int RT = 3>
+template <int KIND, int RT = 3>
 WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_hit, PathRegs& ps, ShadeOut& out) {
   const bool has_nee = RT == 3 ? rp.render_type != 0 : RT != 0;
   out.finished = false; out.survive = false; out.shadow = false;
   bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
   bool entering = true; float2 uv = make_float2(0.0f, 0.0f);
   if (id >= 0) {   // scene.rs:140
-    if (SIMPLE) { shape_hit_normal_tri_plane(rp.scene.shapes, (uint32_t)id, ray, &n, &mat); t = t_hit; some = true; }
-    else some = shape_trace_full<false>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat, &entering, &uv);
+    if (KIND == K_SIMPLE) { shape_hit_normal_tri_plane(rp.scene.shapes, (uint32_t)id, ray, &n, &mat); t = t_hit; some = true; }
+    else some = shape_trace_full<KIND>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat, &entering, &uv);
   }
   if (!some) {   // tracer.rs:325-328
     ps.color = ps.color + ps.T * f3(rp.scene.bg_r, rp.scene.bg_g, rp.scene.bg_b);
@@ -200,7 +200,7 @@ WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_h
     out.finished = true;
     return;
   }
-  if (!SIMPLE && mc.w != (float)MAT_DIFFUSE) {   // ---- extension materials (parity unpinned)
+  if (KIND == K_EXT && mc.w != (float)MAT_DIFFUSE) {   // ---- extension materials (parity unpinned)
     float4 mp = __ldg(&rp.scene.mats[mat].p);
     if (mc.w == (float)MAT_DIFFUSE_TEX) {   // Texture::at, texture.rs:23-31 (`as u32` saturates)
       const DTexture tx = rp.scene.tex[__float_as_uint(mp.y)];

@@ -256,8 +256,8 @@ void Context::render_take(Strategy& s, uint32_t render_type, bool bounded) {
   ensure_slots(s.rx, s.ry, s.rw, s.rh);
   launch_gather_slot_spp(s.take.p, s_pixel.p, slots, W, s.rx, s.ry, s.rw, s_spp.p, stream);
   launches += 1;
-  if (cfg.engine != 1 && bounded) { run_persistent(render_type, s_spp.p, 0); return; }
-  const uint32_t per_pass = cfg.engine == 1 ? WPT_SEGMENT_LEN : 64u;
+  if (!use_wavefront() && bounded) { run_persistent(render_type, s_spp.p, 0); return; }
+  const uint32_t per_pass = use_wavefront() ? WPT_SEGMENT_LEN : 64u;
   d_pass_spp.alloc(slots);
   for (uint32_t pass = 0;; pass++) {
     uint32_t any = 0;
@@ -267,7 +267,7 @@ void Context::render_take(Strategy& s, uint32_t render_type, bool bounded) {
     WPT_CUDA(cudaStreamSynchronize(stream));
     launches += 1;
     if (!any) break;
-    if (cfg.engine == 1) run_wavefront(render_type, d_pass_spp.p, 0);
+    if (use_wavefront()) run_wavefront(render_type, d_pass_spp.p, 0);
     else run_persistent(render_type, d_pass_spp.p, 0);
   }
 }

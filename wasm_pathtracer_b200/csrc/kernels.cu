@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(RenderParams rp, PathSt
         Ray ray = make_ray(xyz(ro), xyz(rd));
         PathRegs ps; ps.color = color; ps.T = T; ps.rng = rng; ps.bounced = (flags & SL_BOUNCED) != 0;
         ShadeOut so;
-        shade_hit<false>(rp, ray, __float_as_int(h.y), h.x, ps, so);
+        shade_hit<K_EXT>(rp, ray, __float_as_int(h.y), h.x, ps, so);
         color = ps.color; T = ps.T; rng = ps.rng;
         if (so.finished) finished = true;
         else {
@@ -299,7 +299,7 @@ WPT_DEV bool trav_begin_const(const MegaParams& P, const Ray& ray, Trav& tv) {
   return true;
 }
 
-template <int BVH, bool SIMPLE, int MINB, int RT>
+template <int BVH, int KIND, int MINB, int RT>
 __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
             if (np && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
           }
         } else {
-          if (leaf) { trav_leaf<BVH, SIMPLE>(sc, ray, tv); need_pop = true; }
+          if (leaf) { trav_leaf<BVH, KIND>(sc, ray, tv); need_pop = true; }
           if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
         }
         trav = __ballot_sync(FULL, phase == PH_TRAV);
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           else finish = true;
         } else {
           ShadeOut so;
-          shade_hit<SIMPLE, RT>(P.rp, ray, g.id, g.t, ps, so);
+          shade_hit<KIND, RT>(P.rp, ray, g.id, g.t, ps, so);
           if (so.finished) finish = true;
           else if (so.shadow) {
             ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           phase = PH_NEED;
         }
       }
-      if (start && (SIMPLE ? trav_begin_const<BVH>(P, ray, tv) : trav_begin<BVH, SIMPLE>(sc, ray, tv))) phase = PH_TRAV;
+      if (start && trav_begin_const<BVH>(P, ray, tv)) phase = PH_TRAV;
     }
   }
   // ---- counters
@@ -481,42 +481,51 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 #endif
 }
 // Register budgets (blocks of 128 threads per SM) instantiated per variant: the measured optimum (gpurun_out/sweep8.log,
-// sweep11.log, sweep12.log) — triangles/planes BVH2 8 (64 registers), BVH4 5 and 8, generic 16 (32 registers) — or, with -DWPT_TUNING,
-// 4 / 5 / 8 / 12 / 16 for every variant (WPT_MEGA_MINB* then selects).
-template <int BVH, bool SIMPLE, int RT>
+// sweep11.log, sweep12.log) — triangles/planes BVH2 8 (64 registers), BVH4 5 and 8, ext 16 (32 registers); the reference-primitives
+// variant (tori, boxes) has 8 / 12 / 16 selectable at run time (WPT_MEGA_MINBG). With -DWPT_TUNING: 4 / 5 / 8 / 12 / 16 for every variant.
+template <int BVH, int KIND, int RT>
 static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   auto grid_for = [&](int b) { int grid = device_sm_count() * b, need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS); return (grid > need && !P.nslots_dev) ? need : grid; };
 #ifdef WPT_TUNING
   int b = blocks_per_sm >= 16 ? 16 : blocks_per_sm >= 12 ? 12 : blocks_per_sm >= 8 ? 8 : blocks_per_sm >= 5 ? 5 : 4;
   switch (b) {
-    case 5: k_mega<BVH, SIMPLE, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P); break;
-    case 8: k_mega<BVH, SIMPLE, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P); break;
-    case 12: k_mega<BVH, SIMPLE, 12, RT><<<grid_for(12), MEGA_THREADS, 0, s>>>(P); break;
-    case 16: k_mega<BVH, SIMPLE, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P); break;
-    default: k_mega<BVH, SIMPLE, 4, RT><<<grid_for(4), MEGA_THREADS, 0, s>>>(P); break;
+    case 5: k_mega<BVH, KIND, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P); break;
+    case 8: k_mega<BVH, KIND, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P); break;
+    case 12: k_mega<BVH, KIND, 12, RT><<<grid_for(12), MEGA_THREADS, 0, s>>>(P); break;
+    case 16: k_mega<BVH, KIND, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P); break;
+    default: k_mega<BVH, KIND, 4, RT><<<grid_for(4), MEGA_THREADS, 0, s>>>(P); break;
   }
 #else
-  (void)blocks_per_sm;
-  if constexpr (!SIMPLE) k_mega<BVH, SIMPLE, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
-  else if constexpr (BVH == 2 || RT == 2) k_mega<BVH, SIMPLE, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
-  else k_mega<BVH, SIMPLE, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P);
+  if constexpr (KIND == K_EXT) k_mega<BVH, KIND, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
+  else if constexpr (KIND == K_REF) {
+    if (BVH == 4 || blocks_per_sm >= 16) k_mega<BVH, KIND, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
+    else if constexpr (BVH == 2) {
+      if (blocks_per_sm >= 12) k_mega<BVH, KIND, 12, RT><<<grid_for(12), MEGA_THREADS, 0, s>>>(P);
+      else k_mega<BVH, KIND, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
+    }
+  }
+  else if constexpr (BVH == 2 || RT == 2) k_mega<BVH, KIND, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
+  else k_mega<BVH, KIND, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P);
 #endif
 }
-template <int BVH, bool SIMPLE>
+template <int BVH, int KIND>
 static void launch_mega_rt(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   switch (P.rp.render_type) {
-    case 0: launch_mega_t<BVH, SIMPLE, 0>(P, blocks_per_sm, s); break;
-    case 2: launch_mega_t<BVH, SIMPLE, 2>(P, blocks_per_sm, s); break;
-    default: launch_mega_t<BVH, SIMPLE, 1>(P, blocks_per_sm, s); break;
+    case 0: launch_mega_t<BVH, KIND, 0>(P, blocks_per_sm, s); break;
+    case 2: launch_mega_t<BVH, KIND, 2>(P, blocks_per_sm, s); break;
+    default: launch_mega_t<BVH, KIND, 1>(P, blocks_per_sm, s); break;
   }
 }
-// blocks_per_sm[variant]: 0 = triangles/planes BVH2, 1 = triangles/planes BVH4, 2 = generic BVH2, 3 = generic BVH4
+// blocks_per_sm[variant]: 0 = triangles/planes BVH2, 1 = triangles/planes BVH4, 2 = tori/boxes/ext BVH2, 3 = tori/boxes/ext BVH4
 void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s) {
   if (!P.nslots) return;
   const bool b4 = P.rp.scene.bvh_kind == 4;
-  const int v = (P.simple_scene ? 0 : 2) + (b4 ? 1 : 0);
-  if (P.simple_scene) { if (b4) launch_mega_rt<4, true>(P, blocks_per_sm[v], s); else launch_mega_rt<2, true>(P, blocks_per_sm[v], s); }
-  else { if (b4) launch_mega_rt<4, false>(P, blocks_per_sm[v], s); else launch_mega_rt<2, false>(P, blocks_per_sm[v], s); }
+  const int v = (P.scene_kind == K_SIMPLE ? 0 : 2) + (b4 ? 1 : 0);
+  switch (P.scene_kind) {
+    case K_SIMPLE: if (b4) launch_mega_rt<4, K_SIMPLE>(P, blocks_per_sm[v], s); else launch_mega_rt<2, K_SIMPLE>(P, blocks_per_sm[v], s); break;
+    case K_REF: if (b4) launch_mega_rt<4, K_REF>(P, blocks_per_sm[v], s); else launch_mega_rt<2, K_REF>(P, blocks_per_sm[v], s); break;
+    default: if (b4) launch_mega_rt<4, K_EXT>(P, blocks_per_sm[v], s); else launch_mega_rt<2, K_EXT>(P, blocks_per_sm[v], s); break;
+  }
 }
 
 // ------------------------------------------------------------------ segments (contract B10)
@@ -665,7 +674,7 @@ __global__ void __launch_bounds__(128) k_photon_emit(RenderParams rp, unsigned l
   bool stored = false;
   if (g.id >= 0) {
     float t; F3 n; uint32_t mat;
-    if (shape_trace_full<false>(rp.scene.shapes, (uint32_t)g.id, ray, &t, &n, &mat)) {
+    if (shape_trace_full<K_EXT>(rp.scene.shapes, (uint32_t)g.id, ray, &t, &n, &mat)) {
       float4 mc = __ldg(&rp.scene.mats[mat].c);
       if (mc.w == (float)MAT_DIFFUSE || mc.w == (float)MAT_DIFFUSE_TEX) {   // hit.mat.is_diffuse(), tracer.rs:144
         F3 hp = (ray.o + t * ray.d) + n * WPT_EPSILON;
@@ -975,7 +984,7 @@ __global__ void k_trace_batch(RenderParams rp, const float* __restrict__ o, cons
   visits[i] = g.visits;
   if (normals) {
     float t; F3 nn = f3(0, 0, 0); uint32_t mat;
-    bool ok = g.id >= 0 && shape_trace_full<false>(rp.scene.shapes, (uint32_t)g.id, ray, &t, &nn, &mat);
+    bool ok = g.id >= 0 && shape_trace_full<K_EXT>(rp.scene.shapes, (uint32_t)g.id, ray, &t, &nn, &mat);
     normals[i * 3] = ok ? nn.x : 0.0f; normals[i * 3 + 1] = ok ? nn.y : 0.0f; normals[i * 3 + 2] = ok ? nn.z : 0.0f;
   }
 }

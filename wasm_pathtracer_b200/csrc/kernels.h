@@ -64,9 +64,9 @@ struct MegaParams {
   float4* pool;                   // k_wpool: path contexts, [warp][pool_ctx][10 x float4]
   uint32_t pool_ctx;              // k_wpool: contexts per warp (<= 128)
   uint32_t chunk;                 // slots a warp fetches at a time (multiple of 32)
-  uint32_t simple_scene;          // triangles and planes only, at most two infinite shapes: kernel variant without torus / box code
-  float4 inf_q1[2];               // simple_scene: (normal, normal.location) of the infinite planes (shape record q1)
-  float4 root_a, root_b;          // simple_scene: the BVH2 root node (box + left_first, count)
+  uint32_t scene_kind;            // kernel variant by scene content (device_core.cuh): 0 triangles + planes, 1 + tori + boxes (the reference's primitives), 2 + the extension
+  float4 inf_q1[2];               // (normal, normal.location) of the (at most two) infinite planes (shape record q1)
+  float4 root_a, root_b;          // the BVH2 root node (box + left_first, count)
   uint32_t seed_path;             // mix32(STREAM_PATH ^ base_seed): the constant part of a path's stream seed
   uint32_t* work_counter;         // zeroed before the launch
   unsigned long long* counters;

@@ -80,11 +80,11 @@ WPT_DEV void ctx_load(const float4* c, WCur& k) {
 // root guard (BVH2, scene.rs:191-212) or the root node's four child boxes (BVH4 has no root box test, scene.rs:292-342;
 // a ray none of whose children survives ends here with the root's one visit). Returns true if the ray has to be queued:
 // then (res_t, res_id) = (bound, plane-hit id), the job's input; else they are the final result of the ray.
-template <int BVH, bool SIMPLE>
+template <int BVH, int KIND>
 WPT_DEV bool wp_begin(const DScene& sc, F3 o, F3 d, float* res_t, int* res_id) {
   Ray ray = make_ray(o, d);
   Trav tv;
-  bool enter = trav_begin<BVH, SIMPLE>(sc, ray, tv);
+  bool enter = trav_begin<BVH, KIND>(sc, ray, tv);
   if (BVH == 4) {
     const float4* p = reinterpret_cast<const float4*>(sc.nodes4);
     float4 x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2), x1 = __ldg(p + 3), y1 = __ldg(p + 4), z1 = __ldg(p + 5);
@@ -99,7 +99,7 @@ WPT_DEV bool wp_begin(const DScene& sc, F3 o, F3 d, float* res_t, int* res_id) {
   return enter;
 }
 
-template <int BVH, bool SIMPLE, int MINB, int RT>
+template <int BVH, int KIND, int MINB, int RT>
 __global__ void __launch_bounds__(WP_THREADS, MINB) k_wpool(MegaParams P) {
   const DScene& sc = P.rp.scene;
   const unsigned FULL = 0xFFFFFFFFu;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(WP_THREADS, MINB) k_wpool(MegaParams P) {
           k.ps.color = f3(0, 0, 0); k.ps.T = f3(1.0f, 1.0f, 1.0f); k.ps.bounced = false;
           k.what = WS_EXTEND; start = true;
         }
-        if (start) park = wp_begin<BVH, SIMPLE>(sc, k.o, k.d, &k.res_t, &k.res_id);
+        if (start) park = wp_begin<BVH, KIND>(sc, k.o, k.d, &k.res_t, &k.res_id);
         {
           const unsigned ms = __ballot_sync(FULL, start), mp = __ballot_sync(FULL, start && park);
           n_rays += (uint32_t)__popc(ms); n_guard += (uint32_t)__popc(BVH == 4 ? (ms & ~mp) : ms);
@@ -224,9 +224,9 @@ __global__ void __launch_bounds__(WP_THREADS, MINB) k_wpool(MegaParams P) {
 #endif
         if (have && !park && k.what == WS_EXTEND) {
           Ray ray; ray.o = k.o; ray.d = k.d;
-          ray.inv = SIMPLE ? f3(0.0f, 0.0f, 0.0f) : f3(1.0f / k.d.x, 1.0f / k.d.y, 1.0f / k.d.z);
+          ray.inv = KIND == K_SIMPLE ? f3(0.0f, 0.0f, 0.0f) : f3(1.0f / k.d.x, 1.0f / k.d.y, 1.0f / k.d.z);
           ShadeOut so;
-          shade_hit<SIMPLE, RT>(P.rp, ray, k.res_id, k.res_t, k.ps, so);
+          shade_hit<KIND, RT>(P.rp, ray, k.res_id, k.res_t, k.ps, so);
           if (so.finished) finish = true;
           else if (so.shadow) {
             k.ext_o = so.next_o; k.ext_d = so.next_d; k.contrib = so.contrib; k.sh_len = so.sh_len; k.sh_light = so.sh_light;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(WP_THREADS, MINB) k_wpool(MegaParams P) {
           if (finish) { k.acc = k.acc + k.ps.color; k.s += 1; k.what = WS_GEN; }   // RenderTarget::write, render_target.rs:55-58
         }
         bool park_b = false;
-        if (start) park_b = wp_begin<BVH, SIMPLE>(sc, k.o, k.d, &k.res_t, &k.res_id);
+        if (start) park_b = wp_begin<BVH, KIND>(sc, k.o, k.d, &k.res_t, &k.res_id);
         {
           const unsigned ms = __ballot_sync(FULL, start), mp = __ballot_sync(FULL, start && park_b);
           n_rays += (uint32_t)__popc(ms); n_guard += (uint32_t)__popc(BVH == 4 ? (ms & ~mp) : ms);
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(WP_THREADS, MINB) k_wpool(MegaParams P) {
             if (np && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) fin = true;
           }
         } else if (leaf) {
-          trav_leaf<BVH, SIMPLE>(sc, ray, tv);
+          trav_leaf<BVH, KIND>(sc, ray, tv);
           if (!trav_pop<BVH>(sc, tv, stack_n, stack_d)) fin = true;
         }
       }
@@ -369,18 +369,18 @@ __global__ void __launch_bounds__(WP_THREADS, MINB) k_wpool(MegaParams P) {
   if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
-template <int BVH, bool SIMPLE, int RT>
+template <int BVH, int KIND, int RT>
 static void launch_wpool_t(const MegaParams& P, int grid, int minb, cudaStream_t s) {
-  if (minb >= 12) k_wpool<BVH, SIMPLE, 12, RT><<<grid, WP_THREADS, 0, s>>>(P);
-  else if (minb >= 8) k_wpool<BVH, SIMPLE, 8, RT><<<grid, WP_THREADS, 0, s>>>(P);
-  else k_wpool<BVH, SIMPLE, 6, RT><<<grid, WP_THREADS, 0, s>>>(P);
+  if (minb >= 12) k_wpool<BVH, KIND, 12, RT><<<grid, WP_THREADS, 0, s>>>(P);
+  else if (minb >= 8) k_wpool<BVH, KIND, 8, RT><<<grid, WP_THREADS, 0, s>>>(P);
+  else k_wpool<BVH, KIND, 6, RT><<<grid, WP_THREADS, 0, s>>>(P);
 }
-template <int BVH, bool SIMPLE>
+template <int BVH, int KIND>
 static void launch_wpool_rt(const MegaParams& P, int grid, int minb, cudaStream_t s) {
   switch (P.rp.render_type) {
-    case 0: launch_wpool_t<BVH, SIMPLE, 0>(P, grid, minb, s); break;
-    case 2: launch_wpool_t<BVH, SIMPLE, 2>(P, grid, minb, s); break;
-    default: launch_wpool_t<BVH, SIMPLE, 1>(P, grid, minb, s); break;
+    case 0: launch_wpool_t<BVH, KIND, 0>(P, grid, minb, s); break;
+    case 2: launch_wpool_t<BVH, KIND, 2>(P, grid, minb, s); break;
+    default: launch_wpool_t<BVH, KIND, 1>(P, grid, minb, s); break;
   }
 }
 uint32_t wpool_warps(int grid) { return (uint32_t)grid * WP_WARPS; }
@@ -388,8 +388,8 @@ size_t wpool_ctx_bytes() { return WP_CTX_F4 * sizeof(float4); }
 void launch_wpool(const MegaParams& P, int grid, int minb, cudaStream_t s) {
   if (!P.nslots) return;
   const bool b4 = P.rp.scene.bvh_kind == 4;
-  if (P.simple_scene) { if (b4) launch_wpool_rt<4, true>(P, grid, minb, s); else launch_wpool_rt<2, true>(P, grid, minb, s); }
-  else { if (b4) launch_wpool_rt<4, false>(P, grid, minb, s); else launch_wpool_rt<2, false>(P, grid, minb, s); }
+  if (P.scene_kind == K_SIMPLE) { if (b4) launch_wpool_rt<4, K_SIMPLE>(P, grid, minb, s); else launch_wpool_rt<2, K_SIMPLE>(P, grid, minb, s); }
+  else { if (b4) launch_wpool_rt<4, K_EXT>(P, grid, minb, s); else launch_wpool_rt<2, K_EXT>(P, grid, minb, s); }
 }
 
 }  // namespace wpt

@@ -78,6 +78,13 @@ extern "C" {
     /// Multi-GPU: called between adaptive rounds to exchange the accumulator rows (NCCL all-gather in the caller).
     pub fn wpt_ctx_set_exchange_callback(ctx: *mut wpt_ctx, callback: Option<unsafe extern "C" fn(user: *mut c_void)>, user: *mut c_void) -> c_int;
     /// Multi-GPU photon warm-up: in-place integer sum of `n_words` u32 at `dev_words` over all ranks (ncclAllReduce, ncclUint32, ncclSum).
+    // native multi-GPU plane (NCCL inside libwpt, csrc/dist_nccl.cpp)
+    pub fn wpt_nccl_unique_id(out: *mut u8) -> c_int;
+    pub fn wpt_ctx_attach_nccl(ctx: *mut wpt_ctx, id: *const u8, rank: u32, world: u32) -> c_int;
+    pub fn wpt_ctx_attach_nccl_comm(ctx: *mut wpt_ctx, nccl_comm: *mut c_void, rank: u32, world: u32) -> c_int;
+    pub fn wpt_ctx_detach_nccl(ctx: *mut wpt_ctx) -> c_int;
+    pub fn wpt_ctx_gather_frame(ctx: *mut wpt_ctx) -> c_int;
+    pub fn wpt_ctx_profile_read_rounds(ctx: *mut wpt_ctx, out: *mut f64) -> c_int;
     pub fn wpt_ctx_set_reduce_callback(ctx: *mut wpt_ctx, callback: Option<unsafe extern "C" fn(user: *mut c_void, dev_words: *mut c_void, n_words: u64)>, user: *mut c_void) -> c_int;
     pub fn wpt_ctx_device_buffers(ctx: *mut wpt_ctx, ptrs: *mut u64, sizes: *mut u64) -> c_int;
     pub fn wpt_ctx_mark_accum_dirty(ctx: *mut wpt_ctx) -> c_int;

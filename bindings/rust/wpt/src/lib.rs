@@ -72,12 +72,28 @@ impl PathTracer {
         let n = unsafe { sys::wpt_ctx_render_adaptive(self.ctx, budget_ticks) };
         if n < 0 { Err(last_error()) } else { Ok(n as u64) }
     }
+    pub fn build_photons(&mut self) -> Result<()> { check(unsafe { sys::wpt_ctx_build_photons(self.ctx) }) }
+    /// Native multi-GPU plane: join the job described by rank 0's `nccl_unique_id()` (the host distributes the 128 bytes).
+    /// Sets rank / world (4-row bands, band b belongs to rank b % world); the library then all-gathers the accumulator rows
+    /// between adaptive rounds and on `gather_frame`, and merges the photon batches with an integer allreduce.
+    pub fn attach_nccl(&mut self, id: &[u8; 128], rank: u32, world: u32) -> Result<()> {
+        check(unsafe { sys::wpt_ctx_attach_nccl(self.ctx, id.as_ptr(), rank, world) })
+    }
+    pub fn detach_nccl(&mut self) -> Result<()> { check(unsafe { sys::wpt_ctx_detach_nccl(self.ctx) }) }
+    pub fn gather_frame(&mut self) -> Result<()> { check(unsafe { sys::wpt_ctx_gather_frame(self.ctx) }) }
     /// rays, paths, BVH node visits (the reference's `num_bvh_hits`), photons shot, photons stored, iterations, launches
     pub fn stats(&mut self) -> Result<[u64; 8]> {
         let mut out = [0u64; 8];
         check(unsafe { sys::wpt_ctx_stats(self.ctx, out.as_mut_ptr()) })?;
         Ok(out)
     }
+}
+
+/// `ncclGetUniqueId` through the library (rank 0 calls it; every rank passes the bytes to `PathTracer::attach_nccl`).
+pub fn nccl_unique_id() -> Result<[u8; 128]> {
+    let mut id = [0u8; 128];
+    check(unsafe { sys::wpt_nccl_unique_id(id.as_mut_ptr()) })?;
+    Ok(id)
 }
 
 impl Drop for PathTracer {

@@ -278,6 +278,7 @@ int wpt_ctx_photon_list(wpt_ctx* ctx, uint32_t* light, float* loc3, float* weigh
   return guard([&] {
     Context* c = C(ctx);
     if (!c->photons_ready) throw std::runtime_error("photon tree not built");
+    c->photon_list_host();
     if (light) std::copy(c->ph_light.begin(), c->ph_light.end(), light);
     if (loc3) std::copy(c->ph_loc.begin(), c->ph_loc.end(), loc3);
     if (weight) std::copy(c->ph_w.begin(), c->ph_w.end(), weight);
@@ -288,6 +289,7 @@ int64_t wpt_ctx_photon_tree(wpt_ctx* ctx, uint32_t* meta, float* cum, float* bin
   guard([&] {
     Context* c = C(ctx);
     if (!c->photons_ready) throw std::runtime_error("photon tree not built");
+    c->photon_tree_host();
     if (meta) std::copy(c->pt_meta.begin(), c->pt_meta.end(), meta);
     if (cum) std::copy(c->pt_cum.begin(), c->pt_cum.end(), cum);
     if (bins) std::copy(c->pt_bins.begin(), c->pt_bins.end(), bins);

@@ -36,10 +36,20 @@ Context::Context(int dev, uint32_t w, uint32_t h, uint32_t sid, const float cam5
   wpt_default_config(&cfg);
   WPT_CUDA(cudaMallocHost((void**)&h_ring, 64 * sizeof(uint32_t)));
   WPT_CUDA(cudaMallocHost((void**)&h_counters, 16 * sizeof(unsigned long long)));
-  w_shadow_n.alloc(2); w_ring.alloc(64); w_counters.alloc(16); w_work.alloc(4);
-  WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 16 * sizeof(unsigned long long), stream));
-  alloc_targets();
-  select_scene(sid);
+  try {
+    w_shadow_n.alloc(2); w_ring.alloc(64); w_counters.alloc(16); w_work.alloc(4);
+    WPT_CUDA(cudaMemsetAsync(w_counters.p, 0, 16 * sizeof(unsigned long long), stream));
+    alloc_targets();
+    select_scene(sid);
+  } catch (...) {   // the destructor does not run for a half-built object: release the stream and the pinned buffers here
+    if (own_stream) { cudaStreamSynchronize(own_stream); cudaStreamDestroy(own_stream); }
+    if (h_scene_blob) cudaFreeHost(h_scene_blob);
+    if (h_rgba) cudaFreeHost(h_rgba);
+    if (h_sampling) cudaFreeHost(h_sampling);
+    if (h_ring) cudaFreeHost(h_ring);
+    if (h_counters) cudaFreeHost(h_counters);
+    throw;
+  }
 }
 
 Context::~Context() {
@@ -107,9 +117,22 @@ void Context::select_scene(uint32_t id) {
   build_scene(ns, std::move(shapes), std::move(mats), cfg.bvh_kind);
   ns.bg[0] = bg[0]; ns.bg[1] = bg[1]; ns.bg[2] = bg[2];
   if (ns.depth2 + 2 > 64 || ns.depth4 * 3 + 4 > 64) throw std::runtime_error("BVH too deep for the device traversal stack");
+  for (const HostMaterial& m : ns.mats)   // validate before anything is replaced (the upload re-allocates the device buffers)
+    if (m.kind == MAT_DIFFUSE_TEX) {
+      auto dm = tex_dims.find(m.tex);
+      if (m.tex >= WPT_MAX_TEXTURES || textures.find(m.tex) == textures.end() || dm == tex_dims.end() || !dm->second.first || !dm->second.second)
+        throw std::runtime_error("textured material without a loaded texture");
+    }
+  // the session keeps its old scene unless the new one is completely uploaded
+  HostScene old = std::move(scene);
   scene = std::move(ns);
+  try { upload_scene(); }
+  catch (...) {
+    scene = std::move(old);
+    try { if (!scene.shapes.empty()) upload_scene(); } catch (...) {}
+    throw;
+  }
   scene_id = id;
-  upload_scene();
   photons_ready = false; photon_shots = photon_count = 0;
 }
 
@@ -238,12 +261,17 @@ void Context::ensure_slots(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh) {
   if (slots && !std::memcmp(key, slot_region, sizeof key)) return;
   uint32_t rows = band_rows(rh, rank, world);
   uint32_t n = rows * rw;
-  s_ray_o.alloc(n); s_ray_d.alloc(n); s_col.alloc(n); s_sh_o.alloc(n); s_sh_d.alloc(n); s_sh_c.alloc(n); s_tail.alloc(n);
-  s_misc.alloc(n); s_hit.alloc(n); s_pixel.alloc(n); s_spp.alloc(n);
-  w_shadow_q0.alloc(n); w_shadow_q1.alloc(n);
+  s_pixel.alloc(n); s_spp.alloc(n);
+  if (use_wavefront()) ensure_wavefront_state(n);   // ~140 B per slot that the persistent kernels never touch
   launch_fill_pixels(s_pixel.p, W, rx, ry, rw, rh, rank, world, stream);
   slots = n;
   std::memcpy(slot_region, key, sizeof key);
+}
+
+void Context::ensure_wavefront_state(uint32_t n) {
+  s_ray_o.alloc(n); s_ray_d.alloc(n); s_col.alloc(n); s_sh_o.alloc(n); s_sh_d.alloc(n); s_sh_c.alloc(n); s_tail.alloc(n);
+  s_misc.alloc(n); s_hit.alloc(n);
+  w_shadow_q0.alloc(n); w_shadow_q1.alloc(n);
 }
 
 PathState Context::path_state() {
@@ -265,6 +293,7 @@ void Context::run_wavefront(uint32_t render_type, const uint32_t* d_spp_per_slot
   require_device();
   if (!slots) return;
   if (render_type == WPT_PNEE && !photons_ready) throw std::runtime_error("photon tree not built");
+  ensure_wavefront_state(slots);   // the engine may have been selected after the slots were laid out
   RenderParams rp = params(render_type);
   PathState st = path_state();
   WaveBuffers wb = wave_buffers();
@@ -320,7 +349,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   P.accum = d_accum.p; P.pixel = s_pixel.p; P.spp_per_slot = d_spp_per_slot; P.uniform_spp = uniform_spp;
   // contract B10: render_exact cuts a pixel's samples into segments of WPT_SEGMENT_LEN, each summed from +0 by its
   // own slot (so one pixel's samples can run on several lanes); a strategy round (per-slot counts) is one segment.
-  static const uint32_t seg_len = std::getenv("WPT_SEGMENT_LEN_EXPERIMENT") ? (uint32_t)std::atoi(std::getenv("WPT_SEGMENT_LEN_EXPERIMENT")) : WPT_SEGMENT_LEN;   // tuning only: changes the bits
+  const uint32_t seg_len = WPT_SEGMENT_LEN;   // 8 segments of 8 samples cover the 64 samples a strategy round may hold per pixel (the list encoding has 3 segment bits)
   P.seg_len = seg_len;
   if (d_spp_per_slot) {
     // strategy round: per-slot counts (0..33 adaptive, anything for random). The segments of all pixels are listed

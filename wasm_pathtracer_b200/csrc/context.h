@@ -97,6 +97,10 @@ struct Context {
   uint64_t photon_shots = 0, photon_count = 0;
   std::vector<uint32_t> ph_light; std::vector<float> ph_loc, ph_w;     // host copies (read-backs)
   std::vector<uint32_t> pt_meta; std::vector<float> pt_cum, pt_bins;   // flattened tree (read-backs)
+  std::vector<uint32_t> oc_child_base_h, oc_count_h, oc_depth_h;       // host copy of the topology
+  bool ph_host_valid = false, tree_host_valid = false;                 // read-back copies are made on first use
+  void photon_list_host();
+  void photon_tree_host();
 
   // pinned host copies of the flattened scene (re-upload without rebuilding)
   void* h_scene_blob = nullptr; size_t h_scene_bytes = 0;
@@ -173,6 +177,7 @@ struct Context {
   void clear_targets();
   void reset();
   void ensure_slots(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh);
+  void ensure_wavefront_state(uint32_t n);
   RenderParams params(uint32_t render_type) const;
   PathState path_state();
   WaveBuffers wave_buffers();

@@ -32,40 +32,28 @@ void Context::build_photons() {
   ph_loc_w.alloc(cap); ph_light_shot.alloc(cap); ph_dense.alloc((size_t)batch * 6);
   uint32_t* d_meta = ph_dense.p; uint32_t* d_light = ph_dense.p + batch; float4* d_lw = reinterpret_cast<float4*>(ph_dense.p + 2 * (size_t)batch);
   RenderParams rp = params(WPT_NORMAL_NEE);
-  std::vector<uint32_t> dense((size_t)batch * 6);
+  // every batch is compacted on the device (stored flags -> exclusive scan -> scatter in shot order, cut at the shot that
+  // stores photon number `target`); the host reads back four counters per batch, never the records
+  d_seg_cnt.alloc((size_t)batch + 1); d_seg_off.alloc((size_t)batch + 1);
+  const size_t sb = seg_scan_bytes(batch);
+  d_scan_tmp.alloc(sb ? sb : 1);
+  a_stats.alloc(4);
   uint64_t shots = 0, stored = 0, visits = 0, own_shots = 0;
   uint32_t guard = 0;
-  ph_light.clear(); ph_loc.clear(); ph_w.clear();
+  ph_host_valid = false; tree_host_valid = false;
   while (stored < target) {
     if (++guard > 100000) throw std::runtime_error("photon warm-up does not converge (no diffuse surface reachable)");
-    const uint32_t before = (uint32_t)stored;
     WPT_CUDA(cudaMemsetAsync(ph_dense.p, 0, (size_t)batch * 6 * sizeof(uint32_t), stream));
+    WPT_CUDA(cudaMemsetAsync(a_stats.p, 0, 4 * sizeof(unsigned long long), stream));
     launch_photon_emit(rp, shots, batch, e_rank, e_world, d_meta, d_light, d_lw, stream);
     launches += 1;
     if (split) reduce_hook(ph_dense.p, (uint64_t)batch * 6);
-    WPT_CUDA(cudaMemcpyAsync(dense.data(), ph_dense.p, dense.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    launch_photon_compact(d_meta, d_light, d_lw, batch, (uint32_t)(target - stored), (uint32_t)stored, e_rank, e_world, d_seg_cnt.p, d_seg_off.p, d_scan_tmp.p, sb,
+                          ph_loc_w.p, ph_light_shot.p, a_stats.p, stream);
+    launches += 3;
+    WPT_CUDA(cudaMemcpyAsync(h_counters + 12, a_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     WPT_CUDA(cudaStreamSynchronize(stream));
-    const uint32_t* meta = dense.data(); const uint32_t* light = dense.data() + batch;
-    const float4* lw = reinterpret_cast<const float4*>(dense.data() + 2 * (size_t)batch);
-    // the photon set ends with the shot that stores photon number `target`: keep shots < cut, in shot order
-    std::vector<float4> lw2; std::vector<uint2> ls2;
-    uint32_t cut = batch;
-    for (uint32_t i = 0; i < batch; i++) {
-      if (i % e_world == e_rank) { visits += meta[i] & 0x7FFFFFFFu; own_shots += 1; }   // this rank's share of the rays
-      if (meta[i] & 0x80000000u) {
-        lw2.push_back(lw[i]); ls2.push_back(make_uint2(light[i], i));
-        if (before + lw2.size() == target) { cut = i + 1; break; }
-      }
-    }
-    if (!lw2.empty()) {
-      WPT_CUDA(cudaMemcpyAsync(ph_loc_w.p + before, lw2.data(), lw2.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
-      WPT_CUDA(cudaMemcpyAsync(ph_light_shot.p + before, ls2.data(), ls2.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream));
-      WPT_CUDA(cudaStreamSynchronize(stream));
-    }
-    stored = before + lw2.size();
-    // host copies for the read-back API
-    for (size_t k = 0; k < lw2.size(); k++) { ph_light.push_back(ls2[k].x); ph_loc.push_back(lw2[k].x); ph_loc.push_back(lw2[k].y); ph_loc.push_back(lw2[k].z); ph_w.push_back(lw2[k].w); }
-    shots += cut;
+    stored += h_counters[12]; shots += h_counters[13]; visits += h_counters[14]; own_shots += h_counters[15];
   }
   photon_shots = shots; photon_count = stored;
   photons_shot_total += shots; photons_stored_total += stored;
@@ -159,7 +147,34 @@ void Context::build_photons() {
     WPT_CUDA(cudaMemcpyAsync(p_nbr.p, nbr.data(), nbr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     WPT_CUDA(cudaStreamSynchronize(stream));
   }
-  // ---- read-back copy in DFS pre-order (children in octant order), like the oracle's flattening
+  oc_child_base_h = child_base; oc_count_h = count; oc_depth_h = depth;   // for the lazy read-back copy (photon_tree_host)
+  photons_ready = true;
+  photon_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  if (std::getenv("WPT_TRACE_PHOTONS")) std::fprintf(stderr, "wpt photon warm-up: %.2f ms (%llu shots, %llu photons, %u octree nodes)\n", photon_build_ms, (unsigned long long)shots, (unsigned long long)stored, nodes);
+}
+
+// Read-back copies for the inspection API (wpt_ctx_photon_list / wpt_ctx_photon_tree), made on first use.
+void Context::photon_list_host() {
+  require_device();
+  if (ph_host_valid) return;
+  const size_t n = (size_t)photon_count;
+  std::vector<float4> lw(n); std::vector<uint2> ls(n);
+  if (n) {
+    WPT_CUDA(cudaMemcpyAsync(lw.data(), ph_loc_w.p, n * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaMemcpyAsync(ls.data(), ph_light_shot.p, n * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+  }
+  ph_light.resize(n); ph_loc.resize(n * 3); ph_w.resize(n);
+  for (size_t k = 0; k < n; k++) { ph_light[k] = ls[k].x; ph_loc[k * 3] = lw[k].x; ph_loc[k * 3 + 1] = lw[k].y; ph_loc[k * 3 + 2] = lw[k].z; ph_w[k] = lw[k].w; }
+  ph_host_valid = true;
+}
+void Context::photon_tree_host() {
+  require_device();
+  if (tree_host_valid) return;
+  const std::vector<uint32_t>& child_base = oc_child_base_h; const std::vector<uint32_t>& count = oc_count_h; const std::vector<uint32_t>& depth = oc_depth_h;
+  const uint32_t nodes = (uint32_t)child_base.size();
+  const uint32_t L = (uint32_t)scene.lights.size();
+  // DFS pre-order (children in octant order), like the oracle's flattening
   std::vector<float> cum((size_t)nodes * L), bins((size_t)nodes * L);
   WPT_CUDA(cudaMemcpyAsync(cum.data(), p_cum.p, cum.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
   WPT_CUDA(cudaMemcpyAsync(bins.data(), p_bins.p, bins.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -174,9 +189,7 @@ void Context::build_photons() {
     pt_bins.insert(pt_bins.end(), bins.begin() + (size_t)n * L, bins.begin() + (size_t)(n + 1) * L);
     if (is_node) for (int c = 7; c >= 0; c--) st.push_back(child_base[n] + c);
   }
-  photons_ready = true;
-  photon_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-  if (std::getenv("WPT_TRACE_PHOTONS")) std::fprintf(stderr, "wpt photon warm-up: %.2f ms (%llu shots, %llu photons, %u octree nodes)\n", photon_build_ms, (unsigned long long)shots, (unsigned long long)stored, nodes);
+  tree_host_valid = true;
 }
 
 void Context::photon_sample_batch(const float* pts3, const uint32_t* seeds, uint64_t n, uint32_t* light, float* pdf) {

@@ -691,6 +691,41 @@ void launch_photon_emit(const RenderParams& rp, unsigned long long shot0, uint32
   k_photon_emit<<<(n + 127) / 128, 128, 0, s>>>(rp, shot0, n, rank, world ? world : 1u, meta, rec_light, rec_loc_w);
 }
 
+// Batch compaction on the device: off[i] = photons stored by the shots before shot i of this batch (exclusive scan of the stored
+// flags). The photon set ends with the shot that stores photon number `target`: shot i belongs to it iff off[i] < remaining.
+// res[0] += photons taken, res[1] += shots taken (= the cut), res[2] += node visits and res[3] += shots of this rank's own shots.
+__global__ void k_photon_flags(const uint32_t* __restrict__ meta, uint32_t n, uint32_t* __restrict__ flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) flag[i] = i < n ? meta[i] >> 31 : 0u;
+}
+__global__ void k_photon_take(const uint32_t* __restrict__ meta, const uint32_t* __restrict__ light, const float4* __restrict__ lw, const uint32_t* __restrict__ off, uint32_t n,
+                              uint32_t remaining, uint32_t base, uint32_t rank, uint32_t world, float4* __restrict__ out_lw, uint2* __restrict__ out_ls, unsigned long long* res) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long taken = 0, shots = 0, visits = 0, own = 0;
+  if (i < n) {
+    const uint32_t m = meta[i], o = off[i];
+    if (o < remaining) {
+      shots = 1;
+      if (i % world == rank) { visits = m & 0x7FFFFFFFu; own = 1; }
+      if (m >> 31) { out_lw[base + o] = lw[i]; out_ls[base + o] = make_uint2(light[i], i); taken = 1; }
+    }
+  }
+  taken = warp_sum_u64(taken); shots = warp_sum_u64(shots); visits = warp_sum_u64(visits); own = warp_sum_u64(own);
+  if ((threadIdx.x & 31) == 0) {
+    if (taken) atomicAdd(&res[0], taken);
+    if (shots) atomicAdd(&res[1], shots);
+    if (visits) atomicAdd(&res[2], visits);
+    if (own) atomicAdd(&res[3], own);
+  }
+}
+void launch_photon_compact(const uint32_t* meta, const uint32_t* light, const float4* lw, uint32_t n, uint32_t remaining, uint32_t base, uint32_t rank, uint32_t world,
+                           uint32_t* flag, uint32_t* off, void* scan_tmp, size_t scan_bytes, float4* out_lw, uint2* out_ls, unsigned long long* res, cudaStream_t s) {
+  if (!n) return;
+  k_photon_flags<<<(n + 1 + 255) / 256, 256, 0, s>>>(meta, n, flag);
+  cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flag, off, (int)(n + 1), s);
+  k_photon_take<<<(n + 255) / 256, 256, 0, s>>>(meta, light, lw, off, n, remaining, base, rank, world ? world : 1u, out_lw, out_ls, res);
+}
+
 // ---- octree (photon_tree.rs). Cells are split level by level; a cell is split iff it finally
 // holds more than 1024 photons (photon_tree.rs:29,179), so the topology does not depend on
 // insertion order. node_of[p] = the deepest existing cell containing photon p.

@@ -99,6 +99,8 @@ void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, u
 
 // photons
 void launch_photon_emit(const RenderParams& rp, unsigned long long shot0, uint32_t n, uint32_t rank, uint32_t world, uint32_t* meta, uint32_t* rec_light, float4* rec_loc_w, cudaStream_t s);
+void launch_photon_compact(const uint32_t* meta, const uint32_t* light, const float4* lw, uint32_t n, uint32_t remaining, uint32_t base, uint32_t rank, uint32_t world,
+                           uint32_t* flag, uint32_t* off, void* scan_tmp, size_t scan_bytes, float4* out_lw, uint2* out_ls, unsigned long long* res, cudaStream_t s);
 void launch_octree_assign(const float4* loc_w, uint32_t n, uint32_t* node_of, const uint32_t* child_base, uint32_t* count, cudaStream_t s);
 void launch_octree_bins(const float4* loc_w, const uint2* light_shot, uint32_t n, const uint32_t* child_base, unsigned long long* fx, uint32_t num_lights, cudaStream_t s);
 void launch_octree_cdf(const unsigned long long* fx, float* bins, float* cum, uint32_t num_nodes, uint32_t num_lights, cudaStream_t s);

@@ -1,5 +1,5 @@
 """Small renders of every device code path for compute-sanitizer (scripts/sanitize.sh): both scenes, BVH2 / BVH4,
-NoNEE / NEE / PNEE (photon warm-up + octree build), adaptive and random strategy rounds, the three engines."""
+NoNEE / NEE / PNEE (photon warm-up + octree build), adaptive and random strategy rounds, both engines."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -7,7 +7,7 @@ import numpy as np
 import wasm_pathtracer_b200 as W
 from bench import mesh_path
 v = W.parse_obj(open(mesh_path(3)).read(), True)
-engines = [int(e) for e in (sys.argv[1] if len(sys.argv) > 1 else "0,1,4").split(",")]
+engines = [int(e) for e in (sys.argv[1] if len(sys.argv) > 1 else "0,1").split(",")]
 for engine in engines:
     for scene, cam, bvh, rtype in ((2, W.CAM_BUNNY, 2, W.NORMAL_NEE), (2, W.CAM_BUNNY, 4, W.PNEE), (0, W.CAM_MUSEUM, 2, W.PNEE), (0, W.CAM_MUSEUM, 2, W.NO_NEE)):
         pt = W.PathTracer(64, 44, scene, *cam, device=0)

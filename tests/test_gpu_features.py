@@ -120,7 +120,7 @@ def test_random_strategy_many_samples_per_pixel(gpu_ok, meshes):
     rgb, cnt = pt.accum(); orgb, ocnt = orc.accum()
     assert cnt.max() > 128 and np.array_equal(cnt, ocnt)
     assert np.array_equal(bits(rgb), bits(orgb))
-    for engine in (1, 4):
+    for engine in (1,):
         pt.reset(); pt.set_config(engine=engine); pt.render_random(ticks)
         assert np.array_equal(bits(pt.accum()[0]), bits(rgb)), engine
     pt.close()
@@ -162,23 +162,6 @@ def test_wavefront_engine_matches_persistent_engine(gpu_ok, meshes):
     rgb1, _ = a.accum(); st1 = a.stats()
     assert np.array_equal(bits(rgb0), bits(rgb1))
     assert (st0["rays"], st0["node_visits"], st0["paths"]) == (st1["rays"], st1["node_visits"], st1["paths"])
-
-
-def test_warp_pool_engine_matches_persistent_engine(gpu_ok, meshes):
-    """k_wpool (engine 4, experimental: a pool of path contexts per warp, logic runs / traversal bursts) renders the same
-    bits and counts as k_mega, for both BVH kinds, PNEE and a ragged viewport."""
-    for (w, h, bvh, rtype) in [(128, 72, 2, W.NORMAL_NEE), (333, 211, 2, W.PNEE), (97, 61, 4, W.NORMAL_NEE)]:
-        a = W.PathTracer(w, h, 2, *W.CAM_BUNNY, device=0); a.store_mesh(1, meshes[4])
-        a.set_config(bvh_kind=bvh, render_type=rtype, photon_target=20000, engine=0)
-        if rtype == W.PNEE:
-            a.build_photons()
-        a.reset(); a.render_exact(3); a.render_exact(1)
-        rgb0, c0 = a.accum(); st0 = a.stats()
-        a.reset(); a.set_config(engine=4); a.render_exact(3); a.render_exact(1)
-        rgb1, c1 = a.accum(); st1 = a.stats()
-        assert np.array_equal(bits(rgb0), bits(rgb1)) and np.array_equal(c0, c1)
-        assert (st0["rays"], st0["node_visits"], st0["paths"]) == (st1["rays"], st1["node_visits"], st1["paths"])
-        a.close()
 
 
 def test_photon_warmup_split_over_ranks_is_bit_exact(gpu_ok, meshes):
@@ -259,7 +242,7 @@ def test_segmented_accumulation_contract_b10(gpu_ok, meshes):
     assert np.array_equal(bits(rgb), bits(orgb))
     st, ost = pt.stats(), orc.stats(0)
     assert (st["rays"], st["node_visits"], st["paths"]) == (ost["rays"], ost["node_visits"], ost["paths"])
-    for engine in (1, 4):
+    for engine in (1,):
         pt.reset(); pt.set_config(engine=engine); pt.render_exact(37); pt.render_exact(5)
         r2, c2 = pt.accum()
         assert np.array_equal(bits(rgb), bits(r2)) and np.array_equal(cnt, c2), engine

@@ -409,6 +409,9 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
     P.seed_path = mix32((uint32_t)STREAM_PATH ^ cfg.base_seed);
   }
   if (cfg.engine == 4) {
+#ifndef WPT_EXPERIMENTAL
+    throw std::runtime_error("engine 4 (experimental warp-pool kernel) is not in this build: make EXTRA=-DWPT_EXPERIMENTAL EXPERIMENTAL_SRCS=wpool.cu");
+#else
     // experimental warp-pool kernel (wpool.cu): grid = SMs x blocks per SM; every warp owns pool_ctx path contexts of 160 B
     static const int w_minb = std::getenv("WPT_WPOOL_MINB") ? std::atoi(std::getenv("WPT_WPOOL_MINB")) : 8;
     static const int w_ctx = std::getenv("WPT_WPOOL_CTX") ? std::atoi(std::getenv("WPT_WPOOL_CTX")) : 96;
@@ -424,6 +427,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
     P.pool = d_pool.p;
     P.t_hi = (uint32_t)w_thi; P.t_lo = (uint32_t)w_tlo; P.t_switch = (uint32_t)w_tsw; P.t_refill = (uint32_t)std::max(1, w_ref);
     launch_wpool(P, grid, minb, stream);
+#endif
   } else launch_mega(P, env_minb, stream);
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());

@@ -226,6 +226,7 @@ void orc_empirical_pdf(const float* bins, uint32_t nb, uint32_t seed, uint32_t n
   for (uint32_t i = 0; i < nb; i++) probs[i] = pdf.bin_prob(i);
 }
 // quartic solver: coef[5] = a4..a0 -> roots (ascending), returns count
+void orc_shared_f64(int which, const double* x, uint32_t n, double* out) { for (uint32_t i = 0; i < n; i++) out[i] = which == 0 ? shared_cos64(x[i]) : which == 1 ? shared_acos64(x[i]) : shared_cbrt64(x[i]); }
 int orc_quartic(const double* coef, double* roots_out) { Roots r = roots_quartic(coef[0], coef[1], coef[2], coef[3], coef[4]); for (int i = 0; i < r.n; i++) roots_out[i] = r.v[i]; return r.n; }
 // OBJ text -> expanded vertices (9 floats per triangle); returns float count, fills up to cap
 int64_t orc_parse_obj(const char* text, uint64_t len, int client_scale, float* out, uint64_t cap) {

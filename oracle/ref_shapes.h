@@ -4,6 +4,7 @@
 // sources absent from the reference mount: restated from the crate's published
 // algorithm — discriminant test, depressed quartic, Ferrari resolvent cubic).
 #pragma once
+#include <cstring>
 #include "ref_core.h"
 
 namespace ref {
@@ -53,6 +54,64 @@ struct Hit {
   Hit(float d, Vec3 n, const Material& m, bool e) : distance(d), normal(normalize(n)), mat(m), is_entering(e) {}
 };
 
+// ---------------------------------------------------------------- shared f64 transcendentals
+#define F64_FN static inline
+static inline unsigned long long f64_bits(double v) { unsigned long long u; std::memcpy(&u, &v, 8); return u; }
+static inline double f64_from_bits(unsigned long long u) { double v; std::memcpy(&v, &u, 8); return v; }
+#define F64_BITS(a) f64_bits(a)
+#define F64_FROM_BITS(b) f64_from_bits(b)
+
+// Shared f64 acos / cos / cbrt for the torus' quartic solver (deviation B11): glibc and CUDA round these
+// routines differently in the last place, and a last-place difference in f64 occasionally flips the f32 rounding of a hit
+// distance (a handful of the 300 000 museum photons). Both sides therefore evaluate the same f64 + - * / sqrt sequence
+// (no FMA contraction on either side): Cody-Waite reduction + Taylor kernels, the asin series, Halley iterations.
+// Accuracy: <= 2 ulp against libm (tests/test_oracle_kat.py).
+F64_FN double shared_cos64(double x) {
+  const double kd = std::floor(x * 0.6366197723675814 + 0.5);
+  const double r = ((x - kd * 1.5707963109016418) - kd * 1.5893254773528196e-08) - kd * 6.36831716351095e-25;   // pi/2 in three parts, kd * part 1 is exact
+  const double z = r * r;
+  const double c = 1.0 + z * (-0.5 + z * (0.041666666666666664 + z * (-0.001388888888888889 + z * (2.48015873015873e-05 + z * (-2.755731922398589e-07 +
+                   z * (2.08767569878681e-09 + z * (-1.1470745597729725e-11 + z * (4.779477332387385e-14 + z * -1.5619206968586225e-16))))))));
+  const double s = r + r * z * (-0.16666666666666666 + z * (0.008333333333333333 + z * (-0.0001984126984126984 + z * (2.7557319223985893e-06 + z * (-2.505210838544172e-08 +
+                   z * (1.6059043836821613e-10 + z * (-7.647163731819816e-13 + z * (2.8114572543455206e-15 + z * -8.22063524662433e-18))))))));
+  switch ((int)kd & 3) {
+    case 0: return c;
+    case 1: return -s;
+    case 2: return -c;
+    default: return s;
+  }
+}
+F64_FN double shared_asin_small64(double x) {   // |x| <= 0.5: x + x z (c1 + z (c2 + ...)), 27 terms of the series (next term 1e-19 at 0.5)
+  const double z = x * x;
+  double p = 0.0019650336162772837;
+  const double c[26] = {0.0020776610325181676, 0.0022014739737101384, 0.002338091892111975, 0.0024894486782468836, 0.00265787063820729, 0.002846178401108942,
+                        0.0030578216492580306, 0.003297059503473485, 0.0035692053938259347, 0.003880964558837669, 0.004240907093679363, 0.004660143486915096,
+                        0.005153309682319905, 0.005740037670841924, 0.006447210311889649, 0.0073125258735988454, 0.008390335809616815, 0.009761609529194078,
+                        0.011551800896139705, 0.01396484375, 0.017352764423076924, 0.022372159090909092, 0.030381944444444444, 0.044642857142857144, 0.075,
+                        0.16666666666666666};
+  for (int i = 0; i < 26; i++) p = c[i] + z * p;
+  return x + x * z * p;
+}
+F64_FN double shared_acos64(double x) {
+  if (x > 0.5) return 2.0 * shared_asin_small64(std::sqrt((1.0 - x) * 0.5));
+  if (x < -0.5) return 3.141592653589793 - 2.0 * shared_asin_small64(std::sqrt((1.0 + x) * 0.5));
+  return 1.5707963267948966 - shared_asin_small64(x);
+}
+F64_FN double shared_cbrt64(double x) {
+  if (x == 0.0 || x != x) return x;
+  double a = x < 0.0 ? -x : x;
+  if (a > 1.7976931348623157e308) return x;
+  double scale = 1.0;
+  if (a < 2.2250738585072014e-308) { a *= 18014398509481984.0; scale = 3.814697265625e-06; }   // subnormal: 2^54, 2^-18
+  double t = F64_FROM_BITS(F64_BITS(a) / 3ull + 0x2A9F7893782DA1CEull);                          // 3 % initial guess
+  for (int i = 0; i < 4; i++) { const double t3 = t * t * t; t = t * ((t3 + a + a) / (t3 + t3 + a)); }   // Halley, cubic convergence
+  t = t - (t * t * t - a) / (3.0 * t * t);
+  return (x < 0.0 ? -t : t) * scale;
+}
+#undef F64_FN
+#undef F64_BITS
+#undef F64_FROM_BITS
+
 // ---------------------------------------------------------------- roots 0.0.4 (restated)
 struct Roots {
   int n = 0;
@@ -98,16 +157,16 @@ static inline Roots roots_cubic_normalized(double a2, double a1, double a0) {
   double d = q3 + r * r;
   double a2_div_3 = a2 / 3.0;
   if (d < 0.0) {
-    double phi_3 = std::acos(r / std::sqrt(-q3)) / 3.0;
+    double phi_3 = shared_acos64(r / std::sqrt(-q3)) / 3.0;
     double sqrt_q_2 = 2.0 * std::sqrt(-q);
     const double two_third_pi = 2.0943951023931954923;
-    out.add(sqrt_q_2 * std::cos(phi_3) - a2_div_3);
-    out.add(sqrt_q_2 * std::cos(phi_3 - two_third_pi) - a2_div_3);
-    out.add(sqrt_q_2 * std::cos(phi_3 + two_third_pi) - a2_div_3);
+    out.add(sqrt_q_2 * shared_cos64(phi_3) - a2_div_3);
+    out.add(sqrt_q_2 * shared_cos64(phi_3 - two_third_pi) - a2_div_3);
+    out.add(sqrt_q_2 * shared_cos64(phi_3 + two_third_pi) - a2_div_3);
   } else {
     double sqrt_d = std::sqrt(d);
-    double s = std::cbrt(r + sqrt_d);
-    double t = std::cbrt(r - sqrt_d);
+    double s = shared_cbrt64(r + sqrt_d);
+    double t = shared_cbrt64(r - sqrt_d);
     out.add(s + t - a2_div_3);
     if (s == t && s + t != 0.0) out.add(-(s + t) / 2.0 - a2_div_3);
   }

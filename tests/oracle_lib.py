@@ -262,6 +262,12 @@ def empirical_pdf(bins, seed, n):
     lib().orc_empirical_pdf(_p(b, C.c_float), b.size, C.c_uint32(seed), n, _p(hist, C.c_uint32), _p(probs, C.c_float)); return hist, probs
 
 
+def shared_f64(which, x):
+    """which: 0 cos, 1 acos, 2 cbrt — the shared f64 routines of the quartic solver (deviation B11)."""
+    x = np.ascontiguousarray(x, np.float64); out = np.empty_like(x)
+    lib().orc_shared_f64(which, _p(x, C.c_double), x.size, _p(out, C.c_double)); return out
+
+
 def quartic(coef):
     c = np.ascontiguousarray(coef, np.float64); out = np.empty(4, np.float64)
     n = lib().orc_quartic(_p(c, C.c_double), _p(out, C.c_double)); return out[:n]

@@ -72,6 +72,23 @@ def test_shared_sincos_accuracy():
     assert np.abs(c - np.cos(a.astype(np.float64))).max() < 6e-7
 
 
+def test_shared_f64_routines_are_within_2_ulp_of_libm():
+    """Deviation B11: the quartic solver's acos / cos / cbrt are one f64 + - * / sqrt sequence shared by the oracle and
+    the CUDA code (glibc and CUDA round their own routines differently in the last place)."""
+    rng = np.random.default_rng(1)
+
+    def ulps(a, b):
+        return np.abs(a - b) / np.spacing(np.abs(b))
+    x = rng.uniform(-2.2, 3.3, 100000)                              # phi/3 +- 2 pi/3 with phi in [0, pi]
+    assert ulps(O.shared_f64(0, x), np.cos(x)).max() <= 2 or np.abs(O.shared_f64(0, x) - np.cos(x)).max() < 3e-16
+    x = rng.uniform(-1, 1, 100000); x[:6] = [1, -1, 0, 0.5, -0.5, 0.999999999]
+    a, b = O.shared_f64(1, x), np.arccos(x)
+    assert ulps(a[b > 0], b[b > 0]).max() <= 2 and a[0] == 0.0
+    x = np.concatenate([rng.uniform(-1e3, 1e3, 50000), 10.0 ** rng.uniform(-300, 300, 50000), [27.0, 8.0, -64.0, 1e-320]])
+    assert ulps(O.shared_f64(2, x), np.cbrt(x)).max() <= 2
+    assert O.shared_f64(2, np.array([0.0, np.inf]))[0] == 0.0 and np.isinf(O.shared_f64(2, np.array([np.inf]))[0])
+
+
 def test_quartic_against_numpy_roots():
     # roots 0.0.4 restatement (parity unpinned): real roots must agree with a companion-matrix solve
     rng = np.random.default_rng(5)

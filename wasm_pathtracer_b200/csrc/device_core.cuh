@@ -121,9 +121,63 @@ WPT_DEV float box_hit_x4(float x0, float y0, float z0, float x1, float y1, float
 // library routine, division and square root it uses — the same routines, hence the same bits, a third of the code.
 static __device__ __noinline__ double nl_div(double a, double b) { return a / b; }
 static __device__ __noinline__ double nl_sqrt(double a) { return sqrt(a); }
-static __device__ __noinline__ double nl_cos(double a) { return cos(a); }
-static __device__ __noinline__ double nl_acos(double a) { return acos(a); }
-static __device__ __noinline__ double nl_cbrt(double a) { return cbrt(a); }
+#define F64_FN static __device__ __noinline__
+#define F64_BITS(a) ((unsigned long long)__double_as_longlong(a))
+#define F64_FROM_BITS(b) __longlong_as_double((long long)(b))
+
+// Shared f64 acos / cos / cbrt for the torus' quartic solver (deviation B11): glibc and CUDA round these
+// routines differently in the last place, and a last-place difference in f64 occasionally flips the f32 rounding of a hit
+// distance (a handful of the 300 000 museum photons). Both sides therefore evaluate the same f64 + - * / sqrt sequence
+// (no FMA contraction on either side): Cody-Waite reduction + Taylor kernels, the asin series, Halley iterations.
+// Accuracy: <= 2 ulp against libm (tests/test_oracle_kat.py).
+F64_FN double shared_cos64(double x) {
+  const double kd = floor(x * 0.6366197723675814 + 0.5);
+  const double r = ((x - kd * 1.5707963109016418) - kd * 1.5893254773528196e-08) - kd * 6.36831716351095e-25;   // pi/2 in three parts, kd * part 1 is exact
+  const double z = r * r;
+  const double c = 1.0 + z * (-0.5 + z * (0.041666666666666664 + z * (-0.001388888888888889 + z * (2.48015873015873e-05 + z * (-2.755731922398589e-07 +
+                   z * (2.08767569878681e-09 + z * (-1.1470745597729725e-11 + z * (4.779477332387385e-14 + z * -1.5619206968586225e-16))))))));
+  const double s = r + r * z * (-0.16666666666666666 + z * (0.008333333333333333 + z * (-0.0001984126984126984 + z * (2.7557319223985893e-06 + z * (-2.505210838544172e-08 +
+                   z * (1.6059043836821613e-10 + z * (-7.647163731819816e-13 + z * (2.8114572543455206e-15 + z * -8.22063524662433e-18))))))));
+  switch ((int)kd & 3) {
+    case 0: return c;
+    case 1: return -s;
+    case 2: return -c;
+    default: return s;
+  }
+}
+F64_FN double shared_asin_small64(double x) {   // |x| <= 0.5: x + x z (c1 + z (c2 + ...)), 27 terms of the series (next term 1e-19 at 0.5)
+  const double z = x * x;
+  double p = 0.0019650336162772837;
+  const double c[26] = {0.0020776610325181676, 0.0022014739737101384, 0.002338091892111975, 0.0024894486782468836, 0.00265787063820729, 0.002846178401108942,
+                        0.0030578216492580306, 0.003297059503473485, 0.0035692053938259347, 0.003880964558837669, 0.004240907093679363, 0.004660143486915096,
+                        0.005153309682319905, 0.005740037670841924, 0.006447210311889649, 0.0073125258735988454, 0.008390335809616815, 0.009761609529194078,
+                        0.011551800896139705, 0.01396484375, 0.017352764423076924, 0.022372159090909092, 0.030381944444444444, 0.044642857142857144, 0.075,
+                        0.16666666666666666};
+  for (int i = 0; i < 26; i++) p = c[i] + z * p;
+  return x + x * z * p;
+}
+F64_FN double shared_acos64(double x) {
+  if (x > 0.5) return 2.0 * shared_asin_small64(sqrt((1.0 - x) * 0.5));
+  if (x < -0.5) return 3.141592653589793 - 2.0 * shared_asin_small64(sqrt((1.0 + x) * 0.5));
+  return 1.5707963267948966 - shared_asin_small64(x);
+}
+F64_FN double shared_cbrt64(double x) {
+  if (x == 0.0 || x != x) return x;
+  double a = x < 0.0 ? -x : x;
+  if (a > 1.7976931348623157e308) return x;
+  double scale = 1.0;
+  if (a < 2.2250738585072014e-308) { a *= 18014398509481984.0; scale = 3.814697265625e-06; }   // subnormal: 2^54, 2^-18
+  double t = F64_FROM_BITS(F64_BITS(a) / 3ull + 0x2A9F7893782DA1CEull);                          // 3 % initial guess
+  for (int i = 0; i < 4; i++) { const double t3 = t * t * t; t = t * ((t3 + a + a) / (t3 + t3 + a)); }   // Halley, cubic convergence
+  t = t - (t * t * t - a) / (3.0 * t * t);
+  return (x < 0.0 ? -t : t) * scale;
+}
+#undef F64_FN
+#undef F64_BITS
+#undef F64_FROM_BITS
+static __device__ __forceinline__ double nl_cos(double a) { return shared_cos64(a); }
+static __device__ __forceinline__ double nl_acos(double a) { return shared_acos64(a); }
+static __device__ __forceinline__ double nl_cbrt(double a) { return shared_cbrt64(a); }
 struct Roots4 {
   int n; double v[4];
   WPT_DEV void add(double x) {

@@ -70,16 +70,15 @@ F64_FN double shared_cos64(double x) {
   const double kd = std::floor(x * 0.6366197723675814 + 0.5);
   const double r = ((x - kd * 1.5707963109016418) - kd * 1.5893254773528196e-08) - kd * 6.36831716351095e-25;   // pi/2 in three parts, kd * part 1 is exact
   const double z = r * r;
+  const int q = (int)kd & 3;
+  if (q & 1) {   // +- sin r
+    const double s = r + r * z * (-0.16666666666666666 + z * (0.008333333333333333 + z * (-0.0001984126984126984 + z * (2.7557319223985893e-06 + z * (-2.505210838544172e-08 +
+                     z * (1.6059043836821613e-10 + z * (-7.647163731819816e-13 + z * (2.8114572543455206e-15 + z * -8.22063524662433e-18))))))));
+    return q == 1 ? -s : s;
+  }
   const double c = 1.0 + z * (-0.5 + z * (0.041666666666666664 + z * (-0.001388888888888889 + z * (2.48015873015873e-05 + z * (-2.755731922398589e-07 +
                    z * (2.08767569878681e-09 + z * (-1.1470745597729725e-11 + z * (4.779477332387385e-14 + z * -1.5619206968586225e-16))))))));
-  const double s = r + r * z * (-0.16666666666666666 + z * (0.008333333333333333 + z * (-0.0001984126984126984 + z * (2.7557319223985893e-06 + z * (-2.505210838544172e-08 +
-                   z * (1.6059043836821613e-10 + z * (-7.647163731819816e-13 + z * (2.8114572543455206e-15 + z * -8.22063524662433e-18))))))));
-  switch ((int)kd & 3) {
-    case 0: return c;
-    case 1: return -s;
-    case 2: return -c;
-    default: return s;
-  }
+  return q == 0 ? c : -c;
 }
 F64_FN double shared_asin_small64(double x) {   // |x| <= 0.5: x + x z (c1 + z (c2 + ...)), 27 terms of the series (next term 1e-19 at 0.5)
   const double z = x * x;
@@ -104,7 +103,7 @@ F64_FN double shared_cbrt64(double x) {
   double scale = 1.0;
   if (a < 2.2250738585072014e-308) { a *= 18014398509481984.0; scale = 3.814697265625e-06; }   // subnormal: 2^54, 2^-18
   double t = F64_FROM_BITS(F64_BITS(a) / 3ull + 0x2A9F7893782DA1CEull);                          // 3 % initial guess
-  for (int i = 0; i < 4; i++) { const double t3 = t * t * t; t = t * ((t3 + a + a) / (t3 + t3 + a)); }   // Halley, cubic convergence
+  for (int i = 0; i < 3; i++) { const double t3 = t * t * t; t = t * ((t3 + a + a) / (t3 + t3 + a)); }   // Halley, cubic convergence: 3e-2 -> 3e-5 -> 2e-14 -> 0
   t = t - (t * t * t - a) / (3.0 * t * t);
   return (x < 0.0 ? -t : t) * scale;
 }

@@ -134,16 +134,15 @@ F64_FN double shared_cos64(double x) {
   const double kd = floor(x * 0.6366197723675814 + 0.5);
   const double r = ((x - kd * 1.5707963109016418) - kd * 1.5893254773528196e-08) - kd * 6.36831716351095e-25;   // pi/2 in three parts, kd * part 1 is exact
   const double z = r * r;
+  const int q = (int)kd & 3;
+  if (q & 1) {   // +- sin r
+    const double s = r + r * z * (-0.16666666666666666 + z * (0.008333333333333333 + z * (-0.0001984126984126984 + z * (2.7557319223985893e-06 + z * (-2.505210838544172e-08 +
+                     z * (1.6059043836821613e-10 + z * (-7.647163731819816e-13 + z * (2.8114572543455206e-15 + z * -8.22063524662433e-18))))))));
+    return q == 1 ? -s : s;
+  }
   const double c = 1.0 + z * (-0.5 + z * (0.041666666666666664 + z * (-0.001388888888888889 + z * (2.48015873015873e-05 + z * (-2.755731922398589e-07 +
                    z * (2.08767569878681e-09 + z * (-1.1470745597729725e-11 + z * (4.779477332387385e-14 + z * -1.5619206968586225e-16))))))));
-  const double s = r + r * z * (-0.16666666666666666 + z * (0.008333333333333333 + z * (-0.0001984126984126984 + z * (2.7557319223985893e-06 + z * (-2.505210838544172e-08 +
-                   z * (1.6059043836821613e-10 + z * (-7.647163731819816e-13 + z * (2.8114572543455206e-15 + z * -8.22063524662433e-18))))))));
-  switch ((int)kd & 3) {
-    case 0: return c;
-    case 1: return -s;
-    case 2: return -c;
-    default: return s;
-  }
+  return q == 0 ? c : -c;
 }
 F64_FN double shared_asin_small64(double x) {   // |x| <= 0.5: x + x z (c1 + z (c2 + ...)), 27 terms of the series (next term 1e-19 at 0.5)
   const double z = x * x;
@@ -168,7 +167,7 @@ F64_FN double shared_cbrt64(double x) {
   double scale = 1.0;
   if (a < 2.2250738585072014e-308) { a *= 18014398509481984.0; scale = 3.814697265625e-06; }   // subnormal: 2^54, 2^-18
   double t = F64_FROM_BITS(F64_BITS(a) / 3ull + 0x2A9F7893782DA1CEull);                          // 3 % initial guess
-  for (int i = 0; i < 4; i++) { const double t3 = t * t * t; t = t * ((t3 + a + a) / (t3 + t3 + a)); }   // Halley, cubic convergence
+  for (int i = 0; i < 3; i++) { const double t3 = t * t * t; t = t * ((t3 + a + a) / (t3 + t3 + a)); }   // Halley, cubic convergence: 3e-2 -> 3e-5 -> 2e-14 -> 0
   t = t - (t * t * t - a) / (3.0 * t * t);
   return (x < 0.0 ? -t : t) * scale;
 }
@@ -307,6 +306,38 @@ static __device__ __noinline__ void d_quartic(double a4, double a3, double a2, d
 }
 
 // ------------------------------------------------------------------ primitives
+// Conservative f32 cull in front of the f64 quartic (no reference counterpart: it only skips solver calls that cannot
+// return a root). The flat torus (axis y, torus.rs:11-16) lies inside the slab |y - c.y| <= r and between the cylinders of
+// radius R - r and R + r around its axis. Over the part of the ray inside the slab (widened by the margin m) the squared
+// distance from the axis is a convex quadratic in t: if its maximum there is below (R - r - m)^2 the ray passes through the
+// hole, if its minimum is above (R + r + m)^2 it passes outside. m = 0.02 is four orders of magnitude above the f32
+// rounding of these expressions, and a ray that stays 0.02 away from the surface has no real root (F >= (2 r m)^2).
+// Only for origins within 64 units of the torus: from tens of thousands of units away (grazing bounces off the infinite
+// floor) the reference's f64 quartic itself returns numerically spurious roots, which have to be reproduced, not fixed.
+WPT_DEV bool torus_may_hit(float4 q0, float4 q1, const Ray& ray) {
+  const float R = q1.x, r = q1.y, m = 0.02f;
+  const float ox = ray.o.x - q0.x, oy = ray.o.y - q0.y, oz = ray.o.z - q0.z;
+  if (!(fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) <= 64.0f)) return true;
+  const float hy = r + m;
+  float t_lo = 0.0f, t_hi = WPT_INF;
+  if (fabsf(ray.d.y) > 1e-6f) {
+    const float ta = (-hy - oy) * ray.inv.y, tb = (hy - oy) * ray.inv.y;
+    t_lo = fmaxf(fminf(ta, tb), 0.0f); t_hi = fmaxf(ta, tb);
+    if (!(t_hi >= t_lo)) return false;            // the slab lies behind the origin
+  } else if (fabsf(oy) > hy) return false;        // parallel to the slab and outside of it
+  const float a = ray.d.x * ray.d.x + ray.d.z * ray.d.z, b = ox * ray.d.x + oz * ray.d.z, c = ox * ox + oz * oz;
+  const float outer = (R + r + m) * (R + r + m);
+  float t_min = a > 0.0f ? fminf(fmaxf(-b / a, t_lo), t_hi) : t_lo;   // the vertex clamped into the interval (t_hi may be inf)
+  if (!(t_min <= 3.0e38f)) t_min = t_lo;
+  const float rho_min = (a * t_min + 2.0f * b) * t_min + c;
+  if (rho_min > outer) return false;
+  if (t_hi <= 3.0e38f) {
+    const float inner = fmaxf(R - r - m, 0.0f) * fmaxf(R - r - m, 0.0f);
+    const float rho_a = (a * t_lo + 2.0f * b) * t_lo + c, rho_b = (a * t_hi + 2.0f * b) * t_hi + c;
+    if (fmaxf(rho_a, rho_b) < inner) return false;
+  }
+  return true;
+}
 // Torus::trace, torus.rs:61-126. Returns hit distance (f32) and outward-or-flipped normal.
 static __device__ __noinline__ bool torus_trace(float4 q0, float4 q1, const Ray& ray, float* t_out, F3* n_out, bool* entering_out = nullptr) {
   double a = (double)q1.x, b = (double)q1.y;
@@ -424,7 +455,7 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
     float u, v;
     if (!square_t(q0, q1, ray, &t, &u, &v)) return false;
   } else {                     // torus: ray.rs:110-116 default = trace().distance
-    if (!torus_trace(q0, q1, ray, &t, nullptr)) return false;
+    if (!torus_may_hit(q0, q1, ray) || !torus_trace(q0, q1, ray, &t, nullptr)) return false;
   }
   if (strict ? !(0.0f < t && t < limit) : !(t <= limit)) return false;
   *t_out = t;
@@ -495,7 +526,7 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
     n = ray.d.y > 0.0f ? f3(0, -1, 0) : f3(0, 1, 0);
     if (uv_out) *uv_out = make_float2(u, v);
   } else {
-    if (!torus_trace(q0, q1, ray, &t, &n, &entering)) return false;
+    if (!torus_may_hit(q0, q1, ray) || !torus_trace(q0, q1, ray, &t, &n, &entering)) return false;
   }
   *t_out = t;
   *n_out = normalize(n);   // Hit::new, ray.rs:59-62
@@ -530,43 +561,17 @@ struct GHit { float t; int id; uint32_t visits; uint32_t prims; };
 
 // trace_shapes_md over a leaf (scene.rs:450-472); updates (best_t, best_id) if the leaf
 // reports a hit — a later leaf wins exact ties because the test is t <= max_dis.
-// Tori (KIND != K_SIMPLE): the hit distance of a torus does not depend on what the scan has accepted so far, only the
-// acceptance test does. So the leaf's tori are intersected first — all lanes of the warp's leaf step that hold a torus run
-// the f64 solver together, once per torus slot, instead of one by one at whatever position the torus has in each lane's
-// leaf — and the ordered scan below takes their distances from a small cache: same tests, same order, same results.
-#define WPT_LEAF_TORI 12
+// (Tried in round 2 and removed: intersecting a leaf's tori first, with all lanes of the leaf step that hold one, and taking
+//  the distances from a cache in the ordered scan. The solver then starts with 14.5 lanes instead of 3, but diverges inside
+//  on the discriminant cases, and the extra loops cost more than they save: 55.5 ms against 54.0 ms on the museum frame,
+//  gpurun_out/r2_ab_museum3.log.)
 template <int KIND>
 WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const Ray& ray, float& bound, int& best_id, uint32_t& prims) {
   prims += count;
   bool have = false; float bt = 0.0f; uint32_t bi = 0;
-  if (KIND != K_SIMPLE && count <= 32u) {
-    uint32_t tor = 0u, hit = 0u;   // bit i: shape first + i is a torus / its solver found a root
-    for (uint32_t i = 0; i < count; i++)
-      if ((__float_as_uint(__ldg(&reinterpret_cast<const float4*>(sc.shapes + first + i)->w)) & 0xFFu) == SH_TORUS) tor |= 1u << i;
-    float tt[WPT_LEAF_TORI];
-    uint32_t cached = 0u, k = 0;
-    for (uint32_t m = tor; m && k < WPT_LEAF_TORI; m &= m - 1u, k++) {
-      const uint32_t i = (uint32_t)__ffs((int)m) - 1u;
-      const float4* p = reinterpret_cast<const float4*>(sc.shapes + first + i);
-      float t = 0.0f;
-      if (torus_trace(__ldg(p), __ldg(p + 1), ray, &t, nullptr)) hit |= 1u << i;
-      tt[k] = t; cached |= 1u << i;
-    }
-    k = 0;
-    for (uint32_t i = 0; i < count; i++) {
-      float t;
-      if (cached >> i & 1u) {   // Tracable::trace_simple of a torus = trace().distance (ray.rs:110-116) + the acceptance test of shape_trace_simple
-        t = tt[k++];
-        const float limit = have ? bt : bound;
-        if (!(hit >> i & 1u) || (have ? !(0.0f < t && t < limit) : !(t <= limit))) continue;
-      } else if (!shape_trace_simple<KIND>(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) continue;
-      have = true; bt = t; bi = first + i;
-    }
-  } else {
-    for (uint32_t i = 0; i < count; i++) {
-      float t;
-      if (shape_trace_simple<KIND>(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) { have = true; bt = t; bi = first + i; }
-    }
+  for (uint32_t i = 0; i < count; i++) {
+    float t;
+    if (shape_trace_simple<KIND>(sc.shapes, first + i, ray, have ? bt : bound, have, &t)) { have = true; bt = t; bi = first + i; }
   }
   if (have) { bound = bt; best_id = (int)bi; }
 }
@@ -676,8 +681,7 @@ WPT_DEV bool trav_pop(const DScene& sc, Trav& tv, const uint32_t* stack_n, const
   }
   return false;
 }
-// Enter the inner node tv.lf. Returns true if the lane has to pop next (BVH2: both children
-// missed; BVH4: always — the surviving children were pushed in reverse sorted order).
+// Enter the inner node tv.lf. Returns true if the lane has to pop next (no child survived).
 template <int BVH>
 WPT_DEV bool trav_inner(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* stack_n, float* stack_d) {
   if (BVH == 4) {
@@ -692,9 +696,16 @@ WPT_DEV bool trav_inner(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* st
     if (nc > 2) { id[2] = ch.z; d[2] = box_hit_x4(x0.z, y0.z, z0.z, x1.z, y1.z, z1.z, ray); }
     if (nc > 3) { id[3] = ch.w; d[3] = box_hit_x4(x0.w, y0.w, z0.w, x1.w, y1.w, z1.w, ray); }
     sort_small(id, d, nc);
+    // surviving children from the farthest to the nearest: all but the nearest go on the stack, the nearest is entered
+    // directly (its box distance was just tested against the bound, so the pop test could not drop it)
+    int pend_id = 0; float pend_d = 0.0f; bool have = false;
 #pragma unroll
     for (int i = 3; i >= 0; i--)
-      if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) { stack_n[tv.sp] = (uint32_t)id[i]; stack_d[tv.sp] = d[i]; tv.sp++; }
+      if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) {
+        if (have) { stack_n[tv.sp] = (uint32_t)pend_id; stack_d[tv.sp] = pend_d; tv.sp++; }
+        pend_id = id[i]; pend_d = d[i]; have = true;
+      }
+    if (have) { tv.lf = (uint32_t)pend_id; return false; }
     return true;
   }
   // BVH2, scene.rs:241-287 written with selects instead of four branches:

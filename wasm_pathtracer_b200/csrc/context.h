@@ -131,6 +131,7 @@ struct Context {
     uint32_t rx = 0, ry = 0, rw = 0, rh = 0;
     DevBuf<uint32_t> round_left, take, round_spp;   // region-indexed
     DevBuf<float> mse;
+    DevBuf<unsigned long long> state;   // device-driven adaptive rounds (kernels.cu k_ad_*)
     uint64_t left_total = 0;      // samples still queued in the current adaptive round
     bool started = false;         // the initial 4-spp queue has been issued
     bool painted = false;
@@ -161,6 +162,7 @@ struct Context {
   void region_error(Strategy& s, float stats3[3]);
   void render_take(Strategy& s, uint32_t render_type, bool bounded);
   uint64_t run_adaptive(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange);
+  uint64_t run_adaptive_host(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange);
   void run_random(Strategy& s, uint32_t render_type, uint64_t ticks);
   void render_random(uint64_t ticks);
 

@@ -61,6 +61,11 @@ void Context::attach_nccl(const uint8_t id128[128], void* existing_comm, uint32_
   }
   cfg.rank = rank; cfg.world = world;
   slots = 0;   // the pixel map depends on the partition
+  if (nccl_comm && world > 1) {   // NCCL sets up its channels at the first collective (~1 s): pay that here, not inside the first render
+    WPT_CUDA(cudaMemsetAsync(w_work.p + 2, 0, sizeof(uint32_t), stream));
+    WPT_NCCL(nccl().AllReduce(w_work.p + 2, w_work.p + 2, 1, ncclUint32, ncclSum, static_cast<ncclComm_t>(nccl_comm), stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+  }
   if (world > 1) {
     exchange_hook = [this] { exchange_native(); };
     reduce_hook = [this](uint32_t* p, uint64_t n) { reduce_native(p, n); };

@@ -223,7 +223,7 @@ void Context::region_error_launch(Strategy& s) {   // error map + {sum, min, max
   a_stats.alloc(4);
   static const unsigned long long init[4] = {0ull, 0x7F800000ull, 0ull, 0ull};
   WPT_CUDA(cudaMemcpyAsync(a_stats.p, init, sizeof init, cudaMemcpyHostToDevice, stream));
-  launch_error_map(d_accum.p, W, H, s.rx, s.ry, s.rw, s.rh, s.mse.p, a_stats.p, stream);
+  launch_error_map(d_accum.p, W, H, s.rx, s.ry, s.rw, s.rh, s.mse.p, a_stats.p, nullptr, stream);
   launches += 1;
 }
 void Context::region_error(Strategy& s, float stats3[3]) {
@@ -288,8 +288,63 @@ void Context::render_take(Strategy& s, uint32_t render_type, bool bounded) {
 // AdaptiveSamplingStrategy in mode B (see the oracle's mb_render_adaptive for the contract).
 // Every rank evaluates the (cheap) error map of the whole region from the gathered
 // accumulators, so no reduction is needed; each rank renders only its own rows.
+// AdaptiveSamplingStrategy in mode B (see the oracle's mb_render_adaptive for the contract), device-driven: the strategy's
+// state (samples left in the round, ticks used, first-queue flag) lives in s.state and every step — open a round if the last
+// one is used up (first queue, or error map -> samples per pixel), cut it to the room left in the budget in the reference's pop
+// order, render, subtract — is a fixed sequence of launches whose kernels read that state. The host enqueues steps ahead of
+// the device and reads one word (ticks used) every AD_CHUNK steps; steps enqueued past the end of the budget find it spent
+// and do nothing. Every rank evaluates the (cheap) error map of the whole region from the gathered accumulators, so no
+// reduction is needed; each rank renders only its own rows.
 uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange) {
+  if (use_wavefront()) return run_adaptive_host(s, render_type, budget, exchange);   // that engine polls the host anyway
+  const uint32_t N = s.rw * s.rh;
+  if (!N || !budget) return 0;
+  if (s.round_left.n < N) {
+    s.round_left.alloc(N); s.take.alloc(N); s.round_spp.alloc(N); s.mse.alloc(N); s.state.alloc(16);
+    launch_fill_u32(s.round_left.p, N, 0, stream);
+    WPT_CUDA(cudaMemsetAsync(s.state.p, 0, 16 * sizeof(unsigned long long), stream));
+  }
+  const uint32_t blocks = (N + 1023) / 1024;
+  a_block_tot.alloc(blocks); a_block_suffix.alloc(blocks);
+  unsigned long long* st = s.state.p;
+  launch_ad_setup(st, budget, stream);
+  static const int chunk = std::getenv("WPT_AD_CHUNK") ? std::max(1, std::atoi(std::getenv("WPT_AD_CHUNK"))) : 4;
+  uint64_t used = 0, steps = 0;
+  while (used < budget) {
+    for (int k = 0; k < chunk; k++) {
+      ev_mark(2, true);
+      launch_ad_begin(st, stream);
+      launch_ad_first(st, s.round_left.p, s.round_spp.p, N, stream);
+      launch_error_map(d_accum.p, W, H, s.rx, s.ry, s.rw, s.rh, s.mse.p, st, st + 9, stream);
+      launch_adaptive_spp(s.mse.p, N, st, s.round_left.p, s.round_spp.p, d_sampling.p, W, s.rx, s.ry, s.rw, st + 9, stream);
+      launch_ad_total(st, stream);
+      launch_cut_device(s.round_left.p, N, a_block_tot.p, a_block_suffix.p, st + 11, s.take.p, stream);
+      ev_mark(2, false);
+      ev_mark(3, true);
+      render_take(s, render_type, true);   // an adaptive round holds at most 33 samples per pixel
+      launch_sub_u32(s.round_left.p, s.take.p, N, stream);
+      launch_ad_end(st, stream);
+      ev_mark(3, false);
+      launches += 10;
+      if (exchange) { ev_mark(4, true); exchange(); ev_mark(4, false); }   // multi-GPU: gather the other ranks' rows before the next error map
+      steps++;
+    }
+    WPT_CUDA(cudaMemcpyAsync(h_counters + 14, st + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaMemcpyAsync(h_counters + 15, st + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    WPT_CUDA(cudaStreamSynchronize(stream));
+    used = h_counters[14];
+    if (steps > 4096 + budget / N) throw std::runtime_error("adaptive rounds do not converge");
+  }
+  adaptive_rounds += h_counters[15];
+  return used;
+}
+
+// The same strategy with the host in the loop (one read-back per round): the multi-kernel wavefront engine.
+uint64_t Context::run_adaptive_host(Strategy& s, uint32_t render_type, uint64_t budget, const std::function<void()>& exchange) {
   // with profiling on, CUDA events split every round into error map / render / exchange (prof_ms[2..4], no extra host syncs)
+  static const bool trace = std::getenv("WPT_TRACE_ROUNDS") != nullptr;   // host wall clock per round, to stderr
+  auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double w0 = trace ? wall() : 0.0;
   const uint32_t N = s.rw * s.rh;
   if (!N) return 0;
   if (s.round_left.n < N) { s.round_left.alloc(N); s.take.alloc(N); s.round_spp.alloc(N); launch_fill_u32(s.round_left.p, N, 0, stream); s.left_total = 0; s.started = false; }
@@ -307,7 +362,7 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
         // round's total (it decides whether the budget ends inside this round)
         ev_mark(2, true);
         region_error_launch(s);
-        launch_adaptive_spp(s.mse.p, N, a_stats.p, s.round_left.p, d_sampling.p, W, s.rx, s.ry, s.rw, stream);
+        launch_adaptive_spp(s.mse.p, N, a_stats.p, s.round_left.p, nullptr, d_sampling.p, W, s.rx, s.ry, s.rw, nullptr, stream);
         launches += 1;
         ev_mark(2, false);
         WPT_CUDA(cudaMemcpyAsync(h_counters + 15, a_stats.p + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -334,6 +389,7 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
       launches += 2;
       taken = room;
     }
+    const double w1 = trace ? wall() : 0.0;
     ev_mark(3, true);
     render_take(s, render_type, true);   // an adaptive round holds at most 33 samples per pixel
     launch_sub_u32(s.round_left.p, s.take.p, N, stream);
@@ -341,8 +397,10 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
     ev_mark(3, false);
     s.left_total -= taken;
     used += taken;
+    const double w2 = trace ? wall() : 0.0;
     if (exchange) { ev_mark(4, true); exchange(); ev_mark(4, false); }   // multi-GPU: gather the other ranks' rows before the next error map
     adaptive_rounds += 1;
+    if (trace) { const double w3 = wall(); std::fprintf(stderr, "wpt round (rank %u): error map + total %.3f ms, enqueue render %.3f ms, exchange %.3f ms, taken %llu\n", cfg.rank, w1 - w0, w2 - w1, w3 - w2, (unsigned long long)taken); w0 = w3; }
   }
   return used;
 }

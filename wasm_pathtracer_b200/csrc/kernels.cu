@@ -831,7 +831,8 @@ template <int K> WPT_DEV F3 gaussian(const float4* __restrict__ accum, uint32_t 
 }
 // error per pixel of the region + {sum in 2^-40 fixed point, min, max}; stats[0]=sum (u64),
 // stats[1]=min bits, stats[2]=max bits (errors are >= 0, so uint order == float order)
-__global__ void k_error_map(const float4* __restrict__ accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats) {
+__global__ void k_error_map(const float4* __restrict__ accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, const unsigned long long* gate) {
+  if (gate && *gate != AD_ERR) return;   // device-driven rounds: only when this step opens a new adaptive round
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long fx = 0; uint32_t mn = 0x7F800000u, mx = 0u;
   if (i < rw * rh) {
@@ -850,16 +851,17 @@ __global__ void k_error_map(const float4* __restrict__ accum, uint32_t W, uint32
     atomicMax(reinterpret_cast<unsigned int*>(&stats[2]), mx);
   }
 }
-void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, cudaStream_t s) {
+void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, const unsigned long long* gate, cudaStream_t s) {
   uint32_t n = rw * rh;
   if (!n) return;
-  k_error_map<<<(n + 127) / 128, 128, 0, s>>>(accum, W, H, rx, ry, rw, rh, mse, stats);
+  k_error_map<<<(n + 127) / 128, 128, 0, s>>>(accum, W, H, rx, ry, rw, rh, mse, stats, gate);
 }
 WPT_DEV uint32_t sampling_rgba(F3 v) { return 0xFF000000u | to_u8(v.x) | (to_u8(v.y) << 8) | (to_u8(v.z) << 16); }
 // error -> samples this round (1..33) + the sampling-density view (sampling_strategy.rs:154-174)
 // stats (device): [0] = sum of the errors in 2^-40 fixed point, [1] = min bits, [2] = max bits (k_error_map), [3] = total of the
 // samples this round allocates (written here): the host reads one word per round instead of synchronising twice
-__global__ void k_adaptive_spp(const float* __restrict__ mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint32_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw) {
+__global__ void k_adaptive_spp(const float* __restrict__ mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint32_t* round_spp, uint32_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, const unsigned long long* gate) {
+  if (gate && *gate != AD_ERR) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float mn = __uint_as_float((uint32_t)stats[1]), mx = __uint_as_float((uint32_t)stats[2]);
   const float avg = (float)(((double)stats[0] * (1.0 / 1099511627776.0)) / (double)n);
@@ -870,7 +872,7 @@ __global__ void k_adaptive_spp(const float* __restrict__ mse, uint32_t n, unsign
     sc = fmaxf(fminf(sc, 1.0f), 0.0f);
     float c = ceilf(1.0f + sc * 32.0f);
     uint32_t spp = c > 0.0f ? (uint32_t)c : 0u;
-    round_left[i] = spp; mine = spp;
+    round_left[i] = spp; if (round_spp) round_spp[i] = spp; mine = spp;
     F3 col;
     if (mn == mx) col = f3(0, 0, 0);
     else if (sc < 0.5f) col = f3(0.0f, 1.0f, 0.0f) * (1.0f - 2.0f * sc) + f3(0.0f, 0.0f, 1.0f) * 2.0f * sc;   // mix_color, :224-230
@@ -880,9 +882,9 @@ __global__ void k_adaptive_spp(const float* __restrict__ mse, uint32_t n, unsign
   mine = warp_sum_u64(mine);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&stats[3], mine);
 }
-void launch_adaptive_spp(const float* mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, cudaStream_t s) {
+void launch_adaptive_spp(const float* mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint32_t* round_spp, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, const unsigned long long* gate, cudaStream_t s) {
   if (!n) return;
-  k_adaptive_spp<<<(n + 255) / 256, 256, 0, s>>>(mse, n, stats, round_left, reinterpret_cast<uint32_t*>(sampling_rgba8), W, rx, ry, rw);
+  k_adaptive_spp<<<(n + 255) / 256, 256, 0, s>>>(mse, n, stats, round_left, round_spp, reinterpret_cast<uint32_t*>(sampling_rgba8), W, rx, ry, rw, gate);
 }
 // fill a region of the sampling view / a u32 array
 __global__ void k_fill_region_rgba(uint32_t* rgba, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t value) {
@@ -927,7 +929,8 @@ __global__ void k_cut_block_totals(const uint32_t* __restrict__ left, uint32_t n
   __syncthreads();
   if (threadIdx.x == 0) { unsigned long long t = 0; for (int k = 0; k < CUT_BLOCK / 32; k++) t += sh[k]; block_tot[blockIdx.x] = t; }
 }
-__global__ void k_cut_apply(const uint32_t* __restrict__ left, uint32_t n, const unsigned long long* __restrict__ block_suffix, unsigned long long budget, uint32_t* take) {
+__global__ void k_cut_apply(const uint32_t* __restrict__ left, uint32_t n, const unsigned long long* __restrict__ block_suffix, unsigned long long budget, const unsigned long long* budget_dev, uint32_t* take) {
+  if (budget_dev) budget = *budget_dev;   // device-driven rounds: the room left in the call's budget
   // block_suffix[b] = sum of left[] over all blocks after b
   __shared__ unsigned long long sh[CUT_BLOCK];
   uint32_t i = blockIdx.x * CUT_BLOCK + threadIdx.x;
@@ -951,7 +954,53 @@ void launch_cut(const uint32_t* left, uint32_t n, unsigned long long* block_tot,
   if (!n) return;
   uint32_t blocks = (n + CUT_BLOCK - 1) / CUT_BLOCK;
   if (pass == 0) k_cut_block_totals<<<blocks, CUT_BLOCK, 0, s>>>(left, n, block_tot);
-  else k_cut_apply<<<blocks, CUT_BLOCK, 0, s>>>(left, n, block_suffix, budget, take);
+  else k_cut_apply<<<blocks, CUT_BLOCK, 0, s>>>(left, n, block_suffix, budget, nullptr, take);
+}
+// ---- device-driven adaptive rounds (Context::run_adaptive): the state of AdaptiveSamplingStrategy (sampling_strategy.rs:77-220)
+// lives on the device, the host only enqueues steps. st[0..2] error stats, [3] total of the round being opened, [4] samples left
+// in the current round, [5] ticks used by this call, [6] the call's budget, [7] first queue issued, [8] ticks this step takes,
+// [9] mode of this step, [10] steps that rendered, [11] room left in the budget.
+__global__ void k_ad_setup(unsigned long long* st, unsigned long long budget) { st[5] = 0; st[6] = budget; st[10] = 0; }
+__global__ void k_ad_begin(unsigned long long* st) {
+  unsigned long long mode;
+  if (st[5] >= st[6]) mode = AD_IDLE;                    // budget spent: the remaining enqueued steps do nothing
+  else if (st[4] != 0) mode = AD_CONT;                   // a round cut by an earlier budget continues
+  else if (!st[7]) { mode = AD_FIRST; st[7] = 1; }       // first queue: 4 samples per pixel (sampling_strategy.rs:197-203)
+  else { mode = AD_ERR; st[0] = 0; st[1] = 0x7F800000ull; st[2] = 0; }
+  st[3] = 0; st[9] = mode;
+}
+__global__ void k_ad_first(unsigned long long* st, uint32_t* round_left, uint32_t* round_spp, uint32_t n) {
+  if (st[9] != AD_FIRST) return;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { round_left[i] = 4u; round_spp[i] = 4u; }
+  if (i == 0) st[3] = 4ull * n;
+}
+__global__ void k_ad_total(unsigned long long* st) {
+  if (st[9] == AD_FIRST || st[9] == AD_ERR) st[4] = st[3];
+  const unsigned long long room = st[9] == AD_IDLE ? 0ull : st[6] - st[5];
+  st[11] = room;
+  st[8] = st[4] < room ? st[4] : room;
+}
+__global__ void k_ad_end(unsigned long long* st) {
+  const unsigned long long taken = st[8];
+  st[4] -= taken; st[5] += taken;
+  if (taken) st[10] += 1;
+}
+__global__ void k_cut_suffix(const unsigned long long* __restrict__ block_tot, uint32_t blocks, unsigned long long* block_suffix) {
+  unsigned long long run = 0;   // block_suffix[b] = samples queued in the blocks after b (a few thousand entries: one thread)
+  for (uint32_t b = blocks; b-- > 0;) { block_suffix[b] = run; run += block_tot[b]; }
+}
+void launch_ad_setup(unsigned long long* st, unsigned long long budget, cudaStream_t s) { k_ad_setup<<<1, 1, 0, s>>>(st, budget); }
+void launch_ad_begin(unsigned long long* st, cudaStream_t s) { k_ad_begin<<<1, 1, 0, s>>>(st); }
+void launch_ad_first(unsigned long long* st, uint32_t* round_left, uint32_t* round_spp, uint32_t n, cudaStream_t s) { if (n) k_ad_first<<<(n + 255) / 256, 256, 0, s>>>(st, round_left, round_spp, n); }
+void launch_ad_total(unsigned long long* st, cudaStream_t s) { k_ad_total<<<1, 1, 0, s>>>(st); }
+void launch_ad_end(unsigned long long* st, cudaStream_t s) { k_ad_end<<<1, 1, 0, s>>>(st); }
+void launch_cut_device(const uint32_t* left, uint32_t n, unsigned long long* block_tot, unsigned long long* block_suffix, const unsigned long long* room_dev, uint32_t* take, cudaStream_t s) {
+  if (!n) return;
+  uint32_t blocks = (n + CUT_BLOCK - 1) / CUT_BLOCK;
+  k_cut_block_totals<<<blocks, CUT_BLOCK, 0, s>>>(left, n, block_tot);
+  k_cut_suffix<<<1, 1, 0, s>>>(block_tot, blocks, block_suffix);
+  k_cut_apply<<<blocks, CUT_BLOCK, 0, s>>>(left, n, block_suffix, 0ull, room_dev, take);
 }
 // slot spp from the region-indexed take[]; round_left -= take for this session's rows only is
 // done by the caller on the region array (all ranks hold the same region arrays)

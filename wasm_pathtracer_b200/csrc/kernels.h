@@ -106,8 +106,15 @@ void launch_octree_bins(const float4* loc_w, const uint2* light_shot, uint32_t n
 void launch_octree_cdf(const unsigned long long* fx, float* bins, float* cum, uint32_t num_nodes, uint32_t num_lights, cudaStream_t s);
 void launch_photon_sample_batch(const DPhotonTree& t, const float* pts, const uint32_t* seeds, uint64_t n, uint32_t* light, float* pdf, cudaStream_t s);
 // adaptive / random strategies
-void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, cudaStream_t s);
-void launch_adaptive_spp(const float* mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, cudaStream_t s);
+enum : unsigned long long { AD_IDLE = 0, AD_FIRST = 1, AD_ERR = 2, AD_CONT = 3 };   // mode of a device-driven adaptive step
+void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, const unsigned long long* gate, cudaStream_t s);
+void launch_ad_setup(unsigned long long* st, unsigned long long budget, cudaStream_t s);
+void launch_ad_begin(unsigned long long* st, cudaStream_t s);
+void launch_ad_first(unsigned long long* st, uint32_t* round_left, uint32_t* round_spp, uint32_t n, cudaStream_t s);
+void launch_ad_total(unsigned long long* st, cudaStream_t s);
+void launch_ad_end(unsigned long long* st, cudaStream_t s);
+void launch_cut_device(const uint32_t* left, uint32_t n, unsigned long long* block_tot, unsigned long long* block_suffix, const unsigned long long* room_dev, uint32_t* take, cudaStream_t s);
+void launch_adaptive_spp(const float* mse, uint32_t n, unsigned long long* stats, uint32_t* round_left, uint32_t* round_spp, uint8_t* sampling_rgba8, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, const unsigned long long* gate, cudaStream_t s);
 void launch_fill_region_rgba(uint8_t* rgba, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t value, cudaStream_t s);
 void launch_fill_u32(uint32_t* a, uint32_t n, uint32_t v, cudaStream_t s);
 void launch_sum_u32(const uint32_t* a, uint32_t n, unsigned long long* out, cudaStream_t s);

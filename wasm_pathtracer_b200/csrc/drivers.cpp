@@ -311,7 +311,11 @@ uint64_t Context::run_adaptive(Strategy& s, uint32_t render_type, uint64_t budge
   static const int chunk = std::getenv("WPT_AD_CHUNK") ? std::max(1, std::atoi(std::getenv("WPT_AD_CHUNK"))) : 4;
   uint64_t used = 0, steps = 0;
   while (used < budget) {
-    for (int k = 0; k < chunk; k++) {
+    // steps to enqueue before the next read-back: at most `chunk`, and not more than the budget left is expected to need at the
+    // pace of the steps so far (a step past the end of the budget is harmless but costs its launches and, on several GPUs, an all-gather)
+    int todo = chunk;
+    if (steps && used) todo = (int)std::min<uint64_t>((uint64_t)chunk, std::max<uint64_t>(1, ((budget - used) * steps + used - 1) / used));
+    for (int k = 0; k < todo; k++) {
       ev_mark(2, true);
       launch_ad_begin(st, stream);
       launch_ad_first(st, s.round_left.p, s.round_spp.p, N, stream);

@@ -372,6 +372,9 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   }
   P.work_counter = w_work.p; P.counters = w_counters.p;
   WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
+#ifdef MEGA_INSTR
+  { static const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull}; WPT_CUDA(cudaMemcpyAsync(w_counters.p + 9, init, sizeof init, cudaMemcpyHostToDevice, stream)); }
+#endif
   cudaEvent_t a = nullptr, b = nullptr;
   if (profiling) { a = ev_get(); b = ev_get(); WPT_CUDA(cudaEventRecord(a, stream)); }
   static const int env_hi = std::getenv("WPT_MEGA_THI") ? std::atoi(std::getenv("WPT_MEGA_THI")) : 20;

@@ -320,6 +320,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   uint32_t slot_id = 0;
 #ifdef MEGA_INSTR
   unsigned long long i_lp = 0, i_ll = 0, i_ts = 0, i_tl = 0, i_sh = 0;   // logic passes, logic lanes, trav steps, trav lanes, shade lanes
+  unsigned long long t_start, t_empty = 0;   // %globaltimer (ns): launch timeline = first start .. first "queue empty" .. last exit (scripts/tail_probe.py)
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 #endif
 
   const uint32_t nslots = P.nslots_dev ? *P.nslots_dev : P.nslots;
@@ -336,6 +338,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         base = __shfl_sync(FULL, base, 0);
         if (chunk_next >= chunk_end) { chunk_next = base; chunk_end = min(base + P.chunk, nslots); if (base >= nslots) { chunk_end = chunk_next = nslots; queue_empty = true; } }
         else { spare_next = base; spare_end = min(base + P.chunk, nslots); if (base >= nslots) { spare_next = spare_end = nslots; queue_empty = true; } }
+#ifdef MEGA_INSTR
+        if (queue_empty && !t_empty) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_empty));
+#endif
       }
       if (phase == PH_NEED) {
         uint32_t r = (uint32_t)__popc(need & ((1u << lane) - 1u));
@@ -478,6 +483,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 #ifdef MEGA_INSTR
   if (lane == 0) { atomicAdd(&P.counters[4], i_lp); atomicAdd(&P.counters[5], i_ll); atomicAdd(&P.counters[6], i_ts); atomicAdd(&P.counters[7], i_tl); }
   if (lane == 1) atomicAdd(&P.counters[8], i_sh);
+  if (lane == 2) {
+    unsigned long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    atomicMin(&P.counters[9], t_start); if (t_empty) atomicMin(&P.counters[10], t_empty); atomicMax(&P.counters[11], t_end);
+    atomicAdd(&P.counters[12], t_end - t_start);   // sum over warps of their lifetimes
+  }
 #endif
 }
 // Register budgets (blocks of 128 threads per SM) instantiated per variant: the measured optimum (gpurun_out/sweep8.log,

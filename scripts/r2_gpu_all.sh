@@ -8,3 +8,5 @@ timeout -k 10 300 bash scripts/r2_gpu_b.sh > $O/r2_perf_b.log 2>&1
 timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-target > $O/r2_ncu_launch.log 2>&1
 timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_mega -s 3 -c 1 -o $O/r2_mega_bench -f python bench.py --steps 1 --warmup 3 --no-cpu --no-target > $O/r2_ncu_full.log 2>&1
 timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_mega -s 1 -c 1 -o $O/r2_mega_museum -f python scripts/time_step.py 8 1 2 1 0 0 > $O/r2_ncu_museum.log 2>&1
+timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_mega -s 1 -c 1 -o $O/r2_mega_bvh4_pnee -f python scripts/time_step.py 16 1 4 2 0 > $O/r2_ncu_pnee.log 2>&1
+timeout -k 10 1200 bash scripts/sanitize.sh > $O/r2_sanitizer.log 2>&1

@@ -373,6 +373,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   P.work_counter = w_work.p; P.counters = w_counters.p;
   WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
 #ifdef MEGA_INSTR
+  d_dbg.alloc(128); WPT_CUDA(cudaMemsetAsync(d_dbg.p, 0, 128 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p;
   { static const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull}; WPT_CUDA(cudaMemcpyAsync(w_counters.p + 9, init, sizeof init, cudaMemcpyHostToDevice, stream)); }
 #endif
   cudaEvent_t a = nullptr, b = nullptr;
@@ -488,6 +489,13 @@ void Context::stats(uint64_t out[8]) {
     std::fprintf(stderr, "wpt counters:");
     for (int i = 0; i < 16; i++) std::fprintf(stderr, " %llu", h_counters[i]);
     std::fprintf(stderr, "\n");
+    if (d_dbg.p) {   // -DMEGA_INSTR: paths finished per 0.25 ms of the last launch (x 32)
+      unsigned long long h[128];
+      WPT_CUDA(cudaMemcpy(h, d_dbg.p, sizeof h, cudaMemcpyDeviceToHost));
+      std::fprintf(stderr, "wpt paths per 0.25 ms:");
+      for (int i = 0; i < 100; i++) std::fprintf(stderr, " %llu", h[i] * 32ull);
+      std::fprintf(stderr, "\n");
+    }
   }
   out[0] = h_counters[0] + photon_rays; out[1] = h_counters[2]; out[2] = h_counters[1] + photon_visits;
   out[3] = photons_shot_total; out[4] = photons_stored_total; out[5] = iterations; out[6] = launches; out[7] = 0;

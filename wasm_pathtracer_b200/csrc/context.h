@@ -152,6 +152,7 @@ struct Context {
   void reduce_native(uint32_t* dev_words, uint64_t n);
   std::function<void(uint32_t*, uint64_t)> reduce_hook;   // multi-GPU: in-place sum-allreduce of 32-bit words on `stream` (photon batches)
   DevBuf<float4> d_seg_buf;    // k_wpool / k_mega: segment sums of a multi-segment launch (contract B10)
+  DevBuf<unsigned long long> d_dbg;   // -DMEGA_INSTR diagnostics
   DevBuf<float4> d_pool;       // k_wpool: path contexts, 160 B each, pool_ctx per warp
   DevBuf<uint32_t> d_seg_cnt, d_seg_off, d_seg_list, d_pass_spp; DevBuf<uint8_t> d_scan_tmp;   // strategy rounds: segment list (contract B10)
   DevBuf<float4> d_seg_acc;    // wavefront engine: the running segment, per pixel

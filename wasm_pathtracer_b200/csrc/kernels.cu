@@ -449,6 +449,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           else finish = true;
         }
         if (finish) { acc_rgb = acc_rgb + ps.color; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
+#ifdef MEGA_INSTR
+        if (finish && lane == 0 && P.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); unsigned long long bkt = (t - t_start) / 250000ull; atomicAdd(&P.dbg[bkt < 99 ? bkt : 99], 1ull); }
+#endif
       }
       n_paths += (uint32_t)__popc(__ballot_sync(FULL, finish));
       if (phase == PH_LOGIC && what == ST_GEN) {

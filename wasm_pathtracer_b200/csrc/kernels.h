@@ -70,6 +70,7 @@ struct MegaParams {
   uint32_t seed_path;             // mix32(STREAM_PATH ^ base_seed): the constant part of a path's stream seed
   uint32_t* work_counter;         // zeroed before the launch
   unsigned long long* counters;
+  unsigned long long* dbg;        // -DMEGA_INSTR: [0..99] paths finished per 0.25 ms of the launch (one lane in 32 sampled)
 };
 void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s);   // per kernel variant, see kernels.cu
 // Warp-pool path kernel (k_wpool, wpool.cu): a warp owns a pool of path contexts and alternates between logic runs and traversal bursts.

@@ -13,7 +13,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+LIB_PATH = os.environ.get("WPT_ORACLE_LIBRARY") or os.path.join(ORACLE_DIR, "liboracle.so")   # override: a sanitizer build (profiles/r2_checks.md)
 
 SCENE_MUSEUM, SCENE_BUNNY = 0, 2
 SCENE_EXT_WHITTED = 256                         # extension scene
@@ -26,6 +26,8 @@ CAM_BUNNY = (-0.9, 5.4, 0.4, 0.58, 0.0)         # src_ts/client/index.ts:158
 
 def build_oracle(force=False):
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".h", ".cpp", "Makefile"))]
+    if os.environ.get("WPT_ORACLE_LIBRARY"):
+        return LIB_PATH
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"], stdout=sys.stderr)
     return LIB_PATH

@@ -11,6 +11,12 @@ namespace wpt {
 #define WPT_DEV __device__ __forceinline__
 #define WPT_STACK 64          // (node, entry distance) entries; host checks BVH depth against it
 #define WPT_INF CUDART_INF_F
+// -DWPT_CHECKED: device-side bounds checks that trap (compute-sanitizer is closed on the pool; profiles/r2_checks.md)
+#ifdef WPT_CHECKED
+#define WPT_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define WPT_CHECK(cond) do { } while (0)
+#endif
 // kernel variants by scene content: triangles + planes only / the reference's primitives and materials (+ torus, box) /
 // everything incl. the extension (sphere, square, textures, reflect / refract — DESIGN.md 9)
 enum : int { K_SIMPLE = 0, K_REF = 1, K_EXT = 2 };
@@ -568,6 +574,7 @@ struct GHit { float t; int id; uint32_t visits; uint32_t prims; };
 template <int KIND>
 WPT_DEV void leaf_scan(const DScene& sc, uint32_t first, uint32_t count, const Ray& ray, float& bound, int& best_id, uint32_t& prims) {
   prims += count;
+  WPT_CHECK(first + count <= sc.num_shapes);
   bool have = false; float bt = 0.0f; uint32_t bi = 0;
   for (uint32_t i = 0; i < count; i++) {
     float t;
@@ -702,7 +709,7 @@ WPT_DEV bool trav_inner(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* st
 #pragma unroll
     for (int i = 3; i >= 0; i--)
       if ((uint32_t)i < nc && d[i] >= 0.0f && !(d[i] > tv.bound)) {
-        if (have) { stack_n[tv.sp] = (uint32_t)pend_id; stack_d[tv.sp] = pend_d; tv.sp++; }
+        if (have) { WPT_CHECK(tv.sp < WPT_STACK); stack_n[tv.sp] = (uint32_t)pend_id; stack_d[tv.sp] = pend_d; tv.sp++; }
         pend_id = id[i]; pend_d = d[i]; have = true;
       }
     if (have) { tv.lf = (uint32_t)pend_id; return false; }
@@ -721,7 +728,7 @@ WPT_DEV bool trav_inner(const DScene& sc, const Ray& ray, Trav& tv, uint32_t* st
   tv.visits += hl ? 1u : 2u;
   const bool lfirst = dl < dr;
   const bool go_left = hl && (!hr || lfirst);
-  if (hl && hr) { stack_n[tv.sp] = lfirst ? tv.lf + 1 : tv.lf; stack_d[tv.sp] = lfirst ? dr : dl; tv.sp++; }
+  if (hl && hr) { WPT_CHECK(tv.sp < WPT_STACK); stack_n[tv.sp] = lfirst ? tv.lf + 1 : tv.lf; stack_d[tv.sp] = lfirst ? dr : dl; tv.sp++; }
   tv.lf = __float_as_uint(go_left ? lb.z : qb.z); tv.cnt = __float_as_uint(go_left ? lb.w : qb.w);
   return !(hl || hr);
 }

@@ -116,6 +116,8 @@ WPT_DEV void photon_sample_inl(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* l
     else n8[k] = tree_walk(t, depth, f3(bx ? X1 : v.x, by ? Y1 : v.y, bz ? Z1 : v.z));
   }
   // EmpiricalPDF::sample (empirical_pdf.rs:43-61) on the sampled cell
+#pragma unroll
+  for (int k = 0; k < 8; k++) WPT_CHECK(n8[k] < t.num_nodes);
   uint32_t sel = (self_x ? 0u : 1u) + (self_y ? 0u : 2u) + (self_z ? 0u : 4u);
   uint32_t sn = n8[0];
 #pragma unroll
@@ -150,6 +152,7 @@ static __device__ __noinline__ void photon_sample(const DPhotonTree& t, Rng& rng
 
 // Triangle::pick_random (triangle.rs:91-114) on light `li`
 WPT_DEV void pick_random(const DScene& sc, uint32_t li, Rng& rng, F3* p, F3* n, F3* intensity, float* area, uint32_t* shape_id) {
+  WPT_CHECK(li < sc.num_lights);
   float4 na = __ldg(&sc.lights[li].n_area), in = __ldg(&sc.lights[li].intensity);
   uint32_t sid = __float_as_uint(in.w);
   const float4* q = reinterpret_cast<const float4*>(sc.shapes + sid);
@@ -184,6 +187,7 @@ WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_h
   out.finished = false; out.survive = false; out.shadow = false;
   bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
   bool entering = true; float2 uv = make_float2(0.0f, 0.0f);
+  WPT_CHECK(id < (int)rp.scene.num_shapes);
   if (id >= 0) {   // scene.rs:140
     if (KIND == K_SIMPLE) { shape_hit_normal_tri_plane(rp.scene.shapes, (uint32_t)id, ray, &n, &mat); t = t_hit; some = true; }
     else some = shape_trace_full<KIND>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat, &entering, &uv);

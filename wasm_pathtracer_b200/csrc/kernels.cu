@@ -353,7 +353,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           if (P.seg_list) { uint32_t e = P.seg_list[idx]; pslot = e >> 3; j = e & 7u; }   // strategy round: (pixel slot, segment) from the list
           else if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
           slot_id = idx;
+          WPT_CHECK(idx < nslots);
           const uint32_t pix = P.pixel[pslot];
+          WPT_CHECK(pix < P.rp.W * P.rp.H);
           const uint32_t py = pix / P.rp.W;   // once per slot, not per sample
           pixp = (pix - py * P.rp.W) | (py << 16);
           uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;

@@ -378,18 +378,23 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
 #endif
   cudaEvent_t a = nullptr, b = nullptr;
   if (profiling) { a = ev_get(); b = ev_get(); WPT_CUDA(cudaEventRecord(a, stream)); }
-  static const int env_hi = std::getenv("WPT_MEGA_THI") ? std::atoi(std::getenv("WPT_MEGA_THI")) : 20;
-  static const int env_lo = std::getenv("WPT_MEGA_TLO") ? std::atoi(std::getenv("WPT_MEGA_TLO")) : 10;
+  // burst thresholds: 20 / 10 for the triangles + planes variant; 12 / 4 for scenes with tori, where parked lanes (torus phase) thin the
+  // bursts out (museum 8-spp frame: 20/10 36.4 ms, 12/4 34.1 ms, gpurun_out/r2f_museum.log); 0 = not set
+  static const int env_hi = std::getenv("WPT_MEGA_THI") ? std::atoi(std::getenv("WPT_MEGA_THI")) : 0;
+  static const int env_lo = std::getenv("WPT_MEGA_TLO") ? std::atoi(std::getenv("WPT_MEGA_TLO")) : 0;
   // blocks per SM (= register budget) of the four kernel variants: triangles/planes BVH2, BVH4, generic BVH2, BVH4
-  // (measured, gpurun_out/sweep8.log, sweep11.log: the generic variant wants every warp it can get although it spills heavily at 32 registers
-  //  (museum, 8-spp frame: 4 blocks/SM 85 ms, 8: 72, 10: 68, 12: 65, 16: 59 — its bound is instruction fetch + latency);
+  // (measured: with the f64 torus solver inlined at two call sites the generic variant wanted every warp it could get — museum, 8-spp frame:
+  //  4 blocks/SM 85 ms, 8: 72, 12: 65, 16: 59 ms; with the deferred torus phase (one call site, run for many parked lanes at once) it is
+  //  8: 35.8, 16: 38.3 ms, gpurun_out/r2f_museum.log;
   //  triangles/planes BVH2 8 or 9, 10 is worse; BVH4 5, or 8 with PNEE)
   static const int env_minb_base[4] = {std::getenv("WPT_MEGA_MINB") ? std::atoi(std::getenv("WPT_MEGA_MINB")) : 8, std::getenv("WPT_MEGA_MINB4") ? std::atoi(std::getenv("WPT_MEGA_MINB4")) : 0,
-                                       std::getenv("WPT_MEGA_MINBG") ? std::atoi(std::getenv("WPT_MEGA_MINBG")) : 16, std::getenv("WPT_MEGA_MINBG4") ? std::atoi(std::getenv("WPT_MEGA_MINBG4")) : 16};
+                                       std::getenv("WPT_MEGA_MINBG") ? std::atoi(std::getenv("WPT_MEGA_MINBG")) : 8, std::getenv("WPT_MEGA_MINBG4") ? std::atoi(std::getenv("WPT_MEGA_MINBG4")) : 16};
   int env_minb[4] = {env_minb_base[0], env_minb_base[1] ? env_minb_base[1] : (render_type == WPT_PNEE ? 8 : 5), env_minb_base[2], env_minb_base[3]};
   static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 2;
   static const int env_reps = std::getenv("WPT_MEGA_REPS") ? std::atoi(std::getenv("WPT_MEGA_REPS")) : 4;   // measured: 1 -> 20.0, 2 -> 19.3, 4 -> 18.8, 8 -> 19.5 ms (gpurun_out/sweep10*.log)
-  P.t_hi = (uint32_t)env_hi; P.t_lo = (uint32_t)env_lo; P.t_inner = (uint32_t)env_ti; P.inner_reps = (uint32_t)std::max(1, env_reps);
+  P.t_hi = (uint32_t)(env_hi ? env_hi : 20); P.t_lo = (uint32_t)(env_lo ? env_lo : 10); P.t_inner = (uint32_t)env_ti; P.inner_reps = (uint32_t)std::max(1, env_reps);
+  static const int env_ttor = std::getenv("WPT_MEGA_TTORUS") ? std::atoi(std::getenv("WPT_MEGA_TTORUS")) : 10;   // measured: 4 39.1, 8 36.4, 10 35.8, 12 35.9 ms (museum, 8 blocks / SM)
+  P.t_torus = (uint32_t)std::max(1, env_ttor);
   static const int env_chunk = std::getenv("WPT_MEGA_CHUNK") ? std::atoi(std::getenv("WPT_MEGA_CHUNK")) : 32;
   P.chunk = (uint32_t)env_chunk;
   // kernel variant by scene content: triangles + planes only / the reference's primitives and materials / everything
@@ -400,6 +405,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   }
   for (const HostMaterial& m : scene.mats) if (m.kind != MAT_DIFFUSE && m.kind != MAT_EMISSIVE) { P.scene_kind = 2; break; }
   if (std::getenv("WPT_NO_SIMPLE")) P.scene_kind = 2;
+  if (P.scene_kind != 0) { if (!env_hi) P.t_hi = 12; if (!env_lo) P.t_lo = 4; }
   {
     // the infinite shapes are planes (only a Plane has no finite box, bvh.rs:376-394), at most two in the reference's
     // scenes: they and the BVH2 root node travel in the kernel parameters (constant bank)

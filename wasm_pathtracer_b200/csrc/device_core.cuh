@@ -413,10 +413,10 @@ WPT_DEV bool square_t(float4 q0, float4 q1, const Ray& ray, float* t_out, float*
 // Tracable::trace_simple for shape record `s`. `limit`/`strict` implement the acceptance test
 // of trace_shapes_md (scene.rs:450-472): the first candidate needs t <= max_dis, later ones
 // 0 < t < best. Rejecting on t before the edge tests does not change any result.
-template <int KIND>
-WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float limit, bool strict, float* t_out) {
-  const float4* p = reinterpret_cast<const float4*>(shapes + idx);
-  float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+// (q0, q1 = the first two words of the record at p, already loaded; TORUS = false leaves the torus branch out: the caller
+// handles tori itself — k_mega's deferred solver phase)
+template <int KIND, bool TORUS>
+WPT_DEV bool shape_trace_simple_q(const float4* __restrict__ p, float4 q0, float4 q1, const Ray& ray, float limit, bool strict, float* t_out) {
   uint32_t type = __float_as_uint(q0.w) & 0xFFu;
   if (type == SH_TRIANGLE) {   // triangle.rs:159-191
     float4 q2 = __ldg(p + 2), q3 = __ldg(p + 3);
@@ -460,18 +460,28 @@ WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx,
   } else if (KIND == K_EXT && type == SH_SQUARE) {   // ray.rs:110-116 default = trace().distance
     float u, v;
     if (!square_t(q0, q1, ray, &t, &u, &v)) return false;
-  } else {                     // torus: ray.rs:110-116 default = trace().distance
+  } else if (TORUS) {          // torus: ray.rs:110-116 default = trace().distance
     if (!torus_may_hit(q0, q1, ray) || !torus_trace(q0, q1, ray, &t, nullptr)) return false;
-  }
+  } else return false;
   if (strict ? !(0.0f < t && t < limit) : !(t <= limit)) return false;
   *t_out = t;
   return true;
 }
+template <int KIND>
+WPT_DEV bool shape_trace_simple(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float limit, bool strict, float* t_out) {
+  const float4* p = reinterpret_cast<const float4*>(shapes + idx);
+  float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+  return shape_trace_simple_q<KIND, true>(p, q0, q1, ray, limit, strict, t_out);
+}
 
 // Tracable::trace for the winning shape (scene.rs:140): distance, Hit::new-normalised normal,
 // material index. Returns false if the full intersection reports no hit.
-template <int KIND>
-WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float* t_out, F3* n_out, uint32_t* mat_out, bool* entering_out = nullptr, float2* uv_out = nullptr) {
+// PRE (k_mega with the torus phase): a torus winner's distance / normal / is_entering were computed by trav_torus (t_pre, pre).
+struct TorusPre { F3 n; bool entering; };
+WPT_DEV void torus_pre_get(const TorusPre* pre, F3* n, bool* entering) { *n = pre->n; *entering = pre->entering; }
+template <int KIND, bool PRE = false>
+WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, const Ray& ray, float* t_out, F3* n_out, uint32_t* mat_out, bool* entering_out = nullptr, float2* uv_out = nullptr,
+                              float t_pre = 0.0f, const TorusPre* pre = nullptr) {
   const float4* p = reinterpret_cast<const float4*>(shapes + idx);
   float4 q0 = __ldg(p), q1 = __ldg(p + 1);
   uint32_t meta = __float_as_uint(q0.w);
@@ -531,6 +541,8 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
     if (!square_t(q0, q1, ray, &t, &u, &v)) return false;
     n = ray.d.y > 0.0f ? f3(0, -1, 0) : f3(0, 1, 0);
     if (uv_out) *uv_out = make_float2(u, v);
+  } else if (PRE) {
+    torus_pre_get(pre, &n, &entering); t = t_pre;
   } else {
     if (!torus_may_hit(q0, q1, ray) || !torus_trace(q0, q1, ray, &t, &n, &entering)) return false;
   }
@@ -600,6 +612,7 @@ struct Trav {
   int best_id;           // best BVH hit (-1: none)
   float inf_t; int inf_id;   // hit among the infinite shapes (scene.rs:168,176)
   uint32_t visits, prims;
+  uint32_t lcur;         // k_mega with the deferred torus phase: leaf-scan state, cursor | have << 8 | resumed << 9 (0 = not inside a leaf)
 };
 
 // scene.rs:346-388 — the exact compare-and-swap network (not stable for n == 4)
@@ -641,7 +654,7 @@ WPT_DEV bool trav_begin(const DScene& sc, const Ray& ray, Trav& tv) {
   tv.inf_t = it; tv.inf_id = iid;
   tv.bound = have ? it : WPT_INF;
   tv.best_id = -1;
-  tv.visits = 0; tv.prims = 0; tv.sp = 0;
+  tv.visits = 0; tv.prims = 0; tv.sp = 0; tv.lcur = 0u;
   if (BVH == 4) { tv.lf = 0u; tv.cnt = 0u; return true; }   // no root box test (scene.rs:292-342)
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes2);
   float4 ra = __ldg(nodes), rb = __ldg(nodes + 1);
@@ -738,6 +751,70 @@ WPT_DEV void trav_leaf(const DScene& sc, const Ray& ray, Trav& tv) {
   tv.visits += 1;
   if (BVH == 4) { uint32_t code = tv.lf; leaf_scan<KIND>(sc, sc.num_inf + (code & 0x7FFFFFFu), (code >> 27) & 0xFu, ray, tv.bound, tv.best_id, tv.prims); }
   else leaf_scan<KIND>(sc, sc.num_inf + tv.lf, tv.cnt, ray, tv.bound, tv.best_id, tv.prims);
+}
+// Resumable leaf scan for scenes with tori (k_mega's deferred solver phase): the same ordered scan as leaf_scan — the first
+// accepted candidate of the leaf needs t <= bound, later ones 0 < t < best (scene.rs:450-472); writing an accepted candidate
+// to (bound, best_id) at once is the same as leaf_scan's (bt, bi) + final copy — but a torus that passes the conservative cull
+// stops the scan: the lane parks with its cursor in tv.lcur and returns true; trav_torus resolves it and the scan goes on.
+enum : uint32_t { LC_HAVE = 1u << 8, LC_RESUMED = 1u << 9,   // state of the leaf scan in progress (cleared at the end of the leaf)
+                  LC_BEST_TORUS = 1u << 10,                  // the best BVH hit so far is a torus (lives until the next trav_begin)
+                  LC_SHADE = 1u << 11, LC_NREADY = 1u << 12, LC_ENTERING = 1u << 13 };   // normal of the winning torus: wanted / stored in (lf, cnt, sp) / Hit::is_entering
+template <int BVH>
+WPT_DEV void leaf_range(const DScene& sc, const Trav& tv, uint32_t* first, uint32_t* count) {
+  if (BVH == 4) { *first = sc.num_inf + (tv.lf & 0x7FFFFFFu); *count = (tv.lf >> 27) & 0xFu; }
+  else { *first = sc.num_inf + tv.lf; *count = tv.cnt; }
+}
+template <int BVH, int KIND>
+WPT_DEV bool trav_leaf_deferred(const DScene& sc, const Ray& ray, Trav& tv) {
+  uint32_t first, count; leaf_range<BVH>(sc, tv, &first, &count);
+  const uint32_t st = tv.lcur;
+  uint32_t i = st & 0xFFu; bool have = (st & LC_HAVE) != 0;
+  uint32_t best_torus = st & LC_BEST_TORUS;
+  if (!(st & LC_RESUMED)) { tv.visits += 1; tv.prims += count; WPT_CHECK(first + count <= sc.num_shapes); }
+  for (; i < count; i++) {
+    const float4* p = reinterpret_cast<const float4*>(sc.shapes + first + i);
+    const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+    if ((__float_as_uint(q0.w) & 0xFFu) == SH_TORUS) {
+      if (!torus_may_hit(q0, q1, ray)) continue;
+      tv.lcur = best_torus | i | (have ? LC_HAVE : 0u) | LC_RESUMED;
+      return true;
+    }
+    float t;
+    if (shape_trace_simple_q<KIND, false>(p, q0, q1, ray, tv.bound, have, &t)) { have = true; tv.bound = t; tv.best_id = (int)(first + i); best_torus = 0u; }
+  }
+  tv.lcur = best_torus;
+  return false;
+}
+// The parked lanes of k_mega's torus phase, one solver call site for both kinds:
+//  * leaf mode — the torus trav_leaf_deferred stopped at: Torus::trace (f64 quartic) + the scan's acceptance test, the cursor
+//    moves on. Returns true if the leaf is finished (the lane pops next);
+//  * shade mode (LC_SHADE) — the traversal is over and its winner is a torus: Scene::trace intersects the winner again for the
+//    Hit (scene.rs:140); same ray, same shape, so the same distance — only the normal and is_entering are new. They are kept
+//    in (lf, cnt, sp), which are dead until the next trav_begin, and shade_hit takes them from there (TorusPre). Returns false.
+template <int BVH>
+WPT_DEV bool trav_torus(const DScene& sc, const Ray& ray, Trav& tv) {
+  const bool shade = (tv.lcur & LC_SHADE) != 0;
+  uint32_t first, count; leaf_range<BVH>(sc, tv, &first, &count);
+  const uint32_t i = tv.lcur & 0xFFu; bool have = (tv.lcur & LC_HAVE) != 0;
+  const uint32_t idx = shade ? (uint32_t)tv.best_id : first + i;
+  const float4* p = reinterpret_cast<const float4*>(sc.shapes + idx);
+  const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+  float t; F3 n = f3(0, 0, 0); bool ent = true;
+  const bool hit = torus_trace(q0, q1, ray, &t, shade ? &n : nullptr, &ent);
+  if (shade) {
+    tv.lf = __float_as_uint(n.x); tv.cnt = __float_as_uint(n.y); tv.sp = __float_as_int(n.z);
+    tv.lcur = LC_BEST_TORUS | LC_NREADY | (ent ? LC_ENTERING : 0u);
+    return false;
+  }
+  uint32_t best_torus = tv.lcur & LC_BEST_TORUS;
+  if (hit && (have ? (0.0f < t && t < tv.bound) : (t <= tv.bound))) { have = true; tv.bound = t; tv.best_id = (int)(first + i); best_torus = LC_BEST_TORUS; }
+  if (i + 1u >= count) { tv.lcur = best_torus; return true; }
+  tv.lcur = best_torus | (i + 1u) | (have ? LC_HAVE : 0u) | LC_RESUMED;
+  return false;
+}
+WPT_DEV TorusPre torus_pre(const Trav& tv) {
+  TorusPre r; r.n = f3(__uint_as_float(tv.lf), __uint_as_float(tv.cnt), __int_as_float(tv.sp)); r.entering = (tv.lcur & LC_ENTERING) != 0;
+  return r;
 }
 // true if the node the lane is about to enter is a leaf
 template <int BVH>

@@ -181,8 +181,8 @@ struct ShadeOut {
 // RT: the render type when it is known at compile time (0 NoNEE, 1 NormalNEE, 2 PNEE: k_mega is instantiated per type — no
 // photon code in the NEE kernels, photon_sample inlined in the PNEE kernel: 9 % / 15 % faster than one kernel that branches
 // and calls), 3 = decided at run time (k_shade, k_pool: out-of-line photon_sample)
-template <int KIND, int RT = 3>
-WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_hit, PathRegs& ps, ShadeOut& out) {
+template <int KIND, int RT = 3, bool PRE = false>
+WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_hit, PathRegs& ps, ShadeOut& out, const TorusPre* pre = nullptr) {
   const bool has_nee = RT == 3 ? rp.render_type != 0 : RT != 0;
   out.finished = false; out.survive = false; out.shadow = false;
   bool some = false; float t = 0.0f; F3 n = f3(0, 0, 0); uint32_t mat = 0;
@@ -190,7 +190,7 @@ WPT_DEV void shade_hit(const RenderParams& rp, const Ray& ray, int id, float t_h
   WPT_CHECK(id < (int)rp.scene.num_shapes);
   if (id >= 0) {   // scene.rs:140
     if (KIND == K_SIMPLE) { shape_hit_normal_tri_plane(rp.scene.shapes, (uint32_t)id, ray, &n, &mat); t = t_hit; some = true; }
-    else some = shape_trace_full<KIND>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat, &entering, &uv);
+    else some = shape_trace_full<KIND, PRE>(rp.scene.shapes, (uint32_t)id, ray, &t, &n, &mat, &entering, &uv, t_hit, pre);
   }
   if (!some) {   // tracer.rs:325-328
     ps.color = ps.color + ps.T * f3(rp.scene.bg_r, rp.scene.bg_g, rp.scene.bg_b);

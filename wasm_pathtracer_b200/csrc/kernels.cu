@@ -266,7 +266,7 @@ void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers
 #ifndef MEGA_T_LO
 #define MEGA_T_LO 10
 #endif
-enum : int { PH_NEED = 0, PH_LOGIC = 1, PH_TRAV = 2, PH_DONE = 3 };
+enum : int { PH_NEED = 0, PH_LOGIC = 1, PH_TRAV = 2, PH_DONE = 3, PH_TORUS = 4 };
 enum : int { ST_GEN = 0, ST_EXTEND = 1, ST_SHADOW = 2 };
 
 // Scene::trace_g up to the BVH for the triangles / planes variant (scene.rs:162-212): at most two infinite shapes, all planes
@@ -289,7 +289,7 @@ WPT_DEV bool trav_begin_const(const MegaParams& P, const Ray& ray, Trav& tv) {
   tv.inf_t = it; tv.inf_id = iid;
   tv.bound = have ? it : WPT_INF;
   tv.best_id = -1;
-  tv.visits = 0; tv.prims = 0; tv.sp = 0;
+  tv.visits = 0; tv.prims = 0; tv.sp = 0; tv.lcur = 0u;
   if (BVH == 4) { tv.lf = 0u; tv.cnt = 0u; return true; }
   const float4 ra = P.root_a, rb = P.root_b;
   tv.visits = 1;
@@ -304,12 +304,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
   const unsigned FULL = 0xFFFFFFFFu;
+#ifdef MEGA_NO_DEFER_TORUS
+  constexpr bool DEFER_TORUS = false;
+#else
+  constexpr bool DEFER_TORUS = KIND != K_SIMPLE;   // variants whose scenes can hold tori
+#endif
   const unsigned lane = threadIdx.x & 31u;
   int phase = PH_NEED, what = ST_GEN;
   uint32_t pixp = 0, s = 0, s_end = 0;   // pixp = px | py << 16 of the slot's pixel
   PathRegs ps; ps.color = f3(0, 0, 0); ps.T = f3(1, 1, 1); ps.rng.s = 1u; ps.bounced = false;
   Ray ray = make_ray(f3(0, 0, 0), f3(1, 1, 1));
-  Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0;
+  Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0; tv.lcur = 0u;
   F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
   // ray / visit / primitive-test / path counters: warp sums (ballot + redux.sync) in uniform registers, one set of global
@@ -376,8 +381,25 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         }
       }
     }
+    // a finished bounce / camera ray whose winner is a torus: its normal comes from the torus phase too (shade mode of trav_torus)
+    if (DEFER_TORUS && phase == PH_LOGIC && what == ST_EXTEND && tv.best_id >= 0 && (tv.lcur & (LC_BEST_TORUS | LC_NREADY)) == LC_BEST_TORUS) { phase = PH_TORUS; tv.lcur |= LC_SHADE; }
     unsigned trav = __ballot_sync(FULL, phase == PH_TRAV);
     unsigned logic = __ballot_sync(FULL, phase == PH_LOGIC);
+    if (DEFER_TORUS) {
+      // ---- deferred torus phase (scenes with tori): a lane whose leaf scan meets a torus that passes the conservative cull
+      // parks in PH_TORUS; the f64 quartic (~37 KB of code) runs for all parked lanes of the warp at once, when P.t_torus of
+      // them wait or nothing else is left to do — many lanes per pass and few passes, instead of ~3 lanes whenever a leaf
+      // step happens to meet a torus. Same arithmetic and the same ordered acceptance as leaf_scan.
+      const unsigned tor = __ballot_sync(FULL, phase == PH_TORUS);
+      if (!(trav | logic | tor)) break;
+      if (tor && (__popc(tor) >= (int)P.t_torus || !(trav | logic))) {
+        if (phase == PH_TORUS) {
+          phase = (tv.lcur & LC_SHADE) ? PH_LOGIC : PH_TRAV;
+          if (trav_torus<BVH>(sc, ray, tv) && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
+        }
+        continue;
+      }
+    }
     if (!(trav | logic)) break;
     if (__popc(trav) >= (int)P.t_hi || !logic) {
       // ---- traversal burst, while-while: one step per iteration — an inner-node step while enough of the burst's lanes
@@ -401,7 +423,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
             if (np && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
           }
         } else {
-          if (leaf) { trav_leaf<BVH, KIND>(sc, ray, tv); need_pop = true; }
+          if (leaf) {
+            if (DEFER_TORUS) { if (trav_leaf_deferred<BVH, KIND>(sc, ray, tv)) phase = PH_TORUS; else need_pop = true; }
+            else { trav_leaf<BVH, KIND>(sc, ray, tv); need_pop = true; }
+          }
           if (need_pop && !trav_pop<BVH>(sc, tv, stack_n, stack_d)) phase = PH_LOGIC;
         }
         trav = __ballot_sync(FULL, phase == PH_TRAV);
@@ -441,7 +466,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           else finish = true;
         } else {
           ShadeOut so;
-          shade_hit<KIND, RT>(P.rp, ray, g.id, g.t, ps, so);
+          if (DEFER_TORUS) { const TorusPre pre = torus_pre(tv); shade_hit<KIND, RT, true>(P.rp, ray, g.id, g.t, ps, so, &pre); }
+          else shade_hit<KIND, RT>(P.rp, ray, g.id, g.t, ps, so);
           if (so.finished) finish = true;
           else if (so.shadow) {
             ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;

@@ -59,6 +59,7 @@ struct MegaParams {
   uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
   uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
   uint32_t inner_reps;            // k_mega: inner-node steps per vote inside a burst
+  uint32_t t_torus;               // k_mega: the deferred torus phase runs when this many lanes of the warp are parked at a torus (or nothing else is left)
   uint32_t t_switch;              // k_wpool: a logic run that cannot refill leaves when fewer than this many lanes still hold a context
   uint32_t t_refill;              // k_wpool: idle lanes of a traversal burst refill from the queue when at least this many are idle
   float4* pool;                   // k_wpool: path contexts, [warp][pool_ctx][10 x float4]

@@ -332,6 +332,23 @@ def main():
                    "prims_per_ray": fprof["prim_tests"] / max(1, fprof["rays"])}
         fp.close()
 
+    # ---- museum (rank 0 only): the reference's other scene (BASELINE config 4's: 27 tori with the f64 quartic, 108 emissive
+    # triangles, 10 boxes) at 1080p, 8 spp, NormalNEE — the kernel variant with the deferred torus phase
+    museum = None
+    if rank == 0 and not args.no_target:
+        mp = W.PathTracer(W_, H_, W.SCENE_MUSEUM, *W.CAM_MUSEUM, device=local)
+        mp.set_config(bvh_kind=2, render_type=W.NORMAL_NEE, engine=args.engine)
+        mp.render_exact(8); mp.synchronize()
+        mp.profile(True)
+        for _ in range(3):
+            mp.reset(); mp.render_exact(8)
+        mprof = mp.profile_read(); mp.profile(False)
+        mms = mprof["trace_ms"] / 3
+        museum = {"config": "museum scene (tori: f64 quartic, boxes, 108 area lights), BVH2, 1920x1080, 8 spp, NormalNEE",
+                  "ms_per_frame": mms, "mrays_per_s": mprof["rays"] / 3 / (mms * 1e-3) / 1e6, "rays_per_frame": mprof["rays"] / 3,
+                  "visits_per_ray": mprof["node_visits"] / max(1, mprof["rays"]), "prims_per_ray": mprof["prim_tests"] / max(1, mprof["rays"])}
+        mp.close()
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         # Algorithmic bytes of the dominant kernel, SURVEY.md 8(d): per ray
@@ -370,7 +387,7 @@ def main():
                 "mpaths_per_s": mpaths, "rays_per_step": rays_all, "paths_per_step": paths_all, "node_visits_per_s": visits_all / (ms_step * 1e-3),
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
-                "gpu_launches": int(launches_step) * args.steps, "clocks": clocks, "target": target, "mesh_filling": filling}
+                "gpu_launches": int(launches_step) * args.steps, "clocks": clocks, "target": target, "mesh_filling": filling, "museum": museum}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             tr = tp_ = 0

@@ -3,6 +3,7 @@
 // fails.
 #include "context.h"
 #include <algorithm>
+#include <string>
 #include <cstring>
 #include <cmath>
 #include <cstdio>
@@ -137,6 +138,7 @@ void Context::select_scene(uint32_t id) {
 }
 
 void Context::upload_scene() {
+  scene_version++;
   if (!has_device) return;
   std::vector<DNode2> n2; std::vector<DNode4> n4; std::vector<DShape> shp; std::vector<DMaterial> mats; std::vector<DLight> lights;
   flatten_scene(scene, n2, n4, shp, mats, lights);
@@ -258,14 +260,34 @@ void Context::ensure_slots(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh) {
   require_device();
   uint32_t world = cfg.world ? cfg.world : 1, rank = cfg.rank;
   uint32_t key[6] = {rx, ry, rw, rh, rank, world};
-  if (slots && !std::memcmp(key, slot_region, sizeof key)) return;
+  // the slot order depends on what the camera sees (launch_order_tiles): rebuilt when the camera, the scene or the BVH kind change
+  // (off unless WPT_TILE_ORDER=1: measured -1.7 % on the bunny frame, +9 % on the indoor museum — gpurun_out/r2h_ab.log, r2h_zone.log)
+  static const bool order_tiles = std::getenv("WPT_TILE_ORDER") && std::atoi(std::getenv("WPT_TILE_ORDER")) != 0;
+  const uint64_t view = order_tiles ? view_key() : 0;
+  if (slots && !std::memcmp(key, slot_region, sizeof key) && view == slot_view) return;
   uint32_t rows = band_rows(rh, rank, world);
   uint32_t n = rows * rw;
   s_pixel.alloc(n); s_spp.alloc(n);
   if (use_wavefront()) ensure_wavefront_state(n);   // ~140 B per slot that the persistent kernels never touch
   launch_fill_pixels(s_pixel.p, W, rx, ry, rw, rh, rank, world, stream);
+  const uint32_t ntiles = ((rw & ~7u) * (rows & ~3u)) >> 5;
+  if (order_tiles && ntiles > 1) {
+    s_pixel_alt.alloc(n); t_key.alloc(ntiles); t_val.alloc(ntiles); t_key2.alloc(ntiles); t_val2.alloc(ntiles);
+    const size_t tb = tile_sort_bytes(ntiles);
+    t_tmp.alloc(tb);
+    launch_order_tiles(params(cfg.render_type), s_pixel.p, n, ntiles, t_key.p, t_val.p, t_key2.p, t_val2.p, t_tmp.p, tb, s_pixel_alt.p, stream);
+    std::swap(s_pixel.p, s_pixel_alt.p); std::swap(s_pixel.n, s_pixel_alt.n);
+    launches += 3;
+  }
   slots = n;
+  slot_view = view;
   std::memcpy(slot_region, key, sizeof key);
+}
+uint64_t Context::view_key() const {   // FNV-1a over the camera, the scene identity and the BVH kind
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+  mix(cam, sizeof cam); mix(&scene_id, sizeof scene_id); mix(&scene_version, sizeof scene_version); mix(&cfg.bvh_kind, sizeof cfg.bvh_kind);
+  return h | 1ull;
 }
 
 void Context::ensure_wavefront_state(uint32_t n) {
@@ -345,6 +367,10 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   if (!slots) return;
   if (render_type == WPT_PNEE && !photons_ready) throw std::runtime_error("photon tree not built");
   MegaParams P{};
+  bool zone_default = false;   // scenes with other primitives than triangles and planes (kernel variants K_REF / K_EXT)
+  for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { zone_default = true; break; }
+  for (int z = 0; z < 3; z++) { P.zone_start[z] = 0xFFFFFFFFu; P.zone_pslot[z] = 0; P.zone_per[z] = 1; P.zone_len[z] = 1; }
+  P.zone_samples = 0; uint32_t zone_first = slots;
   P.rp = params(render_type);
   P.accum = d_accum.p; P.pixel = s_pixel.p; P.spp_per_slot = d_spp_per_slot; P.uniform_spp = uniform_spp;
   // contract B10: render_exact cuts a pixel's samples into segments of WPT_SEGMENT_LEN, each summed from +0 by its
@@ -366,14 +392,51 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
     launches += 3;
   } else {
     P.nseg = std::max(1u, (uniform_spp + seg_len - 1u) / seg_len);
-    if ((uint64_t)slots * P.nseg > 0x7FFFFFFFull) throw std::runtime_error("too many samples per pixel for one render_exact call at this viewport size");
-    P.nslots = slots * P.nseg;
-    if (P.nseg > 1) { d_seg_buf.alloc((size_t)P.nslots); P.seg_buf = d_seg_buf.p; }
+    // End zones: a launch ends when its last slot ends, and a lane needs 25 - 40 us per ray, i.e. ~1 ms for a segment of 8 samples:
+    // when the queue runs dry every lane still holds half a segment on average and the slowest a whole one (scripts/tail_probe.py:
+    // the median warp exits 1.0 ms, the last 2.5 ms after the queue is empty). So the last part of the pixel slots is queued in
+    // shorter slots, graded (WPT_MEGA_ZONES = "percent:samples,..." in queue order, e.g. "15:4,10:2,5:1"): each zone has to last
+    // as long as the slowest slot of the zone before it. Zone slots store one colour per sample and k_combine_segments forms the
+    // segment sums in the same order (same bits).
+    // Measured (gpurun_out/r2h_zone2.log, r2h_tail_zone2.log): "15:4,10:2,5:1" pulls the warp exits together (99 % of the warps within
+    // 0.47 ms of the queue running dry instead of 1.76 ms, the last one after 1.6 instead of 2.6 ms), but every slot fetch stalls its
+    // warp on the atomic + pixel + accumulator loads, so the queue itself lasts longer: bunny frame 16.6 -> 16.8 ms (no gain), museum
+    // 32.5 -> 31.3 ms. Default: on for scenes with tori / boxes, off otherwise.
+    static const char* env_zones_c = std::getenv("WPT_MEGA_ZONES");
+    const std::string env_zones = env_zones_c ? env_zones_c : (zone_default ? "15:4,10:2,5:1" : "");
+    uint32_t zpx[3] = {0, 0, 0}, zlen[3] = {1, 1, 1}; int nz = 0;
+    if (uniform_spp > 1 && cfg.engine == 0) {
+      const char* c = env_zones.c_str();
+      while (*c && nz < 3) {
+        char* e = nullptr; long pct = std::strtol(c, &e, 10); if (e == c || *e != ':') break;
+        c = e + 1; long len = std::strtol(c, &e, 10); if (e == c) break;
+        c = (*e == ',') ? e + 1 : e;
+        if (pct > 0 && len > 0) { zpx[nz] = (uint32_t)((uint64_t)slots * (uint32_t)std::min(100l, pct) / 100u) & ~31u; zlen[nz] = (uint32_t)len; nz++; }
+      }
+    }
+    uint32_t zone_px = zpx[0] + zpx[1] + zpx[2];
+    if (zone_px > slots) { zone_px = 0; nz = 0; }
+    const uint32_t body_px = slots - zone_px;
+    uint64_t total = (uint64_t)body_px * P.nseg;
+    {
+      uint32_t px0 = body_px;
+      for (int z = 0; z < 3; z++) {
+        P.zone_start[z] = 0xFFFFFFFFu; P.zone_pslot[z] = px0; P.zone_len[z] = zlen[z]; P.zone_per[z] = (uniform_spp + zlen[z] - 1u) / zlen[z];
+        if (z < nz && zpx[z]) { P.zone_start[z] = (uint32_t)std::min<uint64_t>(total, 0xFFFFFFFEull); total += (uint64_t)zpx[z] * P.zone_per[z]; px0 += zpx[z]; }
+      }
+    }
+    if (total > 0x7FFFFFFFull) throw std::runtime_error("too many samples per pixel for one render_exact call at this viewport size");
+    P.nslots = (uint32_t)total;
+    zone_first = body_px;
+    P.zone_samples = body_px * P.nseg;
+    const uint64_t buf_n = (uint64_t)body_px * P.nseg + (uint64_t)zone_px * uniform_spp;
+    if (P.nseg > 1 || zone_px) { d_seg_buf.alloc((size_t)buf_n); P.seg_buf = d_seg_buf.p; }
   }
   P.work_counter = w_work.p; P.counters = w_counters.p;
   WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
 #ifdef MEGA_INSTR
-  d_dbg.alloc(128); WPT_CUDA(cudaMemsetAsync(d_dbg.p, 0, 128 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p;
+  const size_t dbg_n = 128 + 3 * (size_t)device_sm_count() * 16 * 4;
+  d_dbg.alloc(dbg_n); WPT_CUDA(cudaMemsetAsync(d_dbg.p, 0, dbg_n * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p;
   { static const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull}; WPT_CUDA(cudaMemcpyAsync(w_counters.p + 9, init, sizeof init, cudaMemcpyHostToDevice, stream)); }
 #endif
   cudaEvent_t a = nullptr, b = nullptr;
@@ -442,7 +505,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());
   if (P.seg_list) { launch_combine_segment_list(d_accum.p, s_pixel.p, slots, d_seg_buf.p, d_seg_off.p, d_spp_per_slot, stream); launches += 1; }
-  else if (P.nseg > 1) { launch_combine_segments(d_accum.p, s_pixel.p, slots, d_seg_buf.p, P.nseg, uniform_spp, stream); launches += 1; }
+  else if (P.seg_buf) { launch_combine_segments(d_accum.p, s_pixel.p, slots, d_seg_buf.p, P.nseg, uniform_spp, zone_first, seg_len, stream); launches += 1; }
   launches += 1; iterations += 1;
   rgba_stale = true;
 }
@@ -501,6 +564,23 @@ void Context::stats(uint64_t out[8]) {
       std::fprintf(stderr, "wpt paths per 0.25 ms:");
       for (int i = 0; i < 100; i++) std::fprintf(stderr, " %llu", h[i] * 32ull);
       std::fprintf(stderr, "\n");
+      // per-warp exit timeline: when did the warps exit relative to the first "queue empty", and what did the last ones hold
+      const size_t nw = (size_t)device_sm_count() * 16 * 4;
+      std::vector<unsigned long long> w(3 * nw);
+      WPT_CUDA(cudaMemcpy(w.data(), d_dbg.p + 128, w.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      struct E { unsigned long long end, empty; uint32_t path, slot; };
+      std::vector<E> ev;
+      unsigned long long first_empty = ~0ull;
+      for (size_t i = 0; i < nw; i++) if (w[3 * i]) { ev.push_back(E{w[3 * i], w[3 * i + 1], (uint32_t)(w[3 * i + 2] >> 32), (uint32_t)w[3 * i + 2]}); if (w[3 * i + 1]) first_empty = std::min(first_empty, w[3 * i + 1]); }
+      std::sort(ev.begin(), ev.end(), [](const E& a, const E& b) { return a.end < b.end; });
+      if (!ev.empty() && first_empty != ~0ull) {
+        std::fprintf(stderr, "wpt warp exits after the first queue-empty (us), percentiles 10/50/90/99/100:");
+        for (double q : {0.10, 0.50, 0.90, 0.99, 1.0}) { const E& e = ev[std::min(ev.size() - 1, (size_t)(q * (ev.size() - 1) + 0.5))]; std::fprintf(stderr, " %.0f", ((double)e.end - (double)first_empty) * 1e-3); }
+        uint32_t mp = 0, ms = 0; for (const E& e : ev) { mp = std::max(mp, e.path); ms = std::max(ms, e.slot); }
+        std::fprintf(stderr, "\nwpt longest path %u rays, longest slot %u rays (whole launch); the last 8 warps to exit (us after queue-empty, own longest path, own longest slot):", mp, ms);
+        for (size_t i = ev.size() >= 8 ? ev.size() - 8 : 0; i < ev.size(); i++) std::fprintf(stderr, " (%.0f, %u, %u)", ((double)ev[i].end - (double)first_empty) * 1e-3, ev[i].path, ev[i].slot);
+        std::fprintf(stderr, "\n");
+      }
     }
   }
   out[0] = h_counters[0] + photon_rays; out[1] = h_counters[2]; out[2] = h_counters[1] + photon_visits;

@@ -84,6 +84,9 @@ struct Context {
   unsigned long long* h_counters = nullptr;   // pinned [8]
   uint32_t slots = 0;                         // slots of the current partition
   uint32_t slot_region[6] = {0, 0, 0, 0, 0, 0};   // region + rank/world the pixel map was built for
+  DevBuf<uint32_t> s_pixel_alt, t_key, t_val, t_key2, t_val2; DevBuf<uint8_t> t_tmp;   // slot order by primary-hit class (launch_order_tiles)
+  uint64_t slot_view = 0, scene_version = 0;   // camera / scene the slot order was computed for; bumped by upload_scene
+  uint64_t view_key() const;
 
   // photons: records (loc.xyz, weight) + (light, shot), octree build scratch, flattened tree
   DevBuf<float4> ph_loc_w;

@@ -14,14 +14,14 @@ WPT_DEV unsigned long long warp_sum_u64(unsigned long long v) {
 }
 
 // tracer.rs:176-191 — camera ray through pixel (x,y) with jitter (j1,j2)
-WPT_DEV Ray camera_ray(const DCamera& c, uint32_t x, uint32_t y, float j1, float j2) {
+WPT_DEV F3 camera_dir(const DCamera& c, uint32_t x, uint32_t y, float j1, float j2) {
   float fx = (((float)x + j1) * c.w_inv - 0.5f) * c.ar;
   float fy = 0.5f - ((float)y + j2) * c.h_inv;
   F3 p = normalize(f3(fx, fy, 0.8f));
   F3 rx = f3(p.x, c.cx * p.y - c.sx * p.z, c.sx * p.y + c.cx * p.z);        // rot_x, vec3.rs:108-119
-  F3 ry = f3(c.cy * rx.x + c.sy * rx.z, rx.y, -c.sy * rx.x + c.cy * rx.z);  // rot_y, vec3.rs:95-106
-  return make_ray(f3(c.ox, c.oy, c.oz), ry);
+  return f3(c.cy * rx.x + c.sy * rx.z, rx.y, -c.sy * rx.x + c.cy * rx.z);   // rot_y, vec3.rs:95-106
 }
+WPT_DEV Ray camera_ray(const DCamera& c, uint32_t x, uint32_t y, float j1, float j2) { return make_ray(f3(c.ox, c.oy, c.oz), camera_dir(c, x, y, j1, j2)); }
 
 // ------------------------------------------------------------------ PNEE light choice
 // PhotonTree::sample (photon_tree.rs:80-159) on the flattened octree.

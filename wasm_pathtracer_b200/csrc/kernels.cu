@@ -9,6 +9,7 @@
 #include "kernels.h"
 #include "device_core.cuh"
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace wpt {
 
@@ -68,6 +69,46 @@ void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, u
   uint32_t rows = band_rows(h, rank, world);
   if (!rows || !w) return;
   k_fill_pixels<<<(w * rows + 255) / 256, 256, 0, s>>>(pixel, W, x0, y0, w, rows, rank, world);
+}
+
+// ---- slot order by primary-hit class. A launch ends when its last path ends, and a lone lane runs a ray in ~25 us (a
+// dependent chain of node fetches), so a 100-ray path that starts shortly before the slot queue runs dry keeps the whole GPU
+// waiting for 2.5 ms (scripts/tail_probe.py). Long paths start on finite geometry; paths through background pixels are one ray
+// long. So the tiles are dealt in three stably partitioned classes — (0) a primary ray hits a BVH shape, (1) only an infinite
+// plane, (2) background — and the queue ends with the cheapest tiles: the long paths are over before the queue is empty. The
+// order of the slots changes no result (per-path streams, per-slot segment sums, combined in order afterwards).
+__global__ void k_tile_class(RenderParams rp, const uint32_t* __restrict__ pixel, uint32_t ntiles, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, tile = gid >> 3, k = gid & 7u;
+  const bool active = tile < ntiles;
+  uint32_t cls = 2u;
+  if (active) {   // eight probes per 8x4 tile, through the pixel centres
+    const uint32_t pix = pixel[(size_t)tile * 32u + k * 4u + (k & 3u)];
+    const uint32_t py = pix / rp.W, px = pix - py * rp.W;
+    const Ray ray = camera_ray(rp.cam, px, py, 0.5f, 0.5f);
+    const GHit g = trace_g(rp.scene, ray);
+    cls = g.id < 0 ? 2u : ((uint32_t)g.id < rp.scene.num_inf ? 1u : 0u);
+  }
+  cls = min(cls, __shfl_xor_sync(0xFFFFFFFFu, cls, 1));
+  cls = min(cls, __shfl_xor_sync(0xFFFFFFFFu, cls, 2));
+  cls = min(cls, __shfl_xor_sync(0xFFFFFFFFu, cls, 4));
+  if (active && k == 0u) { key[tile] = cls; val[tile] = tile; }
+}
+__global__ void k_permute_tiles(const uint32_t* __restrict__ in, const uint32_t* __restrict__ order, uint32_t ntiles, uint32_t n, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (i >> 5) < ntiles ? in[(size_t)order[i >> 5] * 32u + (i & 31u)] : in[i];   // the ragged strips behind the full tiles stay where they are
+}
+size_t tile_sort_bytes(uint32_t ntiles) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)ntiles, 0, 2);
+  return bytes;
+}
+void launch_order_tiles(const RenderParams& rp, const uint32_t* pixel, uint32_t n, uint32_t ntiles, uint32_t* key, uint32_t* val, uint32_t* key_out, uint32_t* val_out,
+                        void* tmp, size_t tmp_bytes, uint32_t* pixel_out, cudaStream_t s) {
+  if (!ntiles) return;
+  k_tile_class<<<(ntiles * 8u + 127u) / 128u, 128, 0, s>>>(rp, pixel, ntiles, key, val);
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key_out, val, val_out, (int)ntiles, 0, 2, s);   // stable: raster order inside a class
+  k_permute_tiles<<<(n + 255u) / 256u, 256, 0, s>>>(pixel, val_out, ntiles, n, pixel_out);
 }
 
 // ------------------------------------------------------------------ multi-GPU row exchange (band partition, wpt_types.h)
@@ -309,11 +350,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 #else
   constexpr bool DEFER_TORUS = KIND != K_SIMPLE;   // variants whose scenes can hold tori
 #endif
+  // Ray::new's reciprocal direction (ray.rs:31-33): computed where the ray is made (three sites + the camera), or once per half
+  // of a logic pass for every ray that starts there. One site runs with more lanes but keeps three more values live — measured
+  // (gpurun_out/r2g_ab.log): museum 33.3 -> 31.8 ms, BVH2 + PNEE 24.2 -> 23.5 ms, but headline 16.9 -> 17.2 and BVH4 + PNEE 30.8 -> 32.1 ms.
+  constexpr bool INV_ONE_SITE = KIND != K_SIMPLE || (BVH == 2 && RT == 2);
   const unsigned lane = threadIdx.x & 31u;
   int phase = PH_NEED, what = ST_GEN;
   uint32_t pixp = 0, s = 0, s_end = 0;   // pixp = px | py << 16 of the slot's pixel
   PathRegs ps; ps.color = f3(0, 0, 0); ps.T = f3(1, 1, 1); ps.rng.s = 1u; ps.bounced = false;
   Ray ray = make_ray(f3(0, 0, 0), f3(1, 1, 1));
+  auto set_ray = [&](F3 o, F3 d) { if (INV_ONE_SITE) { ray.o = o; ray.d = d; } else ray = make_ray(o, d); };
   Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0; tv.lcur = 0u;
   F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
@@ -327,6 +373,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   unsigned long long i_lp = 0, i_ll = 0, i_ts = 0, i_tl = 0, i_sh = 0;   // logic passes, logic lanes, trav steps, trav lanes, shade lanes
   unsigned long long t_start, t_empty = 0;   // %globaltimer (ns): launch timeline = first start .. first "queue empty" .. last exit (scripts/tail_probe.py)
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  uint32_t i_path_rays = 0, i_slot_rays = 0, i_max_path = 0, i_max_slot = 0;   // rays of the lane's current path / slot, and their maxima
 #endif
 
   const uint32_t nslots = P.nslots_dev ? *P.nslots_dev : P.nslots;
@@ -354,8 +401,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         bool ok = r < avail ? true : (idx < spare_end);
         if (ok) {
           // contract B10: the samples of this launch are summed per segment from +0; a slot is one segment
-          uint32_t pslot = idx, j = 0;
+          uint32_t pslot = idx, j = 0, zlen = 0;
           if (P.seg_list) { uint32_t e = P.seg_list[idx]; pslot = e >> 3; j = e & 7u; }   // strategy round: (pixel slot, segment) from the list
+          else if (idx >= P.zone_start[0]) {   // end zones of the queue: shorter slots (zone_len samples), see run_persistent
+            const int z = idx >= P.zone_start[2] ? 2 : (idx >= P.zone_start[1] ? 1 : 0);
+            const uint32_t r = idx - P.zone_start[z], q = r / P.zone_per[z];
+            pslot = P.zone_pslot[z] + q; j = r - q * P.zone_per[z]; zlen = P.zone_len[z];
+          }
           else if (P.nseg > 1) { pslot = idx / P.nseg; j = idx - pslot * P.nseg; }
           slot_id = idx;
           WPT_CHECK(idx < nslots);
@@ -365,10 +417,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           pixp = (pix - py * P.rp.W) | (py << 16);
           uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;
           uint32_t s0 = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
-          uint32_t b = min(j * P.seg_len, spp);
+          const uint32_t len = zlen ? zlen : P.seg_len, b = min(j * len, spp), e = min(b + len, spp);
           s = s0 + b;
-          s_end = s0 + min(b + P.seg_len, spp);
+          s_end = s0 + e;
+          // a zone slot stores every sample's colour on its own (k_combine_segments forms the segment sums): slot_id = flag | index one past its last sample
+          if (zlen) slot_id = 0x80000000u | (P.zone_samples + (pslot - P.zone_pslot[0]) * P.uniform_spp + e);
           acc_rgb = f3(0.0f, 0.0f, 0.0f);
+#ifdef MEGA_INSTR
+          i_slot_rays = 0;
+#endif
           what = ST_GEN; phase = PH_LOGIC;
         } else if (queue_empty) phase = PH_DONE;
       }
@@ -458,11 +515,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         const unsigned mc = __ballot_sync(FULL, cons);
         if (mc) { n_rays += (uint32_t)__popc(mc); n_visits += __reduce_add_sync(FULL, g.visits); n_prims += __reduce_add_sync(FULL, g.prims); }
       }
+#ifdef MEGA_INSTR
+      if (cons) { i_path_rays++; i_slot_rays++; i_max_path = max(i_max_path, i_path_rays); i_max_slot = max(i_max_slot, i_slot_rays); }
+#endif
       if (cons) {
         if (what == ST_SHADOW) {   // Scene::shadow_ray, scene.rs:114-132
           bool occluded = g.id >= 0 && g.t < sh_len && g.id != sh_light;
           if (!occluded) ps.color = ps.color + contrib;
-          if (alive_after_shadow) { ray = make_ray(ext_o, ext_d); what = ST_EXTEND; start = true; }
+          if (alive_after_shadow) { set_ray(ext_o, ext_d); what = ST_EXTEND; start = true; }
           else finish = true;
         } else {
           ShadeOut so;
@@ -472,11 +532,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           else if (so.shadow) {
             ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
             alive_after_shadow = so.survive;
-            ray = make_ray(so.sh_o, so.sh_d); what = ST_SHADOW; start = true;
-          } else if (so.survive) { ray = make_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
+            set_ray(so.sh_o, so.sh_d); what = ST_SHADOW; start = true;
+          } else if (so.survive) { set_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
           else finish = true;
         }
-        if (finish) { acc_rgb = acc_rgb + ps.color; s += 1; what = ST_GEN; }   // RenderTarget::write, render_target.rs:55-58
+        if (finish) {   // RenderTarget::write, render_target.rs:55-58
+          if (slot_id >> 31) P.seg_buf[(slot_id & 0x7FFFFFFFu) - (s_end - s)] = make_float4(ps.color.x, ps.color.y, ps.color.z, 0.0f);
+          else acc_rgb = acc_rgb + ps.color;
+          s += 1; what = ST_GEN;
+        }
 #ifdef MEGA_INSTR
         if (finish && lane == 0 && P.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); unsigned long long bkt = (t - t_start) / 250000ull; atomicAdd(&P.dbg[bkt < 99 ? bkt : 99], 1ull); }
 #endif
@@ -489,11 +553,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           ps.rng.s = sd == 0 ? 0xBABABEBEu : sd;
           float j1 = ps.rng.f32();
           float j2 = ps.rng.f32();
-          ray = camera_ray(P.rp.cam, px, py, j1, j2);
+          set_ray(f3(P.rp.cam.ox, P.rp.cam.oy, P.rp.cam.oz), camera_dir(P.rp.cam, px, py, j1, j2));
           ps.color = f3(0, 0, 0); ps.T = f3(1.0f, 1.0f, 1.0f); ps.bounced = false;
+#ifdef MEGA_INSTR
+          i_path_rays = 0;
+#endif
           what = ST_EXTEND; start = true;
         } else {
-          if (P.nseg > 1 || P.seg_list) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
+          if (slot_id >> 31) { }
+          else if (P.seg_buf) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
           else {   // the only segment of its pixel: add it here
             float4 a = P.accum[pix];
             P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));
@@ -501,7 +569,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           phase = PH_NEED;
         }
       }
-      if (start && trav_begin_const<BVH>(P, ray, tv)) phase = PH_TRAV;
+      if (start) {
+        if (INV_ONE_SITE) ray.inv = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+        if (trav_begin_const<BVH>(P, ray, tv)) phase = PH_TRAV;
+      }
     }
   }
   // ---- counters
@@ -519,6 +590,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
     atomicMin(&P.counters[9], t_start); if (t_empty) atomicMin(&P.counters[10], t_empty); atomicMax(&P.counters[11], t_end);
     atomicAdd(&P.counters[12], t_end - t_start);   // sum over warps of their lifetimes
+  }
+  {   // per warp: exit time, time it saw the queue empty, longest path and longest slot (rays) of its lanes
+    const uint32_t mp = __reduce_max_sync(FULL, i_max_path), ms = __reduce_max_sync(FULL, i_max_slot);
+    if (lane == 3 && P.dbg) {
+      unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      const uint32_t w = blockIdx.x * (MEGA_THREADS / 32) + (threadIdx.x >> 5);
+      P.dbg[128 + 3 * w] = t_end; P.dbg[128 + 3 * w + 1] = t_empty; P.dbg[128 + 3 * w + 2] = ((unsigned long long)mp << 32) | ms;
+    }
   }
 #endif
 }
@@ -572,18 +651,30 @@ void launch_mega(const MegaParams& P, const int blocks_per_sm[4], cudaStream_t s
 
 // ------------------------------------------------------------------ segments (contract B10)
 // accum[pix] += seg_0; += seg_1; ... in segment order, one thread per pixel; the sample count grows by spp.
-__global__ void k_combine_segments(float4* accum, const uint32_t* __restrict__ pixel, uint32_t npix, const float4* __restrict__ seg_buf, uint32_t nseg, uint32_t spp) {
+// Pixel slots from `zone_pslot` on (the end zones of the queue) stored every sample's colour on its own: their segment sums
+// are formed here, from +0 in sample order — the same additions as a lane makes for a whole segment.
+__global__ void k_combine_segments(float4* accum, const uint32_t* __restrict__ pixel, uint32_t npix, const float4* __restrict__ seg_buf, uint32_t nseg, uint32_t spp,
+                                   uint32_t zone_pslot, uint32_t seg_len) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   uint32_t pix = pixel[i];
   float4 a = accum[pix];
-  for (uint32_t j = 0; j < nseg; j++) { float4 g = seg_buf[(size_t)i * nseg + j]; a.x += g.x; a.y += g.y; a.z += g.z; }
+  if (i < zone_pslot) {
+    for (uint32_t j = 0; j < nseg; j++) { float4 g = seg_buf[(size_t)i * nseg + j]; a.x += g.x; a.y += g.y; a.z += g.z; }
+  } else {
+    const float4* sp = seg_buf + (size_t)zone_pslot * nseg + (size_t)(i - zone_pslot) * spp;
+    for (uint32_t j = 0; j < nseg; j++) {
+      float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+      for (uint32_t k = j * seg_len; k < min((j + 1u) * seg_len, spp); k++) { float4 g = sp[k]; sx += g.x; sy += g.y; sz += g.z; }
+      a.x += sx; a.y += sy; a.z += sz;
+    }
+  }
   a.w = __uint_as_float(__float_as_uint(a.w) + spp);
   accum[pix] = a;
 }
-void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, uint32_t nseg, uint32_t spp, cudaStream_t s) {
+void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, uint32_t nseg, uint32_t spp, uint32_t zone_pslot, uint32_t seg_len, cudaStream_t s) {
   if (!npix) return;
-  k_combine_segments<<<(npix + 255) / 256, 256, 0, s>>>(accum, pixel, npix, seg_buf, nseg, spp);
+  k_combine_segments<<<(npix + 255) / 256, 256, 0, s>>>(accum, pixel, npix, seg_buf, nseg, spp, zone_pslot, seg_len);
 }
 // ---- strategy rounds: every pixel slot has its own sample count (0..33 for an adaptive round). The segments of all
 // pixels are listed pixel by pixel (exclusive scan of ceil(spp / seg_len)); pixels without samples get no slot at all.

@@ -56,6 +56,10 @@ struct MegaParams {
   float4* seg_buf;                    // nseg > 1: segment sums [pixel slot * nseg + j], combined in order by launch_combine_segments
   const uint32_t* seg_list;           // strategy rounds: slot -> (pixel slot << 3 | segment); then nslots comes from nslots_dev and seg_buf is indexed by slot
   const uint32_t* nslots_dev;
+  // render_exact, end zones of the slot queue (up to three, in queue order; unused ones start at 0xFFFFFFFF): zone z begins at slot zone_start[z]
+  // with pixel slot zone_pslot[z]; a pixel has zone_per[z] slots of zone_len[z] samples. Zone slots write one colour per sample to
+  // seg_buf[zone_samples + (pixel slot - zone_pslot[0]) * uniform_spp + sample].
+  uint32_t zone_start[3], zone_pslot[3], zone_per[3], zone_len[3], zone_samples;
   uint32_t t_hi, t_lo;            // warp-vote thresholds of the traversal bursts
   uint32_t t_inner;               // leave the inner phase when lanes-at-inner * t_inner <= burst lanes
   uint32_t inner_reps;            // k_mega: inner-node steps per vote inside a burst
@@ -82,7 +86,7 @@ size_t wpool_ctx_bytes();
 void launch_setup_slots(const PathState& st, const uint32_t* spp_per_slot, uint32_t uniform_spp, const float4* accum, cudaStream_t s);
 void launch_trace(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
 void launch_shade(const RenderParams& rp, const PathState& st, const WaveBuffers& wb, uint32_t iter, int grid, cudaStream_t s);
-void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, uint32_t nseg, uint32_t spp, cudaStream_t s);
+void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, uint32_t nseg, uint32_t spp, uint32_t zone_pslot, uint32_t seg_len, cudaStream_t s);
 // Strategy rounds (per-slot sample counts): cut every pixel's samples into segments of seg_len, listed pixel by pixel.
 // seg_off needs npix + 1 entries (seg_off[npix] = number of segments); scan_tmp is scratch of at least seg_scan_bytes(npix) bytes.
 size_t seg_scan_bytes(uint32_t npix);
@@ -97,6 +101,10 @@ void launch_trace_batch(const RenderParams& rp, const float* o, const float* d, 
 // multi-GPU accumulator exchange: this rank's rows of the region -> contiguous staging (padded to `per` rows), and back from all ranks' staging
 void launch_pack_rows(const float4* accum, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t rank, uint32_t world, uint32_t per, float4* send, cudaStream_t s);
 void launch_unpack_rows(const float4* recv, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t rank, uint32_t world, uint32_t per, float4* accum, cudaStream_t s);
+// slot order by primary-hit class (kernels.cu): tiles whose primary rays hit finite geometry first, background tiles last
+size_t tile_sort_bytes(uint32_t ntiles);
+void launch_order_tiles(const RenderParams& rp, const uint32_t* pixel, uint32_t n, uint32_t ntiles, uint32_t* key, uint32_t* val, uint32_t* key_out, uint32_t* val_out,
+                        void* tmp, size_t tmp_bytes, uint32_t* pixel_out, cudaStream_t s);
 void launch_fill_pixels(uint32_t* pixel, uint32_t W, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t rank, uint32_t world, cudaStream_t s);
 
 // photons

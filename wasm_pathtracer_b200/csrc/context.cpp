@@ -367,8 +367,15 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   if (!slots) return;
   if (render_type == WPT_PNEE && !photons_ready) throw std::runtime_error("photon tree not built");
   MegaParams P{};
-  bool zone_default = false;   // scenes with other primitives than triangles and planes (kernel variants K_REF / K_EXT)
-  for (const HostShape& sh : scene.shapes) if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) { zone_default = true; break; }
+  // kernel variant by scene content: triangles + planes only / the reference's primitives and materials / everything
+  uint32_t scene_kind = 0;
+  for (const HostShape& sh : scene.shapes) {
+    if (sh.type == SH_SPHERE || sh.type == SH_SQUARE) { scene_kind = 2; break; }
+    if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) scene_kind = 1;
+  }
+  for (const HostMaterial& m : scene.mats) if (m.kind != MAT_DIFFUSE && m.kind != MAT_EMISSIVE) { scene_kind = 2; break; }
+  if (std::getenv("WPT_NO_SIMPLE")) scene_kind = 2;
+  const bool zones_ok = scene_kind != 0;   // the triangles / planes variants are compiled without the end-zone code (kernels.cu)
   for (int z = 0; z < 3; z++) { P.zone_start[z] = 0xFFFFFFFFu; P.zone_pslot[z] = 0; P.zone_per[z] = 1; P.zone_len[z] = 1; }
   P.zone_samples = 0; uint32_t zone_first = slots;
   P.rp = params(render_type);
@@ -401,9 +408,9 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
     // Measured (gpurun_out/r2h_zone2.log, r2h_tail_zone2.log): "15:4,10:2,5:1" pulls the warp exits together (99 % of the warps within
     // 0.47 ms of the queue running dry instead of 1.76 ms, the last one after 1.6 instead of 2.6 ms), but every slot fetch stalls its
     // warp on the atomic + pixel + accumulator loads, so the queue itself lasts longer: bunny frame 16.6 -> 16.8 ms (no gain), museum
-    // 32.5 -> 31.3 ms. Default: on for scenes with tori / boxes, off otherwise.
+    // 32.5 -> 31.3 ms. So only the kernel variants for scenes with tori / boxes / the extension carry the zone code, on by default.
     static const char* env_zones_c = std::getenv("WPT_MEGA_ZONES");
-    const std::string env_zones = env_zones_c ? env_zones_c : (zone_default ? "15:4,10:2,5:1" : "");
+    const std::string env_zones = !zones_ok ? "" : (env_zones_c ? env_zones_c : "15:4,10:2,5:1");
     uint32_t zpx[3] = {0, 0, 0}, zlen[3] = {1, 1, 1}; int nz = 0;
     if (uniform_spp > 1 && cfg.engine == 0) {
       const char* c = env_zones.c_str();
@@ -460,14 +467,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   P.t_torus = (uint32_t)std::max(1, env_ttor);
   static const int env_chunk = std::getenv("WPT_MEGA_CHUNK") ? std::atoi(std::getenv("WPT_MEGA_CHUNK")) : 32;
   P.chunk = (uint32_t)env_chunk;
-  // kernel variant by scene content: triangles + planes only / the reference's primitives and materials / everything
-  P.scene_kind = 0;
-  for (const HostShape& sh : scene.shapes) {
-    if (sh.type == SH_SPHERE || sh.type == SH_SQUARE) { P.scene_kind = 2; break; }
-    if (sh.type != SH_TRIANGLE && sh.type != SH_PLANE) P.scene_kind = 1;
-  }
-  for (const HostMaterial& m : scene.mats) if (m.kind != MAT_DIFFUSE && m.kind != MAT_EMISSIVE) { P.scene_kind = 2; break; }
-  if (std::getenv("WPT_NO_SIMPLE")) P.scene_kind = 2;
+  P.scene_kind = scene_kind;
   if (P.scene_kind != 0) { if (!env_hi) P.t_hi = 12; if (!env_lo) P.t_lo = 4; }
   {
     // the infinite shapes are planes (only a Plane has no finite box, bvh.rs:376-394), at most two in the reference's

@@ -82,6 +82,8 @@ WPT_DEV void photon_sample_inl(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* l
     return;
   }
   // find_leaf (photon_tree.rs:201-211)
+  // (tried and removed: a 64^3 entry table for the first six halvings of the +-1024 cube — 1.6 % at best, and its code cost the
+  //  BVH4 + PNEE variant more than that, gpurun_out/r2j_entry.log, r2k_ab.log)
   Cell b = {-size, -size, -size, size, size, size};
   uint32_t depth = 0, node = 0;
   for (;;) {

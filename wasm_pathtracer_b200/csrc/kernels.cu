@@ -352,8 +352,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 #endif
   // Ray::new's reciprocal direction (ray.rs:31-33): computed where the ray is made (three sites + the camera), or once per half
   // of a logic pass for every ray that starts there. One site runs with more lanes but keeps three more values live — measured
-  // (gpurun_out/r2g_ab.log): museum 33.3 -> 31.8 ms, BVH2 + PNEE 24.2 -> 23.5 ms, but headline 16.9 -> 17.2 and BVH4 + PNEE 30.8 -> 32.1 ms.
-  constexpr bool INV_ONE_SITE = KIND != K_SIMPLE || (BVH == 2 && RT == 2);
+  // (gpurun_out/r2g_ab.log): museum 33.3 -> 31.8 ms, but headline 16.9 -> 17.2 and BVH4 + PNEE 30.8 -> 32.1 ms.
+  constexpr bool INV_ONE_SITE = KIND != K_SIMPLE;
+  // end zones of the slot queue (run_persistent): only in the variants that gain from them — their code costs the triangles /
+  // planes variants 1.5 % (headline) to 6 % (BVH4 + PNEE) even when unused (gpurun_out/r2k_ab.log)
+  constexpr bool ZONES = KIND != K_SIMPLE;
   const unsigned lane = threadIdx.x & 31u;
   int phase = PH_NEED, what = ST_GEN;
   uint32_t pixp = 0, s = 0, s_end = 0;   // pixp = px | py << 16 of the slot's pixel
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           // contract B10: the samples of this launch are summed per segment from +0; a slot is one segment
           uint32_t pslot = idx, j = 0, zlen = 0;
           if (P.seg_list) { uint32_t e = P.seg_list[idx]; pslot = e >> 3; j = e & 7u; }   // strategy round: (pixel slot, segment) from the list
-          else if (idx >= P.zone_start[0]) {   // end zones of the queue: shorter slots (zone_len samples), see run_persistent
+          else if (ZONES && idx >= P.zone_start[0]) {   // end zones of the queue: shorter slots (zone_len samples), see run_persistent
             const int z = idx >= P.zone_start[2] ? 2 : (idx >= P.zone_start[1] ? 1 : 0);
             const uint32_t r = idx - P.zone_start[z], q = r / P.zone_per[z];
             pslot = P.zone_pslot[z] + q; j = r - q * P.zone_per[z]; zlen = P.zone_len[z];
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           s = s0 + b;
           s_end = s0 + e;
           // a zone slot stores every sample's colour on its own (k_combine_segments forms the segment sums): slot_id = flag | index one past its last sample
-          if (zlen) slot_id = 0x80000000u | (P.zone_samples + (pslot - P.zone_pslot[0]) * P.uniform_spp + e);
+          if (ZONES && zlen) slot_id = 0x80000000u | (P.zone_samples + (pslot - P.zone_pslot[0]) * P.uniform_spp + e);
           acc_rgb = f3(0.0f, 0.0f, 0.0f);
 #ifdef MEGA_INSTR
           i_slot_rays = 0;
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           else finish = true;
         }
         if (finish) {   // RenderTarget::write, render_target.rs:55-58
-          if (slot_id >> 31) P.seg_buf[(slot_id & 0x7FFFFFFFu) - (s_end - s)] = make_float4(ps.color.x, ps.color.y, ps.color.z, 0.0f);
+          if (ZONES && (slot_id >> 31)) P.seg_buf[(slot_id & 0x7FFFFFFFu) - (s_end - s)] = make_float4(ps.color.x, ps.color.y, ps.color.z, 0.0f);
           else acc_rgb = acc_rgb + ps.color;
           s += 1; what = ST_GEN;
         }
@@ -560,8 +563,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 #endif
           what = ST_EXTEND; start = true;
         } else {
-          if (slot_id >> 31) { }
-          else if (P.seg_buf) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
+          if (ZONES && (slot_id >> 31)) { }
+          else if (ZONES ? P.seg_buf != nullptr : (P.nseg > 1 || P.seg_list)) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
           else {   // the only segment of its pixel: add it here
             float4 a = P.accum[pix];
             P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));

@@ -388,13 +388,22 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
     // strategy round: per-slot counts (0..33 adaptive, anything for random). The segments of all pixels are listed
     // pixel by pixel on the device; pixels without samples get no slot. At most 8 segments per pixel fit the list
     // encoding (pixel slot << 3 | segment); the strategies cap a round at 33 samples, random rounds are checked.
-    if (slots >= (1u << 29)) throw std::runtime_error("viewport too large for the segment list encoding");
-    const uint32_t max_seg = 8;
-    d_seg_cnt.alloc((size_t)slots + 1); d_seg_off.alloc((size_t)slots + 1); d_seg_list.alloc((size_t)slots * max_seg);
+    if (slots >= (1u << 26)) throw std::runtime_error("viewport too large for the segment list encoding");
+    // Short slots: a round is one launch, and with few pixel slots per lane (small frames, many GPUs) it lasts as long as its slowest
+    // slot — ~1 ms per segment of 8 samples plus the stragglers (scripts/tail_probe.py). Below four pixel slots per lane the round is
+    // cut into slots of 2 samples (WPT_MEGA_LIST_LEN overrides; 0 = segments); they store one colour per sample and
+    // k_combine_segment_list forms the segment sums in the same order, so the slot length is a scheduling choice, not part of contract B10.
+    static const int env_list = std::getenv("WPT_MEGA_LIST_LEN") ? std::atoi(std::getenv("WPT_MEGA_LIST_LEN")) : -1;
+    const uint32_t lanes = (uint32_t)device_sm_count() * 8u * 128u;
+    uint32_t list_len = env_list >= 0 ? (uint32_t)std::min(env_list, 64) : (slots < 4u * lanes ? 2u : 0u);
+    if (cfg.engine != 0) list_len = 0;
+    const uint32_t per_px = list_len ? (64u + list_len - 1u) / list_len : 8u;   // slots a pixel can have (a round holds at most 64 samples per pixel)
+    d_seg_cnt.alloc((size_t)slots + 1); d_seg_off.alloc((size_t)slots + 1); d_seg_list.alloc((size_t)slots * per_px);
     size_t sb = seg_scan_bytes(slots);
     d_scan_tmp.alloc(sb ? sb : 1);
-    launch_build_segment_list(d_spp_per_slot, slots, seg_len, d_seg_cnt.p, d_seg_off.p, d_scan_tmp.p, sb, d_seg_list.p, stream);
-    d_seg_buf.alloc((size_t)slots * max_seg);
+    launch_build_segment_list(d_spp_per_slot, slots, list_len ? list_len : seg_len, d_seg_cnt.p, d_seg_off.p, d_scan_tmp.p, sb, d_seg_list.p, list_len ? 6u : 3u, stream);
+    d_seg_buf.alloc(list_len ? (size_t)slots * per_px * list_len : (size_t)slots * 8u);
+    P.list_len = list_len;
     P.nseg = 1; P.seg_list = d_seg_list.p; P.nslots_dev = d_seg_off.p + slots; P.nslots = slots; P.seg_buf = d_seg_buf.p;
     launches += 3;
   } else {
@@ -504,7 +513,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   } else launch_mega(P, env_minb, stream);
   if (profiling) { WPT_CUDA(cudaEventRecord(b, stream)); ev_pending.push_back(EvPair{a, b, 0}); }
   WPT_CUDA(cudaGetLastError());
-  if (P.seg_list) { launch_combine_segment_list(d_accum.p, s_pixel.p, slots, d_seg_buf.p, d_seg_off.p, d_spp_per_slot, stream); launches += 1; }
+  if (P.seg_list) { launch_combine_segment_list(d_accum.p, s_pixel.p, slots, d_seg_buf.p, d_seg_off.p, d_spp_per_slot, P.list_len, seg_len, stream); launches += 1; }
   else if (P.seg_buf) { launch_combine_segments(d_accum.p, s_pixel.p, slots, d_seg_buf.p, P.nseg, uniform_spp, zone_first, seg_len, stream); launches += 1; }
   launches += 1; iterations += 1;
   rgba_stale = true;

@@ -340,7 +340,7 @@ WPT_DEV bool trav_begin_const(const MegaParams& P, const Ray& ray, Trav& tv) {
   return true;
 }
 
-template <int BVH, int KIND, int MINB, int RT>
+template <int BVH, int KIND, int MINB, int RT, bool ZN>
 __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   constexpr bool INV_ONE_SITE = KIND != K_SIMPLE;
   // end zones of the slot queue (run_persistent): only in the variants that gain from them — their code costs the triangles /
   // planes variants 1.5 % (headline) to 6 % (BVH4 + PNEE) even when unused (gpurun_out/r2k_ab.log)
-  constexpr bool ZONES = KIND != K_SIMPLE;
+  constexpr bool ZONES = ZN;   // ZN: always for KIND != K_SIMPLE; for the triangles / planes variants only when a strategy round is cut into short slots (P.list_len)
   const unsigned lane = threadIdx.x & 31u;
   int phase = PH_NEED, what = ST_GEN;
   uint32_t pixp = 0, s = 0, s_end = 0;   // pixp = px | py << 16 of the slot's pixel
@@ -405,7 +405,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         if (ok) {
           // contract B10: the samples of this launch are summed per segment from +0; a slot is one segment
           uint32_t pslot = idx, j = 0, zlen = 0;
-          if (P.seg_list) { uint32_t e = P.seg_list[idx]; pslot = e >> 3; j = e & 7u; }   // strategy round: (pixel slot, segment) from the list
+          if (P.seg_list) {   // strategy round: (pixel slot, segment) from the list; with P.list_len (pixel slot, short slot of list_len samples)
+            const uint32_t e = P.seg_list[idx];
+            if (ZONES && P.list_len) { pslot = e >> 6; j = e & 63u; zlen = P.list_len; } else { pslot = e >> 3; j = e & 7u; }
+          }
           else if (ZONES && idx >= P.zone_start[0]) {   // end zones of the queue: shorter slots (zone_len samples), see run_persistent
             const int z = idx >= P.zone_start[2] ? 2 : (idx >= P.zone_start[1] ? 1 : 0);
             const uint32_t r = idx - P.zone_start[z], q = r / P.zone_per[z];
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           s = s0 + b;
           s_end = s0 + e;
           // a zone slot stores every sample's colour on its own (k_combine_segments forms the segment sums): slot_id = flag | index one past its last sample
-          if (ZONES && zlen) slot_id = 0x80000000u | (P.zone_samples + (pslot - P.zone_pslot[0]) * P.uniform_spp + e);
+          if (ZONES && zlen) slot_id = 0x80000000u | (P.seg_list ? idx * zlen + (e - b) : P.zone_samples + (pslot - P.zone_pslot[0]) * P.uniform_spp + e);   // list: slot idx owns entries idx * len ..
           acc_rgb = f3(0.0f, 0.0f, 0.0f);
 #ifdef MEGA_INSTR
           i_slot_rays = 0;
@@ -607,30 +610,36 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 // Register budgets (blocks of 128 threads per SM) instantiated per variant: the measured optimum (gpurun_out/sweep8.log,
 // sweep11.log, sweep12.log) — triangles/planes BVH2 8 (64 registers), BVH4 5 and 8, ext 16 (32 registers); the reference-primitives
 // variant (tori, boxes) has 8 / 12 / 16 selectable at run time (WPT_MEGA_MINBG). With -DWPT_TUNING: 4 / 5 / 8 / 12 / 16 for every variant.
-template <int BVH, int KIND, int RT>
-static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
+template <int BVH, int KIND, int RT, bool ZN>
+static void launch_mega_z(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   auto grid_for = [&](int b) { int grid = device_sm_count() * b, need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS); return (grid > need && !P.nslots_dev) ? need : grid; };
 #ifdef WPT_TUNING
   int b = blocks_per_sm >= 16 ? 16 : blocks_per_sm >= 12 ? 12 : blocks_per_sm >= 8 ? 8 : blocks_per_sm >= 5 ? 5 : 4;
   switch (b) {
-    case 5: k_mega<BVH, KIND, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P); break;
-    case 8: k_mega<BVH, KIND, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P); break;
-    case 12: k_mega<BVH, KIND, 12, RT><<<grid_for(12), MEGA_THREADS, 0, s>>>(P); break;
-    case 16: k_mega<BVH, KIND, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P); break;
-    default: k_mega<BVH, KIND, 4, RT><<<grid_for(4), MEGA_THREADS, 0, s>>>(P); break;
+    case 5: k_mega<BVH, KIND, 5, RT, ZN><<<grid_for(5), MEGA_THREADS, 0, s>>>(P); break;
+    case 8: k_mega<BVH, KIND, 8, RT, ZN><<<grid_for(8), MEGA_THREADS, 0, s>>>(P); break;
+    case 12: k_mega<BVH, KIND, 12, RT, ZN><<<grid_for(12), MEGA_THREADS, 0, s>>>(P); break;
+    case 16: k_mega<BVH, KIND, 16, RT, ZN><<<grid_for(16), MEGA_THREADS, 0, s>>>(P); break;
+    default: k_mega<BVH, KIND, 4, RT, ZN><<<grid_for(4), MEGA_THREADS, 0, s>>>(P); break;
   }
 #else
-  if constexpr (KIND == K_EXT) k_mega<BVH, KIND, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
+  if constexpr (KIND == K_EXT) k_mega<BVH, KIND, 16, RT, ZN><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
   else if constexpr (KIND == K_REF) {
-    if (BVH == 4 || blocks_per_sm >= 16) k_mega<BVH, KIND, 16, RT><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
+    if (BVH == 4 || blocks_per_sm >= 16) k_mega<BVH, KIND, 16, RT, ZN><<<grid_for(16), MEGA_THREADS, 0, s>>>(P);
     else if constexpr (BVH == 2) {
-      if (blocks_per_sm >= 12) k_mega<BVH, KIND, 12, RT><<<grid_for(12), MEGA_THREADS, 0, s>>>(P);
-      else k_mega<BVH, KIND, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
+      if (blocks_per_sm >= 12) k_mega<BVH, KIND, 12, RT, ZN><<<grid_for(12), MEGA_THREADS, 0, s>>>(P);
+      else k_mega<BVH, KIND, 8, RT, ZN><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
     }
   }
-  else if constexpr (BVH == 2 || RT == 2) k_mega<BVH, KIND, 8, RT><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
-  else k_mega<BVH, KIND, 5, RT><<<grid_for(5), MEGA_THREADS, 0, s>>>(P);
+  else if constexpr (BVH == 2 || RT == 2) k_mega<BVH, KIND, 8, RT, ZN><<<grid_for(8), MEGA_THREADS, 0, s>>>(P);
+  else k_mega<BVH, KIND, 5, RT, ZN><<<grid_for(5), MEGA_THREADS, 0, s>>>(P);
 #endif
+}
+template <int BVH, int KIND, int RT>
+static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
+  if constexpr (KIND != K_SIMPLE) launch_mega_z<BVH, KIND, RT, true>(P, blocks_per_sm, s);
+  else if (P.list_len) launch_mega_z<BVH, KIND, RT, true>(P, blocks_per_sm, s);
+  else launch_mega_z<BVH, KIND, RT, false>(P, blocks_per_sm, s);
 }
 template <int BVH, int KIND>
 static void launch_mega_rt(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
@@ -686,37 +695,49 @@ __global__ void k_seg_count(const uint32_t* __restrict__ slot_spp, uint32_t npix
   if (i > npix) return;
   cnt[i] = i < npix ? (slot_spp[i] + seg_len - 1u) / seg_len : 0u;   // cnt[npix] = 0: the scan's last entry is the total
 }
-__global__ void k_seg_fill(const uint32_t* __restrict__ off, uint32_t npix, uint32_t* __restrict__ list) {
+__global__ void k_seg_fill(const uint32_t* __restrict__ off, uint32_t npix, uint32_t* __restrict__ list, uint32_t shift) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   uint32_t a = off[i], b = off[i + 1];
-  for (uint32_t j = 0; a + j < b; j++) list[a + j] = (i << 3) | j;
+  for (uint32_t j = 0; a + j < b; j++) list[a + j] = (i << shift) | j;
 }
 size_t seg_scan_bytes(uint32_t npix) {
   size_t bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(npix + 1));
   return bytes;
 }
-void launch_build_segment_list(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t* seg_cnt, uint32_t* seg_off, void* scan_tmp, size_t scan_bytes, uint32_t* seg_list, cudaStream_t s) {
+void launch_build_segment_list(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t* seg_cnt, uint32_t* seg_off, void* scan_tmp, size_t scan_bytes, uint32_t* seg_list, uint32_t shift, cudaStream_t s) {
   if (!npix) return;
   k_seg_count<<<(npix + 1 + 255) / 256, 256, 0, s>>>(slot_spp, npix, seg_len, seg_cnt);
   cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, seg_cnt, seg_off, (int)(npix + 1), s);
-  k_seg_fill<<<(npix + 255) / 256, 256, 0, s>>>(seg_off, npix, seg_list);
+  k_seg_fill<<<(npix + 255) / 256, 256, 0, s>>>(seg_off, npix, seg_list, shift);
 }
-__global__ void k_combine_segment_list(float4* accum, const uint32_t* __restrict__ pixel, uint32_t npix, const float4* __restrict__ seg_buf, const uint32_t* __restrict__ off, const uint32_t* __restrict__ slot_spp) {
+// list_len != 0: the round was cut into short slots that stored one colour per sample (slot k owns entries k * list_len ..); the
+// segment sums (seg_len samples from +0, in sample order) are formed here — the same additions as a lane makes for a whole segment.
+__global__ void k_combine_segment_list(float4* accum, const uint32_t* __restrict__ pixel, uint32_t npix, const float4* __restrict__ seg_buf, const uint32_t* __restrict__ off, const uint32_t* __restrict__ slot_spp,
+                                       uint32_t list_len, uint32_t seg_len) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   uint32_t a = off[i], b = off[i + 1];
   if (a == b) return;
   uint32_t pix = pixel[i];
   float4 acc = accum[pix];
+  if (list_len) {
+    const float4* sp = seg_buf + (size_t)a * list_len;
+    const uint32_t spp = slot_spp[i];
+    for (uint32_t k0 = 0; k0 < spp; k0 += seg_len) {
+      float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+      for (uint32_t k = k0; k < min(k0 + seg_len, spp); k++) { float4 g = sp[k]; sx += g.x; sy += g.y; sz += g.z; }
+      acc.x += sx; acc.y += sy; acc.z += sz;
+    }
+  } else
   for (uint32_t k = a; k < b; k++) { float4 g = seg_buf[k]; acc.x += g.x; acc.y += g.y; acc.z += g.z; }
   acc.w = __uint_as_float(__float_as_uint(acc.w) + slot_spp[i]);
   accum[pix] = acc;
 }
-void launch_combine_segment_list(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, const uint32_t* seg_off, const uint32_t* slot_spp, cudaStream_t s) {
+void launch_combine_segment_list(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, const uint32_t* seg_off, const uint32_t* slot_spp, uint32_t list_len, uint32_t seg_len, cudaStream_t s) {
   if (!npix) return;
-  k_combine_segment_list<<<(npix + 255) / 256, 256, 0, s>>>(accum, pixel, npix, seg_buf, seg_off, slot_spp);
+  k_combine_segment_list<<<(npix + 255) / 256, 256, 0, s>>>(accum, pixel, npix, seg_buf, seg_off, slot_spp, list_len, seg_len);
 }
 // wavefront engine: the samples of pass `pass` (= segment index) of every slot; any_left counts slots that still have samples
 __global__ void k_segment_pass_spp(const uint32_t* __restrict__ slot_spp, uint32_t npix, uint32_t seg_len, uint32_t pass, uint32_t* __restrict__ pass_spp, uint32_t* any_left) {

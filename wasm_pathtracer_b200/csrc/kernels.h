@@ -56,6 +56,7 @@ struct MegaParams {
   float4* seg_buf;                    // nseg > 1: segment sums [pixel slot * nseg + j], combined in order by launch_combine_segments
   const uint32_t* seg_list;           // strategy rounds: slot -> (pixel slot << 3 | segment); then nslots comes from nslots_dev and seg_buf is indexed by slot
   const uint32_t* nslots_dev;
+  uint32_t list_len;                  // strategy rounds cut into short slots of list_len samples (list entries pixel slot << 6 | slot, one colour per sample in seg_buf[slot * list_len ..]); 0 = segments of seg_len
   // render_exact, end zones of the slot queue (up to three, in queue order; unused ones start at 0xFFFFFFFF): zone z begins at slot zone_start[z]
   // with pixel slot zone_pslot[z]; a pixel has zone_per[z] slots of zone_len[z] samples. Zone slots write one colour per sample to
   // seg_buf[zone_samples + (pixel slot - zone_pslot[0]) * uniform_spp + sample].
@@ -90,8 +91,8 @@ void launch_combine_segments(float4* accum, const uint32_t* pixel, uint32_t npix
 // Strategy rounds (per-slot sample counts): cut every pixel's samples into segments of seg_len, listed pixel by pixel.
 // seg_off needs npix + 1 entries (seg_off[npix] = number of segments); scan_tmp is scratch of at least seg_scan_bytes(npix) bytes.
 size_t seg_scan_bytes(uint32_t npix);
-void launch_build_segment_list(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t* seg_cnt, uint32_t* seg_off, void* scan_tmp, size_t scan_bytes, uint32_t* seg_list, cudaStream_t s);
-void launch_combine_segment_list(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, const uint32_t* seg_off, const uint32_t* slot_spp, cudaStream_t s);
+void launch_build_segment_list(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t* seg_cnt, uint32_t* seg_off, void* scan_tmp, size_t scan_bytes, uint32_t* seg_list, uint32_t shift, cudaStream_t s);
+void launch_combine_segment_list(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_buf, const uint32_t* seg_off, const uint32_t* slot_spp, uint32_t list_len, uint32_t seg_len, cudaStream_t s);
 void launch_segment_pass_spp(const uint32_t* slot_spp, uint32_t npix, uint32_t seg_len, uint32_t pass, uint32_t* pass_spp, uint32_t* any_left, cudaStream_t s);
 void launch_add_segment(float4* accum, const uint32_t* pixel, uint32_t npix, const float4* seg_acc, cudaStream_t s);
 void launch_clear_pixels(float4* buf, const uint32_t* pixel, uint32_t npix, cudaStream_t s);

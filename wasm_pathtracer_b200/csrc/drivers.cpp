@@ -209,12 +209,22 @@ void Context::photon_sample_batch(const float* pts3, const uint32_t* seeds, uint
 // ------------------------------------------------------------------ sampling strategies
 Context::Strategy& Context::strategy_for(uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh) {
   for (auto& s : strategies) if (s.rx == rx && s.ry == ry && s.rw == rw && s.rh == rh) return s;
+  if (strategies.size() >= 8) strategies.clear();   // regions come and go (split screen, custom regions): bound the buffers kept for them
   strategies.emplace_back();
   Strategy& s = strategies.back();
   s.rx = rx; s.ry = ry; s.rw = rw; s.rh = rh;
   return s;
 }
-void Context::clear_strategies() { strategies.clear(); }
+// reset(): every strategy starts over (as a freshly constructed one would), but keeps its device buffers — freeing and
+// re-allocating them costs two implicit device synchronisations per buffer and frame
+void Context::clear_strategies() {
+  for (auto& s : strategies) {
+    const uint32_t N = s.rw * s.rh;
+    if (s.round_left.n >= N && N) launch_fill_u32(s.round_left.p, N, 0, stream);
+    if (s.state.p) WPT_CUDA(cudaMemsetAsync(s.state.p, 0, 16 * sizeof(unsigned long long), stream));
+    s.left_total = 0; s.started = false; s.painted = false; s.random_ticks = 0;
+  }
+}
 
 // error map + {min, avg, max} of the region (sampling_strategy.rs:133-151, mode-B reduction)
 void Context::region_error_launch(Strategy& s) {   // error map + {sum, min, max} into a_stats, no host synchronisation

@@ -1047,7 +1047,7 @@ __global__ void __launch_bounds__(EM_BX * EM_BY) k_error_map(const float4* __res
   }
 }
 void launch_error_map(const float4* accum, uint32_t W, uint32_t H, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, float* mse, unsigned long long* stats, const unsigned long long* gate, cudaStream_t s) {
-  if (!(rw * rh)) return;
+  if (!rw || !rh) return;
   k_error_map<<<dim3((rw + EM_BX - 1) / EM_BX, (rh + EM_BY - 1) / EM_BY), dim3(EM_BX, EM_BY), 0, s>>>(accum, W, H, rx, ry, rw, rh, mse, stats, gate);
 }
 WPT_DEV uint32_t sampling_rgba(F3 v) { return 0xFF000000u | to_u8(v.x) | (to_u8(v.y) << 8) | (to_u8(v.z) << 16); }
@@ -1087,7 +1087,7 @@ __global__ void k_fill_region_rgba(uint32_t* rgba, uint32_t W, uint32_t rx, uint
   rgba[(size_t)(ry + i / rw) * W + rx + i % rw] = value;
 }
 void launch_fill_region_rgba(uint8_t* rgba, uint32_t W, uint32_t rx, uint32_t ry, uint32_t rw, uint32_t rh, uint32_t value, cudaStream_t s) {
-  if (!(rw * rh)) return;
+  if (!rw || !rh) return;
   k_fill_region_rgba<<<(rw * rh + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t*>(rgba), W, rx, ry, rw, rh, value);
 }
 __global__ void k_fill_u32(uint32_t* a, uint32_t n, uint32_t v) {

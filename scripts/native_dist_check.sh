@@ -12,7 +12,7 @@ for mode in "--type 1" "--type 2 --photons 20000" "--type 1 --adaptive" "--type 
   done
   for p in $pids; do wait $p; done
   for r in $(seq 0 $((N - 1))); do
-    got=$(grep frame_fnv1a /tmp/wpt_rank_$r.json | sed 's/.*frame_fnv1a": "\([0-9a-f]*\)".*/\1/' /tmp/wpt_rank_$r.json)
+    got=$(grep frame_fnv1a /tmp/wpt_rank_$r.json | sed 's/.*frame_fnv1a": "\([0-9a-f]*\)".*/\1/')
     echo "mode [$mode] rank $r of $N: frame hash $got, 1-GPU hash $ref: $([ "$got" = "$ref" ] && echo SAME || echo DIFFERENT)"
   done
 done

@@ -64,6 +64,17 @@ void Context::attach_nccl(const uint8_t id128[128], void* existing_comm, uint32_
   if (nccl_comm && world > 1) {   // NCCL sets up its channels at the first collective (~1 s): pay that here, not inside the first render
     WPT_CUDA(cudaMemsetAsync(w_work.p + 2, 0, sizeof(uint32_t), stream));
     WPT_NCCL(nccl().AllReduce(w_work.p + 2, w_work.p + 2, 1, ncclUint32, ncclSum, static_cast<ncclComm_t>(nccl_comm), stream));
+    // ... and NCCL picks its kernels by message size and loads them lazily (first photon warm-up on 8 GPUs: 113 ms instead of 6):
+    // one collective of each kind at the sizes the plane uses — a photon batch (131 072 shots x 6 words) and a band of accumulator rows
+    {
+      DevBuf<uint32_t> warm, gath;
+      const size_t words = 131072u * 6u, part = 1u << 20;
+      warm.alloc(std::max(words, part)); gath.alloc(part * world);
+      WPT_CUDA(cudaMemsetAsync(warm.p, 0, std::max(words, part) * sizeof(uint32_t), stream));
+      WPT_NCCL(nccl().AllReduce(warm.p, warm.p, words, ncclUint32, ncclSum, static_cast<ncclComm_t>(nccl_comm), stream));
+      WPT_NCCL(nccl().AllGather(warm.p, gath.p, part, ncclFloat, static_cast<ncclComm_t>(nccl_comm), stream));
+      WPT_CUDA(cudaStreamSynchronize(stream));
+    }
     WPT_CUDA(cudaStreamSynchronize(stream));
   }
   if (world > 1) {

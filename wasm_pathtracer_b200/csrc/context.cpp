@@ -448,6 +448,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
     const uint64_t buf_n = (uint64_t)body_px * P.nseg + (uint64_t)zone_px * uniform_spp;
     if (P.nseg > 1 || zone_px) { d_seg_buf.alloc((size_t)buf_n); P.seg_buf = d_seg_buf.p; }
   }
+  P.seg_buf_n = P.seg_buf ? (uint32_t)std::min<size_t>(d_seg_buf.n, 0xFFFFFFFFu) : 0u;
   P.work_counter = w_work.p; P.counters = w_counters.p;
   WPT_CUDA(cudaMemsetAsync(w_work.p, 0, sizeof(uint32_t), stream));
 #ifdef MEGA_INSTR

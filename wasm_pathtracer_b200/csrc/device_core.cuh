@@ -825,6 +825,7 @@ WPT_DEV bool trav_torus(const DScene& sc, const Ray& ray, Trav& tv) {
   uint32_t first, count; leaf_range<BVH>(sc, tv, &first, &count);
   const uint32_t i = tv.lcur & 0xFFu; bool have = (tv.lcur & LC_HAVE) != 0;
   const uint32_t idx = shade ? (uint32_t)tv.best_id : first + i;
+  WPT_CHECK(idx < sc.num_shapes && (shade || i < count));
   const float4* p = reinterpret_cast<const float4*>(sc.shapes + idx);
   const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
   float t; F3 n = f3(0, 0, 0); bool ent = true;

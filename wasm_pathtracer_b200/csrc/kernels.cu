@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           else finish = true;
         }
         if (finish) {   // RenderTarget::write, render_target.rs:55-58
-          if (ZONES && (slot_id >> 31)) P.seg_buf[(slot_id & 0x7FFFFFFFu) - (s_end - s)] = make_float4(ps.color.x, ps.color.y, ps.color.z, 0.0f);
+          if (ZONES && (slot_id >> 31)) { WPT_CHECK((slot_id & 0x7FFFFFFFu) - (s_end - s) < P.seg_buf_n); P.seg_buf[(slot_id & 0x7FFFFFFFu) - (s_end - s)] = make_float4(ps.color.x, ps.color.y, ps.color.z, 0.0f); }
           else acc_rgb = acc_rgb + ps.color;
           s += 1; what = ST_GEN;
         }
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           what = ST_EXTEND; start = true;
         } else {
           if (ZONES && (slot_id >> 31)) { }
-          else if (ZONES ? P.seg_buf != nullptr : (P.nseg > 1 || P.seg_list)) P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f);
+          else if (ZONES ? P.seg_buf != nullptr : (P.nseg > 1 || P.seg_list)) { WPT_CHECK(slot_id < P.seg_buf_n); P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f); }
           else {   // the only segment of its pixel: add it here
             float4 a = P.accum[pix];
             P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));

@@ -54,6 +54,7 @@ struct MegaParams {
   uint32_t uniform_spp, nslots;       // nslots = pixel slots x nseg
   uint32_t nseg, seg_len;             // contract B10: a pixel's samples of this launch are cut into nseg segments of seg_len
   float4* seg_buf;                    // nseg > 1: segment sums [pixel slot * nseg + j], combined in order by launch_combine_segments
+  uint32_t seg_buf_n;                 // entries of seg_buf (checked build: WPT_CHECK on every store)
   const uint32_t* seg_list;           // strategy rounds: slot -> (pixel slot << 3 | segment); then nslots comes from nslots_dev and seg_buf is indexed by slot
   const uint32_t* nslots_dev;
   uint32_t list_len;                  // strategy rounds cut into short slots of list_len samples (list entries pixel slot << 6 | slot, one colour per sample in seg_buf[slot * list_len ..]); 0 = segments of seg_len

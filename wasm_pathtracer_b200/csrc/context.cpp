@@ -473,7 +473,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
   static const int env_ti = std::getenv("WPT_MEGA_TINNER") ? std::atoi(std::getenv("WPT_MEGA_TINNER")) : 2;
   static const int env_reps = std::getenv("WPT_MEGA_REPS") ? std::atoi(std::getenv("WPT_MEGA_REPS")) : 4;   // measured: 1 -> 20.0, 2 -> 19.3, 4 -> 18.8, 8 -> 19.5 ms (gpurun_out/sweep10*.log)
   P.t_hi = (uint32_t)(env_hi ? env_hi : 20); P.t_lo = (uint32_t)(env_lo ? env_lo : 10); P.t_inner = (uint32_t)env_ti; P.inner_reps = (uint32_t)std::max(1, env_reps);
-  static const int env_ttor = std::getenv("WPT_MEGA_TTORUS") ? std::atoi(std::getenv("WPT_MEGA_TTORUS")) : 10;   // measured: 4 39.1, 8 36.4, 10 35.8, 12 35.9 ms (museum, 8 blocks / SM)
+  static const int env_ttor = std::getenv("WPT_MEGA_TTORUS") ? std::atoi(std::getenv("WPT_MEGA_TTORUS")) : 12;   // measured: 4 39.1, 8 36.4, 10 35.8, 12 35.9 ms at first; 8 29.8, 10 29.1, 12 28.9, 14 29.1 ms at the end of the round (museum, 8 blocks / SM)
   P.t_torus = (uint32_t)std::max(1, env_ttor);
   static const int env_chunk = std::getenv("WPT_MEGA_CHUNK") ? std::atoi(std::getenv("WPT_MEGA_CHUNK")) : 32;
   P.chunk = (uint32_t)env_chunk;

@@ -489,7 +489,15 @@ WPT_DEV bool shape_trace_full(const DShape* __restrict__ shapes, uint32_t idx, c
   *mat_out = meta >> 8;
   F3 n; float t;
   bool entering = true;   // Hit::is_entering (only the extension's refracting material reads it)
-  if (type == SH_TRIANGLE) {   // triangle.rs:116-157
+  if (PRE && type == SH_TRIANGLE) {   // the traversal's distance (see shape_hit_normal_tri_plane): only the side test is left
+    float4 q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    const float n_dot_d = dot(f3(q1.w, q2.w, q3.x), ray.d);
+    const F3 nn = f3(q3.y, q3.z, q3.w);
+    t = t_pre; n = (n_dot_d > 0.0f) ? -nn : nn; entering = !(n_dot_d > 0.0f);
+  } else if (PRE && type == SH_PLANE) {
+    const F3 nr = xyz(q1);
+    t = t_pre; n = (dot(nr, ray.d) > 0.0f) ? -nr : nr;
+  } else if (type == SH_TRIANGLE) {   // triangle.rs:116-157
     float4 q2 = __ldg(p + 2), q3 = __ldg(p + 3);
     F3 v0 = xyz(q0), v1 = xyz(q1), v2 = xyz(q2);
     F3 nu = f3(q1.w, q2.w, q3.x);

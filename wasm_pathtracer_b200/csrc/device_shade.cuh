@@ -136,6 +136,8 @@ WPT_DEV void photon_sample_inl(const DPhotonTree& t, Rng& rng, F3 v, uint32_t* l
   // 1.0 in place of cum[res + 1] for the last bin — the same subtraction either way, so the test is hoisted out
   const bool last = res + 1 == t.num_lights;
   const size_t L = t.num_lights;
+  // (tried: one 8-byte load per cell when there are two lights, as in the bunny scene — BVH2 + PNEE 24.1 -> 25.2 ms, BVH4 + PNEE
+  //  30.8 -> 32.9 ms: slower, gpurun_out/r2c_ab.log)
   auto bp = [&](uint32_t nd) { const float* c = t.cum + (size_t)nd * L + res; float a = __ldg(c); float hi = last ? 1.0f : __ldg(c + 1); return hi - a; };
   float pdf = 0.0f;   // the reference's order of the eight terms (photon_tree.rs:149-156)
   pdf += bp(n8[0]) * wx * wy * wz;

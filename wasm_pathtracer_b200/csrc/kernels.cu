@@ -340,7 +340,7 @@ WPT_DEV bool trav_begin_const(const MegaParams& P, const Ray& ray, Trav& tv) {
   return true;
 }
 
-template <int BVH, int KIND, int MINB, int RT, bool ZN>
+template <int BVH, int KIND, int MINB, int RT, int ZN>
 __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   const DScene& sc = P.rp.scene;
   uint32_t stack_n[WPT_STACK]; float stack_d[WPT_STACK];
@@ -356,7 +356,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   constexpr bool INV_ONE_SITE = KIND != K_SIMPLE;
   // end zones of the slot queue (run_persistent): only in the variants that gain from them — their code costs the triangles /
   // planes variants 1.5 % (headline) to 6 % (BVH4 + PNEE) even when unused (gpurun_out/r2k_ab.log)
-  constexpr bool ZONES = ZN;   // ZN: always for KIND != K_SIMPLE; for the triangles / planes variants only when a strategy round is cut into short slots (P.list_len)
+  // ZN = 0: segments only; 1: + end zones of render_exact (KIND != K_SIMPLE); 2: + strategy rounds in short slots (P.list_len != 0, any KIND).
+  // Separate instantiations: code that a launch does not use still costs these kernels 1.5 - 6 % (register budget).
+  constexpr bool ZONES = ZN != 0, SHORT_LIST = ZN == 2;
   const unsigned lane = threadIdx.x & 31u;
   int phase = PH_NEED, what = ST_GEN;
   uint32_t pixp = 0, s = 0, s_end = 0;   // pixp = px | py << 16 of the slot's pixel
@@ -407,9 +409,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           uint32_t pslot = idx, j = 0, zlen = 0;
           if (P.seg_list) {   // strategy round: (pixel slot, segment) from the list; with P.list_len (pixel slot, short slot of list_len samples)
             const uint32_t e = P.seg_list[idx];
-            if (ZONES && P.list_len) { pslot = e >> 6; j = e & 63u; zlen = P.list_len; } else { pslot = e >> 3; j = e & 7u; }
+            if (SHORT_LIST) { pslot = e >> 6; j = e & 63u; zlen = P.list_len; } else { pslot = e >> 3; j = e & 7u; }
           }
-          else if (ZONES && idx >= P.zone_start[0]) {   // end zones of the queue: shorter slots (zone_len samples), see run_persistent
+          else if (ZN == 1 && idx >= P.zone_start[0]) {   // end zones of the queue: shorter slots (zone_len samples), see run_persistent
             const int z = idx >= P.zone_start[2] ? 2 : (idx >= P.zone_start[1] ? 1 : 0);
             const uint32_t r = idx - P.zone_start[z], q = r / P.zone_per[z];
             pslot = P.zone_pslot[z] + q; j = r - q * P.zone_per[z]; zlen = P.zone_len[z];
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           s = s0 + b;
           s_end = s0 + e;
           // a zone slot stores every sample's colour on its own (k_combine_segments forms the segment sums): slot_id = flag | index one past its last sample
-          if (ZONES && zlen) slot_id = 0x80000000u | (P.seg_list ? idx * zlen + (e - b) : P.zone_samples + (pslot - P.zone_pslot[0]) * P.uniform_spp + e);   // list: slot idx owns entries idx * len ..
+          if (ZONES && zlen) slot_id = 0x80000000u | (SHORT_LIST ? idx * zlen + (e - b) : P.zone_samples + (pslot - P.zone_pslot[0]) * P.uniform_spp + e);   // list: slot idx owns entries idx * len ..
           acc_rgb = f3(0.0f, 0.0f, 0.0f);
 #ifdef MEGA_INSTR
           i_slot_rays = 0;
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
 // Register budgets (blocks of 128 threads per SM) instantiated per variant: the measured optimum (gpurun_out/sweep8.log,
 // sweep11.log, sweep12.log) — triangles/planes BVH2 8 (64 registers), BVH4 5 and 8, ext 16 (32 registers); the reference-primitives
 // variant (tori, boxes) has 8 / 12 / 16 selectable at run time (WPT_MEGA_MINBG). With -DWPT_TUNING: 4 / 5 / 8 / 12 / 16 for every variant.
-template <int BVH, int KIND, int RT, bool ZN>
+template <int BVH, int KIND, int RT, int ZN>
 static void launch_mega_z(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
   auto grid_for = [&](int b) { int grid = device_sm_count() * b, need = (int)((P.nslots + MEGA_THREADS - 1) / MEGA_THREADS); return (grid > need && !P.nslots_dev) ? need : grid; };
 #ifdef WPT_TUNING
@@ -637,9 +639,9 @@ static void launch_mega_z(const MegaParams& P, int blocks_per_sm, cudaStream_t s
 }
 template <int BVH, int KIND, int RT>
 static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
-  if constexpr (KIND != K_SIMPLE) launch_mega_z<BVH, KIND, RT, true>(P, blocks_per_sm, s);
-  else if (P.list_len) launch_mega_z<BVH, KIND, RT, true>(P, blocks_per_sm, s);
-  else launch_mega_z<BVH, KIND, RT, false>(P, blocks_per_sm, s);
+  if (P.list_len) launch_mega_z<BVH, KIND, RT, 2>(P, blocks_per_sm, s);
+  else if constexpr (KIND != K_SIMPLE) launch_mega_z<BVH, KIND, RT, 1>(P, blocks_per_sm, s);
+  else launch_mega_z<BVH, KIND, RT, 0>(P, blocks_per_sm, s);
 }
 template <int BVH, int KIND>
 static void launch_mega_rt(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {

@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   // planes variants 1.5 % (headline) to 6 % (BVH4 + PNEE) even when unused (gpurun_out/r2k_ab.log)
   // ZN = 0: segments only; 1: + end zones of render_exact (KIND != K_SIMPLE); 2: + strategy rounds in short slots (P.list_len != 0, any KIND).
   // Separate instantiations: code that a launch does not use still costs these kernels 1.5 - 6 % (register budget).
-  constexpr bool ZONES = ZN != 0, SHORT_LIST = ZN == 2;
+  // 3: a strategy round in segments (the list, no zones). 0 / 1 are render_exact launches (no list), 2 / 3 strategy rounds (list).
+  constexpr bool ZONES = ZN == 1 || ZN == 2, SHORT_LIST = ZN == 2, LIST = ZN >= 2;
   const unsigned lane = threadIdx.x & 31u;
   int phase = PH_NEED, what = ST_GEN;
   uint32_t pixp = 0, s = 0, s_end = 0;   // pixp = px | py << 16 of the slot's pixel
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   uint32_t i_path_rays = 0, i_slot_rays = 0, i_max_path = 0, i_max_slot = 0;   // rays of the lane's current path / slot, and their maxima
 #endif
 
-  const uint32_t nslots = P.nslots_dev ? *P.nslots_dev : P.nslots;
+  const uint32_t nslots = LIST ? *P.nslots_dev : P.nslots;
   for (;;) {
     // ---- pixel fetch: the warp owns a chunk of consecutive slots (= neighbouring tiles) and
     // hands them to its lanes; one atomic per chunk
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
         if (ok) {
           // contract B10: the samples of this launch are summed per segment from +0; a slot is one segment
           uint32_t pslot = idx, j = 0, zlen = 0;
-          if (P.seg_list) {   // strategy round: (pixel slot, segment) from the list; with P.list_len (pixel slot, short slot of list_len samples)
+          if (LIST) {   // strategy round: (pixel slot, segment) from the list; with P.list_len (pixel slot, short slot of list_len samples)
             const uint32_t e = P.seg_list[idx];
             if (SHORT_LIST) { pslot = e >> 6; j = e & 63u; zlen = P.list_len; } else { pslot = e >> 3; j = e & 7u; }
           }
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           WPT_CHECK(pix < P.rp.W * P.rp.H);
           const uint32_t py = pix / P.rp.W;   // once per slot, not per sample
           pixp = (pix - py * P.rp.W) | (py << 16);
-          uint32_t spp = P.spp_per_slot ? P.spp_per_slot[pslot] : P.uniform_spp;
+          uint32_t spp = LIST ? P.spp_per_slot[pslot] : P.uniform_spp;
           uint32_t s0 = __float_as_uint(P.accum[pix].w);   // samples accumulated so far = next sample index
           const uint32_t len = zlen ? zlen : P.seg_len, b = min(j * len, spp), e = min(b + len, spp);
           s = s0 + b;
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           what = ST_EXTEND; start = true;
         } else {
           if (ZONES && (slot_id >> 31)) { }
-          else if (ZONES ? P.seg_buf != nullptr : (P.nseg > 1 || P.seg_list)) { WPT_CHECK(slot_id < P.seg_buf_n); P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f); }
+          else if (ZONES ? P.seg_buf != nullptr : (LIST || P.nseg > 1)) { WPT_CHECK(slot_id < P.seg_buf_n); P.seg_buf[slot_id] = make_float4(acc_rgb.x, acc_rgb.y, acc_rgb.z, 0.0f); }
           else {   // the only segment of its pixel: add it here
             float4 a = P.accum[pix];
             P.accum[pix] = make_float4(a.x + acc_rgb.x, a.y + acc_rgb.y, a.z + acc_rgb.z, __uint_as_float(s));
@@ -639,7 +640,7 @@ static void launch_mega_z(const MegaParams& P, int blocks_per_sm, cudaStream_t s
 }
 template <int BVH, int KIND, int RT>
 static void launch_mega_t(const MegaParams& P, int blocks_per_sm, cudaStream_t s) {
-  if (P.list_len) launch_mega_z<BVH, KIND, RT, 2>(P, blocks_per_sm, s);
+  if (P.seg_list) { if (P.list_len) launch_mega_z<BVH, KIND, RT, 2>(P, blocks_per_sm, s); else launch_mega_z<BVH, KIND, RT, 3>(P, blocks_per_sm, s); }
   else if constexpr (KIND != K_SIMPLE) launch_mega_z<BVH, KIND, RT, 1>(P, blocks_per_sm, s);
   else launch_mega_z<BVH, KIND, RT, 0>(P, blocks_per_sm, s);
 }

@@ -397,6 +397,7 @@ void Context::run_persistent(uint32_t render_type, const uint32_t* d_spp_per_slo
     const uint32_t lanes = (uint32_t)device_sm_count() * 8u * 128u;
     uint32_t list_len = env_list >= 0 ? (uint32_t)std::min(env_list, 64) : (slots < 4u * lanes ? 2u : 0u);
     if (cfg.engine != 0) list_len = 0;
+    if (list_len && (uint64_t)slots * ((64u + list_len - 1u) / list_len) * list_len >= (1ull << 31)) list_len = 0;   // per-sample indices carry a flag in bit 31
     const uint32_t per_px = list_len ? (64u + list_len - 1u) / list_len : 8u;   // slots a pixel can have (a round holds at most 64 samples per pixel)
     d_seg_cnt.alloc((size_t)slots + 1); d_seg_off.alloc((size_t)slots + 1); d_seg_list.alloc((size_t)slots * per_px);
     size_t sb = seg_scan_bytes(slots);

@@ -149,3 +149,63 @@ def test_stand_in_mesh_is_deterministic(built):
     assert p.shape == (642, 3) and f.shape == (1280, 3)
     text = open(os.path.join(ROOT, "assets", "_gen", "standin_3.obj")).read()
     assert hashlib.sha256(text.encode()).hexdigest() == open(os.path.join(ROOT, "tests", "golden", "standin_3.sha256")).read().strip()
+
+
+def test_predicated_sort_network_is_the_branchy_one():
+    """device_core.cuh keeps two forms of `sort_small` (scene.rs:346-388): the reference's branches and, behind -DWPT_SORT_PREDICATED,
+    the same compare-and-swap network with predicated swaps. Both written out here in Python, all inputs over a value set with
+    ties, infinities and NaN, n = 0..4: same permutation, so the macro changes no visit order."""
+    import itertools
+    import math
+
+    def branchy(d, n):
+        ids, d = [0, 1, 2, 3], list(d)
+
+        def sw(i, j):
+            ids[i], ids[j] = ids[j], ids[i]; d[i], d[j] = d[j], d[i]
+        if n == 2:
+            if d[1] < d[0]: sw(0, 1)
+        elif n == 3:
+            if d[1] < d[0]: sw(0, 1)
+            if d[2] < d[1]: sw(1, 2)
+            if d[1] < d[0]: sw(0, 1)
+        elif n == 4:
+            if d[1] < d[0]: sw(0, 1)
+            if d[3] < d[2]: sw(2, 3)
+            if d[0] < d[2]:
+                if d[2] < d[1]:
+                    sw(1, 2)
+                    if d[3] < d[2]: sw(2, 3)
+            else:
+                sw(0, 2); sw(1, 2)
+                if d[3] < d[1]:
+                    sw(1, 3); sw(2, 3)
+                elif d[3] < d[2]:
+                    sw(2, 3)
+        return ids
+
+    def predicated(d, n):
+        ids, d = [0, 1, 2, 3], list(d)
+
+        def cs(i, j, c):
+            if c:
+                ids[i], ids[j] = ids[j], ids[i]; d[i], d[j] = d[j], d[i]
+        n3, n4 = n == 3, n == 4
+        cs(0, 1, n >= 2 and d[1] < d[0])
+        cs(1, 2, n3 and d[2] < d[1])
+        cs(0, 1, n3 and d[1] < d[0])
+        cs(2, 3, n4 and d[3] < d[2])
+        a, b = n4 and d[0] < d[2], n4 and not (d[0] < d[2])
+        a1 = a and d[2] < d[1]
+        cs(1, 2, a1)
+        cs(2, 3, a1 and d[3] < d[2])
+        cs(0, 2, b); cs(1, 2, b)
+        b1 = b and d[3] < d[1]
+        b2 = b and not b1 and d[3] < d[2]
+        cs(1, 3, b1); cs(2, 3, b1 or b2)
+        return ids
+
+    vals = [0.0, 0.5, 1.0, 2.0, -math.inf, math.inf, math.nan]
+    for n in range(5):
+        for d in itertools.product(vals, repeat=4):
+            assert branchy(d, n) == predicated(d, n), (n, d)

@@ -367,7 +367,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
   Ray ray = make_ray(f3(0, 0, 0), f3(1, 1, 1));
   auto set_ray = [&](F3 o, F3 d) { if (INV_ONE_SITE) { ray.o = o; ray.d = d; } else ray = make_ray(o, d); };
   Trav tv; tv.lf = tv.cnt = 0; tv.sp = 0; tv.bound = 0; tv.best_id = -1; tv.inf_t = 0; tv.inf_id = -1; tv.visits = tv.prims = 0; tv.lcur = 0u;
+  // The state a lane keeps across its shadow ray (bounce origin / direction, the light's contribution): nine floats that are written
+  // once and read once per shadow ray. The BVH2 triangles + planes variants keep them in shared memory ([k][thread]: no bank conflicts) —
+  // spills 242 -> 178 B per thread, headline 16.73 -> 16.59 ms, BVH2 + PNEE 24.2 -> 23.9 ms; BVH4 + PNEE unchanged and the museum variant
+  // slower (29.1 -> 31.1 ms: its L1 shrinks by the 37 KB), so those keep registers (gpurun_out/r2e_smem.log).
+  constexpr bool EXT_SMEM = KIND == K_SIMPLE && BVH == 2;
+  __shared__ float sh_ext[EXT_SMEM ? 9 * MEGA_THREADS : 1];
   F3 ext_o = f3(0, 0, 0), ext_d = f3(0, 0, 0), contrib = f3(0, 0, 0);
+  auto ext_put = [&](F3 o, F3 d, F3 c) {
+    if (EXT_SMEM) {
+      float* q = sh_ext + threadIdx.x;
+      q[0] = o.x; q[MEGA_THREADS] = o.y; q[2 * MEGA_THREADS] = o.z; q[3 * MEGA_THREADS] = d.x; q[4 * MEGA_THREADS] = d.y; q[5 * MEGA_THREADS] = d.z;
+      q[6 * MEGA_THREADS] = c.x; q[7 * MEGA_THREADS] = c.y; q[8 * MEGA_THREADS] = c.z;
+    } else { ext_o = o; ext_d = d; contrib = c; }
+  };
+  auto ext_get = [&](int k) {
+    if (EXT_SMEM) { const float* q = sh_ext + threadIdx.x + 3 * k * MEGA_THREADS; return f3(q[0], q[MEGA_THREADS], q[2 * MEGA_THREADS]); }
+    return k == 0 ? ext_o : (k == 1 ? ext_d : contrib);
+  };
   float sh_len = 0.0f; int sh_light = -1; bool alive_after_shadow = false;
   // ray / visit / primitive-test / path counters: warp sums (ballot + redux.sync) in uniform registers, one set of global
   // atomics per warp at the end — no per-ray atomics
@@ -530,8 +547,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
       if (cons) {
         if (what == ST_SHADOW) {   // Scene::shadow_ray, scene.rs:114-132
           bool occluded = g.id >= 0 && g.t < sh_len && g.id != sh_light;
-          if (!occluded) ps.color = ps.color + contrib;
-          if (alive_after_shadow) { set_ray(ext_o, ext_d); what = ST_EXTEND; start = true; }
+          if (!occluded) ps.color = ps.color + ext_get(2);
+          if (alive_after_shadow) { set_ray(ext_get(0), ext_get(1)); what = ST_EXTEND; start = true; }
           else finish = true;
         } else {
           ShadeOut so;
@@ -539,7 +556,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, MINB) k_mega(MegaParams P) {
           else shade_hit<KIND, RT>(P.rp, ray, g.id, g.t, ps, so);
           if (so.finished) finish = true;
           else if (so.shadow) {
-            ext_o = so.next_o; ext_d = so.next_d; contrib = so.contrib; sh_len = so.sh_len; sh_light = so.sh_light;
+            ext_put(so.next_o, so.next_d, so.contrib); sh_len = so.sh_len; sh_light = so.sh_light;
             alive_after_shadow = so.survive;
             set_ray(so.sh_o, so.sh_d); what = ST_SHADOW; start = true;
           } else if (so.survive) { set_ray(so.next_o, so.next_d); what = ST_EXTEND; start = true; }
